@@ -1,0 +1,589 @@
+"""CPU oracle for the caption decode hot path (TEST INFRASTRUCTURE, not product code).
+
+A numpy fp32 restatement of the reference's decode loop -- the ``beam_search_sample`` /
+``sample`` / ``sample_rl`` methods of ``Models/{BUTD,NIC,AoA}_Model.py`` and the id->word
+driver in ``Engine.eval_captions_json_generation`` -- of zyj0021200/simpleImageCaptionZoo.
+Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference``
+legs of ``bench.py`` may import this module; the product path (``simpleimagecaptionzoo_b200``)
+never does and has no CPU fallback.
+
+PARITY PINNING.  The reference has no tests, fixtures or golden vectors of its own for this
+path, so by the reference's standards parity is "unpinned".  The
+oracle is instead pinned against outputs of the reference's own Python code, imported from
+/root/reference in the build container with the shims listed in ``tests/golden/make_golden.py``
+(floor division on the parent index, parametrised step limit); the resulting vectors are
+committed under ``tests/golden/`` and ``tests/test_oracle_golden.py`` checks this file
+against every one of them.
+
+Every function cites the reference lines it restates.  Arithmetic is fp32 throughout, like
+the reference.  ``operand_round`` optionally emulates the operand rounding of the tensor-core
+math modes of the CUDA path (tf32 / bf16 / bf16x3 splits with fp32 accumulation) so that the
+tests can state the expected agreement of each mode; ``None`` is the plain fp32 oracle.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+f32 = np.float32
+PAD, STA, END, UNK = 0, 1, 2, 3  # PreProcess/Build_caption_vocab.py:37-40
+
+
+# ---------------------------------------------------------------------------------------------------
+# elementary pieces
+# ---------------------------------------------------------------------------------------------------
+
+def fold_weight_norm(g: np.ndarray, v: np.ndarray) -> np.ndarray:
+    """Effective weight of a legacy ``weight_norm`` Linear: w = g * v / ||v||_2 per output row
+    (torch.nn.utils.weight_norm, dim=0; used at BUTD_Model.py:43-45,84, NIC_Model.py:49,
+    AoA_Model.py:212).  The reference re-materialises this on every call."""
+    v64 = v.astype(np.float64)
+    norm = np.sqrt((v64 * v64).sum(axis=1, keepdims=True))
+    return (v64 * (g.astype(np.float64) / norm)).astype(f32)
+
+
+def sigmoid(x):
+    return (1.0 / (1.0 + np.exp(-x, dtype=f32))).astype(f32)
+
+
+def log_softmax(x: np.ndarray) -> np.ndarray:
+    """Fun.log_softmax(scores, dim=1) (BUTD_Model.py:271)."""
+    m = x.max(axis=-1, keepdims=True)
+    z = x - m
+    return (z - np.log(np.exp(z, dtype=f32).sum(axis=-1, keepdims=True, dtype=f32), dtype=f32)).astype(f32)
+
+
+def softmax(x: np.ndarray) -> np.ndarray:
+    m = x.max(axis=-1, keepdims=True)
+    e = np.exp(x - m, dtype=f32)
+    return (e / e.sum(axis=-1, keepdims=True, dtype=f32)).astype(f32)
+
+
+def round_tf32(x: np.ndarray) -> np.ndarray:
+    """fp32 -> tf32 (10-bit mantissa), round to nearest, ties away (PTX cvt.rna.tf32.f32)."""
+    b = np.ascontiguousarray(x, dtype=f32).view(np.uint32)
+    return ((b + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(f32)
+
+
+def round_bf16(x: np.ndarray) -> np.ndarray:
+    """fp32 -> bf16 -> fp32, round to nearest even (PTX cvt.rn.bf16.f32)."""
+    b = np.ascontiguousarray(x, dtype=f32).view(np.uint32)
+    r = b + np.uint32(0x7FFF) + ((b >> np.uint32(16)) & np.uint32(1))
+    return (r & np.uint32(0xFFFF0000)).view(f32)
+
+
+class _Mat:
+    """x @ W^T with optional emulation of tensor-core operand rounding (fp32 accumulate)."""
+
+    def __init__(self, mode):
+        assert mode in (None, "fp32", "tf32", "bf16", "bf16x3")
+        self.mode = None if mode == "fp32" else mode
+        self._cache = {}
+
+    def _w(self, W):
+        key = id(W)
+        if key not in self._cache:
+            if self.mode == "tf32":
+                v = (round_tf32(W),)
+            elif self.mode == "bf16":
+                v = (round_bf16(W),)
+            elif self.mode == "bf16x3":
+                hi = round_bf16(W)
+                v = (hi, round_bf16(W - hi))
+            else:
+                v = (W,)
+            self._cache[key] = (W, tuple(np.ascontiguousarray(a.T) for a in v))
+        return self._cache[key][1]
+
+    def __call__(self, x, W):
+        shp = x.shape[:-1]
+        x2 = np.ascontiguousarray(x, dtype=f32).reshape(-1, x.shape[-1])
+        w = self._w(W)
+        if self.mode is None:
+            y = x2 @ w[0]
+        elif self.mode == "tf32":
+            y = round_tf32(x2) @ w[0]
+        elif self.mode == "bf16":
+            y = round_bf16(x2) @ w[0]
+        else:
+            xh = round_bf16(x2)
+            xl = round_bf16(x2 - xh)
+            y = xh @ w[0] + (xh @ w[1] + xl @ w[0])
+        return y.astype(f32).reshape(*shp, -1)
+
+
+def lstm_cell(mm, x, h, c, W_ih, W_hh, b_ih, b_hh):
+    """torch.nn.LSTMCell forward, gate order i,f,g,o (BUTD_Model.py:82-83,265,268;
+    NIC_Model.py:48,173; AoA_Model.py:204,440)."""
+    gates = mm(x, W_ih) + b_ih + mm(h, W_hh) + b_hh
+    H = h.shape[-1]
+    i, f, g, o = (gates[..., j * H:(j + 1) * H] for j in range(4))
+    c2 = sigmoid(f) * c + sigmoid(i) * np.tanh(g, dtype=f32)
+    h2 = sigmoid(o) * np.tanh(c2, dtype=f32)
+    return h2.astype(f32), c2.astype(f32)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the three decoders.  State tensors are (B, k, .): image-major, k beam/sample rows per image.
+# ---------------------------------------------------------------------------------------------------
+
+class ButdOracle:
+    """Models/BUTD_Model.py DecoderRNN (:64-95) + SoftAttention (:40-62)."""
+    arch = "BUTD"
+
+    def __init__(self, sd: dict, operand_round=None):
+        p = "decoder."
+        self.mm = _Mat(operand_round)
+        self.W_enc = fold_weight_norm(sd[p + "atten.enc_att.weight_g"], sd[p + "atten.enc_att.weight_v"])
+        self.b_enc = sd[p + "atten.enc_att.bias"]
+        self.W_dec = fold_weight_norm(sd[p + "atten.dec_att.weight_g"], sd[p + "atten.dec_att.weight_v"])
+        self.b_dec = sd[p + "atten.dec_att.bias"]
+        self.w_aff = fold_weight_norm(sd[p + "atten.affine.weight_g"], sd[p + "atten.affine.weight_v"])[0]
+        self.b_aff = sd[p + "atten.affine.bias"][0]
+        self.embed = sd[p + "embed.0.weight"]
+        self.td = tuple(sd[p + "TD_atten." + n] for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"))
+        self.lm = tuple(sd[p + "language_model." + n] for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"))
+        self.W_pred = fold_weight_norm(sd[p + "predict.weight_g"], sd[p + "predict.weight_v"])
+        self.b_pred = sd[p + "predict.bias"]
+        self.H = self.td[1].shape[1]
+        self.V = self.W_pred.shape[0]
+
+    def prepare(self, feats, mask=None):
+        """Step-invariant terms: enc_att(feats) (BUTD_Model.py:57, recomputed every step by the
+        reference) and the mean feature (:251)."""
+        feats = np.ascontiguousarray(feats, dtype=f32)
+        self.feats = feats
+        self.enc_ctx = (self.mm(feats, self.W_enc) + self.b_enc).astype(f32)
+        self.mean = feats.mean(axis=1, dtype=f32).astype(f32)
+        self.B, self.R = feats.shape[:2]
+
+    def init_state(self, k):
+        z = lambda: np.zeros((self.B, k, self.H), f32)  # BUTD_Model.py:92-95,261-262
+        return dict(h1=z(), c1=z(), h2=z(), c2=z())
+
+    def select(self, sl):
+        """Restrict the prepared per-image tensors to images ``sl`` (view)."""
+        o = object.__new__(type(self))
+        o.__dict__.update(self.__dict__)
+        o.feats, o.enc_ctx, o.mean = self.feats[sl], self.enc_ctx[sl], self.mean[sl]
+        o.B = o.feats.shape[0]
+        return o
+
+    def step(self, tok, st):
+        """One decode step (BUTD_Model.py:264-270 / :172-182 / :210-220)."""
+        B, k = tok.shape
+        emb = np.maximum(self.embed[tok], 0)  # Embedding -> ReLU (:77-81); dropout = id in eval
+        mean = np.broadcast_to(self.mean[:, None, :], (B, k, self.mean.shape[-1]))
+        x = np.concatenate([st["h2"], mean, emb], axis=-1)
+        h1, c1 = lstm_cell(self.mm, x, st["h1"], st["c1"], *self.td)
+        dec_ctx = self.mm(h1, self.W_dec) + self.b_dec  # (:58)
+        act = np.maximum(self.enc_ctx[:, None, :, :] + dec_ctx[:, :, None, :], 0)  # (:59) ReLU
+        e = (act @ self.w_aff + self.b_aff).astype(f32)  # (B,k,R)
+        alpha = softmax(e)  # (:60)
+        ctx = np.einsum("bkr,brd->bkd", alpha, self.feats, dtype=f32).astype(f32)  # (:61)
+        h2, c2 = lstm_cell(self.mm, np.concatenate([ctx, h1], axis=-1), st["h2"], st["c2"], *self.lm)
+        logits = (self.mm(h2, self.W_pred) + self.b_pred).astype(f32)  # (:270)
+        return logits, dict(h1=h1, c1=c1, h2=h2, c2=c2), alpha
+
+
+class NicOracle:
+    """Models/NIC_Model.py DecoderRNN (:39-56)."""
+    arch = "NIC"
+
+    def __init__(self, sd: dict, operand_round=None):
+        p = "decoder."
+        self.mm = _Mat(operand_round)
+        self.embed = sd[p + "embed.weight"]
+        self.lstm = tuple(sd[p + "lstm." + n] for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"))
+        self.W_pred = fold_weight_norm(sd[p + "predict.weight_g"], sd[p + "predict.weight_v"])
+        self.b_pred = sd[p + "predict.bias"]
+        self.H = self.lstm[1].shape[1]
+        self.V = self.W_pred.shape[0]
+
+    def prepare(self, feats, mask=None):
+        """init_hidden_state: (h,c) = lstm(image_embedding, (0,0)) (NIC_Model.py:52-56)."""
+        feats = np.ascontiguousarray(feats, dtype=f32)
+        self.B = feats.shape[0]
+        z = np.zeros((self.B, self.H), f32)
+        self.h0, self.c0 = lstm_cell(self.mm, feats, z, z, *self.lstm)
+
+    def select(self, sl):
+        o = object.__new__(type(self))
+        o.__dict__.update(self.__dict__)
+        o.h0, o.c0 = self.h0[sl], self.c0[sl]
+        o.B = o.h0.shape[0]
+        return o
+
+    def init_state(self, k):
+        rep = lambda a: np.repeat(a[:, None, :], k, axis=1).copy()  # features.expand(k,.) :164
+        return dict(h=rep(self.h0), c=rep(self.c0))
+
+    def step(self, tok, st):
+        emb = self.embed[tok]  # plain nn.Embedding, no ReLU (NIC_Model.py:47,172)
+        h, c = lstm_cell(self.mm, emb, st["h"], st["c"], *self.lstm)  # :173
+        logits = (self.mm(h, self.W_pred) + self.b_pred).astype(f32)  # :174
+        return logits, dict(h=h, c=c), None
+
+
+class AoaOracle:
+    """Models/AoA_Model.py AoA_Decoder (:197-227) + AoABlock (:71-120) + LayerNorm (:14-25)."""
+    arch = "AOA"
+
+    def __init__(self, sd: dict, num_heads=8, operand_round=None):
+        p = "decoder."
+        self.mm = _Mat(operand_round)
+        self.nh = num_heads
+        self.lstm = tuple(sd[p + "lstm." + n] for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"))
+        g = lambda n: (sd[p + "aoa_block." + n + ".weight"], sd[p + "aoa_block." + n + ".bias"])
+        self.WQ, self.bQ = g("linear_Q")
+        self.WK, self.bK = g("linear_K")
+        self.WV, self.bV = g("linear_V")
+        self.WA, self.bA = g("aoa_module.0")
+        self.embed = sd[p + "embed.0.weight"]
+        self.gain, self.bias = sd[p + "h_norm.gain"], sd[p + "h_norm.bias"]
+        self.W_pred = fold_weight_norm(sd[p + "predict.weight_g"], sd[p + "predict.weight_v"])
+        self.b_pred = sd[p + "predict.bias"]
+        self.H = self.lstm[1].shape[1]
+        self.V = self.W_pred.shape[0]
+
+    def prepare(self, feats, mask=None):
+        """feats: refined (B,R,H); mask: (B,R) float or None.  Mean / masked mean
+        (AoA_Model.py:422-425) and the step-invariant K,V projections (:114-115)."""
+        feats = np.ascontiguousarray(feats, dtype=f32)
+        self.B, self.R = feats.shape[:2]
+        self.mask = None if mask is None else np.ascontiguousarray(mask, dtype=f32)
+        if mask is None:
+            self.mean = feats.mean(axis=1, dtype=f32).astype(f32)
+        else:
+            m = self.mask[:, :, None]
+            self.mean = ((feats * m).sum(1, dtype=f32) / m.sum(1, dtype=f32)).astype(f32)
+        d = self.H // self.nh
+        self.Kp = (self.mm(feats, self.WK) + self.bK).astype(f32).reshape(self.B, self.R, self.nh, d)
+        self.Vp = (self.mm(feats, self.WV) + self.bV).astype(f32).reshape(self.B, self.R, self.nh, d)
+
+    def select(self, sl):
+        o = object.__new__(type(self))
+        o.__dict__.update(self.__dict__)
+        o.mean, o.Kp, o.Vp = self.mean[sl], self.Kp[sl], self.Vp[sl]
+        o.mask = None if self.mask is None else self.mask[sl]
+        o.B = o.mean.shape[0]
+        return o
+
+    def init_state(self, k):
+        z = lambda: np.zeros((self.B, k, self.H), f32)  # AoA_Model.py:223-227
+        return dict(h=z(), c=z(), ctx=z())
+
+    def step(self, tok, st):
+        B, k = tok.shape
+        H, nh = self.H, self.nh
+        d = H // nh
+        emb = np.maximum(self.embed[tok], 0)  # :206-210
+        x = np.concatenate([emb, self.mean[:, None, :] + st["ctx"]], axis=-1)  # :441
+        h, c = lstm_cell(self.mm, x, st["h"], st["c"], *self.lstm)
+        mu = h.mean(-1, keepdims=True, dtype=f32)  # LayerNorm :22-25 (unbiased std, eps on std)
+        sd_ = h.std(-1, keepdims=True, ddof=1, dtype=f32)
+        q = (self.gain * (h - mu) / (sd_ + f32(1e-6)) + self.bias).astype(f32)
+        Q = (self.mm(q, self.WQ) + self.bQ).astype(f32).reshape(B, k, nh, d)  # :113
+        s = (np.einsum("bkhd,brhd->bkhr", Q, self.Kp, dtype=f32) / f32(math.sqrt(d))).astype(f32)  # :62
+        if self.mask is not None:
+            s = np.where(self.mask[:, None, None, :] == 0, f32(-1e9), s)  # :63-64
+        p = softmax(s)  # :65
+        xatt = np.einsum("bkhr,brhd->bkhd", p, self.Vp, dtype=f32).astype(f32).reshape(B, k, H)  # :68,117
+        a = (self.mm(np.concatenate([xatt, q], axis=-1), self.WA) + self.bA).astype(f32)  # :118
+        ctx = (a[..., :H] * sigmoid(a[..., H:])).astype(f32)  # nn.GLU
+        logits = (self.mm(ctx, self.W_pred) + self.b_pred).astype(f32)  # :455
+        return logits, dict(h=h, c=c, ctx=ctx), p.mean(axis=2, dtype=f32)  # alphas = head mean :119
+
+
+def make_decoder(arch, sd, operand_round=None, num_heads=8):
+    arch = arch.upper()
+    if arch == "BUTD":
+        return ButdOracle(sd, operand_round)
+    if arch == "NIC":
+        return NicOracle(sd, operand_round)
+    if arch == "AOA":
+        return AoaOracle(sd, num_heads, operand_round)
+    raise ValueError(arch)
+
+
+# ---------------------------------------------------------------------------------------------------
+# beam search
+# ---------------------------------------------------------------------------------------------------
+
+def _topk_sorted(flat: np.ndarray, k: int):
+    """values, indices of the k largest entries, sorted descending (tensor.topk(k,0,True,True))."""
+    n = flat.shape[0]
+    k = min(k, n)
+    if n > 4 * k:
+        part = np.argpartition(-flat, k - 1)[:k]
+    else:
+        part = np.arange(n)
+    order = part[np.argsort(-flat[part], kind="stable")][:k]
+    return flat[order], order
+
+
+@dataclass
+class BeamResult:
+    tokens: np.ndarray          # (B, 1+max_seq) int32: <sta>, words, <end> if completed, then <pad>=0
+    lengths: np.ndarray         # (B,) int32: number of valid entries in tokens (incl. <sta>, <end>)
+    scores: np.ndarray          # (B,) fp32: sum of log-probs of the emitted words (no length norm)
+    completed: np.ndarray       # (B,) bool: a hypothesis ended with <end>
+    min_gap: np.ndarray = field(default=None)  # (B, max_seq) fp32: per step, min adjacent gap in the
+    #                                            sorted top-(k+1) candidate list (inf when unused)
+
+
+def beam_search_image(dec, beam: int, max_seq: int):
+    """Literal restatement of ``beam_search_sample`` for ONE prepared image (dec.B == 1):
+    BUTD_Model.py:236-318 == NIC_Model.py:153-212 == AoA_Model.py:403-502, with the two shims
+    of SURVEY 8c (``//`` for the parent index, ``max_step_limit`` = ``max_seq``).
+    Returns (seq list incl. <sta>, score, completed, per-step min gap list)."""
+    assert dec.B == 1
+    V = dec.V
+    k = beam
+    prev_words = np.full((1, k), STA, np.int64)  # :248
+    seqs = [[STA] for _ in range(k)]  # :249
+    top_scores = np.zeros((k,), f32)  # :250
+    st = dec.init_state(k)  # :261-262
+    complete_seqs, complete_scores, gaps = [], [], []
+    step = 1
+    while step <= max_seq:  # :263
+        logits, st, _ = dec.step(prev_words, st)
+        scores = log_softmax(logits[0])  # :271
+        scores = top_scores[:, None] + scores  # :272
+        flat = scores[0] if step == 1 else scores.reshape(-1)  # :273-276
+        vals, idx = _topk_sorted(flat, k + 1)
+        gaps.append(float(np.min(vals[:-1] - vals[1:])) if len(vals) > 1 else float("inf"))
+        vals, idx = vals[:k], idx[:k]
+        prev_inds = idx // V  # :277 (floor division shim)
+        next_inds = idx % V  # :278
+        seqs = [seqs[p] + [int(w)] for p, w in zip(prev_inds, next_inds)]  # :279
+        incomplete = [i for i, w in enumerate(next_inds) if w != END]  # :282
+        complete = [i for i in range(len(next_inds)) if i not in incomplete]  # :283
+        for i in complete:  # :285-288
+            complete_seqs.append(seqs[i])
+            complete_scores.append(float(vals[i]))
+        k -= len(complete)  # :290
+        if k == 0:
+            break
+        seqs = [seqs[i] for i in incomplete]  # :294
+        sel = prev_inds[incomplete]
+        st = {n: a[:, sel] for n, a in st.items()}  # :297-300 (AoA also ctx :482)
+        top_scores = vals[incomplete].astype(f32)  # :301
+        prev_words = next_inds[incomplete][None, :].astype(np.int64)  # :302
+        step += 1
+    if complete_seqs:  # :306-311 -- best COMPLETED hypothesis, first max, even if a live one is better
+        i = complete_scores.index(max(complete_scores))
+        return complete_seqs[i], complete_scores[i], True, gaps
+    i = int(np.argmax(top_scores))  # :313-314
+    return seqs[i], float(top_scores[i]), False, gaps
+
+
+def beam_search_reference_form(dec, beam: int, max_seq: int) -> BeamResult:
+    """The reference's own driver shape: one image per call (Utils.py:72-73 forces batch 1)."""
+    B = dec.B
+    toks = np.zeros((B, 1 + max_seq), np.int32)
+    lens = np.zeros(B, np.int32)
+    scs = np.zeros(B, f32)
+    comp = np.zeros(B, bool)
+    gaps = np.full((B, max_seq), np.inf, f32)
+    for b in range(B):
+        seq, sc, c, g = beam_search_image(dec.select(slice(b, b + 1)), beam, max_seq)
+        toks[b, :len(seq)] = seq
+        lens[b], scs[b], comp[b] = len(seq), sc, c
+        gaps[b, :len(g)] = g
+    return BeamResult(toks, lens, scs, comp, gaps)
+
+
+def beam_search_batched(dec, beam: int, max_seq: int) -> BeamResult:
+    """Fixed-slot batched form of the same algorithm (the shape the CUDA path uses; SURVEY 8a
+    "Fixed-shape GPU form"): K slots per image with a live count, dead slots carry -inf, top-K
+    then honour only the first n_live entries, running best-completed with strict '>' (== first
+    max), stable compaction of survivors."""
+    B, V, K, T = dec.B, dec.V, beam, max_seq
+    st = dec.init_state(K)
+    tok = np.full((B, K), STA, np.int64)
+    cum = np.zeros((B, K), f32)
+    n_live = np.full(B, K, np.int64)
+    seqs = np.zeros((B, K, 1 + T), np.int32)
+    seqs[:, :, 0] = STA
+    best_score = np.full(B, -np.inf, f32)
+    best_seq = np.zeros((B, 1 + T), np.int32)
+    best_len = np.zeros(B, np.int32)
+    gaps = np.full((B, T), np.inf, f32)
+    bidx = np.arange(B)
+    for t in range(1, T + 1):
+        if not (n_live > 0).any():
+            break
+        logits, new_st, _ = dec.step(tok, st)
+        cand = cum[:, :, None] + log_softmax(logits)  # (B,K,V)
+        live_rows = np.arange(K)[None, :] < (np.minimum(n_live, 1) if t == 1 else n_live)[:, None]
+        cand = np.where(live_rows[:, :, None], cand, f32(-np.inf)).reshape(B, K * V)
+        kk = min(K + 1, K * V)
+        part = np.argpartition(-cand, kk - 1, axis=1)[:, :kk]
+        pv = np.take_along_axis(cand, part, 1)
+        o = np.argsort(-pv, axis=1, kind="stable")
+        idx = np.take_along_axis(part, o, 1)
+        val = np.take_along_axis(pv, o, 1)
+        new_tok = np.full((B, K), PAD, np.int64)
+        new_cum = np.full((B, K), -np.inf, f32)
+        new_seqs = np.zeros_like(seqs)
+        parent_of_slot = np.zeros((B, K), np.int64)
+        n_new = np.zeros(B, np.int64)
+        for b in range(B):
+            nl = int(n_live[b])
+            if nl == 0:
+                continue
+            d = val[b, :nl] - val[b, 1:nl + 1]
+            d = d[np.isfinite(d)]
+            gaps[b, t - 1] = d.min() if d.size else np.inf
+            for j in range(nl):
+                parent, word = divmod(int(idx[b, j]), V)
+                s = seqs[b, parent].copy()
+                s[t] = word
+                if word == END:
+                    if val[b, j] > best_score[b]:
+                        best_score[b], best_seq[b], best_len[b] = val[b, j], s, t + 1
+                else:
+                    n = int(n_new[b])
+                    new_tok[b, n], new_cum[b, n], new_seqs[b, n] = word, val[b, j], s
+                    parent_of_slot[b, n] = parent
+                    n_new[b] += 1
+        st = {n: a[bidx[:, None], parent_of_slot] for n, a in new_st.items()}
+        tok, cum, seqs, n_live = new_tok, new_cum, new_seqs, n_new
+    completed = np.isfinite(best_score)
+    tokens = np.where(completed[:, None], best_seq, seqs[:, 0])
+    lengths = np.where(completed, best_len, 1 + T).astype(np.int32)
+    scores = np.where(completed, best_score, cum[:, 0]).astype(f32)
+    return BeamResult(tokens.astype(np.int32), lengths, scores, completed, gaps)
+
+
+# ---------------------------------------------------------------------------------------------------
+# greedy and sampling rollouts
+# ---------------------------------------------------------------------------------------------------
+
+def greedy_sample(dec, max_len: int = 20):
+    """``sample``: max_len fixed steps of argmax, no <end> handling (BUTD_Model.py:153-189,
+    NIC_Model.py:100-119, AoA_Model.py:295-344).  Returns ids (B,max_len) int32, per-step gap
+    between best and second-best logit (B,max_len), alphas (B,max_len,R) or None."""
+    B = dec.B
+    st = dec.init_state(1)
+    tok = np.full((B, 1), STA, np.int64)
+    ids = np.zeros((B, max_len), np.int32)
+    gaps = np.zeros((B, max_len), f32)
+    alphas = []
+    for t in range(max_len):
+        logits, st, alpha = dec.step(tok, st)
+        lg = logits[:, 0]
+        pred = lg.argmax(axis=1)  # preds.max(1)[1]
+        top2 = np.partition(lg, -2, axis=1)[:, -2:]
+        gaps[:, t] = top2[:, 1] - top2[:, 0]
+        ids[:, t] = pred
+        tok = pred[:, None].astype(np.int64)
+        if alpha is not None:
+            alphas.append(alpha[:, 0])
+    return ids, gaps, (np.stack(alphas, 1) if alphas else None)
+
+
+def _fmix32(h):
+    h = h ^ (h >> np.uint32(16))
+    h = h * np.uint32(0x85EBCA6B)
+    h = h ^ (h >> np.uint32(13))
+    h = h * np.uint32(0xC2B2AE35)
+    return h ^ (h >> np.uint32(16))
+
+
+def gumbel_noise(seed: int, rows: np.ndarray, t: int, V: int) -> np.ndarray:
+    """Counter-based Gumbel(0,1) noise g[row, v] shared bit-for-bit (in the uniforms) with the CUDA
+    sampling epilogue: u = (fmix32(fmix32(fmix32(seed ^ row*0x9E3779B1) ^ t*0x85EBCA77) ^ v*0xC2B2AE3D)
+    >> 8 + 0.5) * 2^-24, g = -log(-log(u))."""
+    with np.errstate(over="ignore"):
+        h = _fmix32(np.uint32(seed & 0xFFFFFFFF) ^ (rows.astype(np.uint32) * np.uint32(0x9E3779B1)))
+        h = _fmix32(h ^ np.uint32((t * 0x85EBCA77) & 0xFFFFFFFF))
+        v = np.arange(V, dtype=np.uint32) * np.uint32(0xC2B2AE3D)
+        x = _fmix32(h[:, None] ^ v[None, :])
+    u = ((x >> np.uint32(8)).astype(f32) + f32(0.5)) * f32(2.0 ** -24)
+    return (-np.log(-np.log(u, dtype=f32), dtype=f32)).astype(f32)
+
+
+def multinomial_sample(dec, max_len: int = 20, n_per_image: int = 1, seed: int = 0):
+    """``sample_rl`` in eval mode (BUTD_Model.py:191-234, NIC_Model.py:121-151, AoA_Model.py:346-401).
+    ``torch.multinomial(exp(logprobs),1)`` is restated as the Gumbel-max draw argmax(logprobs + g)
+    -- the same distribution -- with the counter-based noise above (row = image*n_per_image+j), so
+    that the CUDA path can be compared token for token.  <end> is stored as 0 and 0 is fed back
+    (:226-231); log-probs are recorded for every row at every executed step (:232); the loop stops
+    once every row has finished (:233), leaving zeros behind.
+    Returns seq (B,n,max_len) int32, seqLogprobs (B,n,max_len) fp32, gap (B,n,max_len)."""
+    B, n = dec.B, n_per_image
+    st = dec.init_state(n)
+    tok = np.full((B, n), STA, np.int64)
+    seq = np.zeros((B, n, max_len), np.int32)
+    lps = np.zeros((B, n, max_len), f32)
+    gaps = np.full((B, n, max_len), np.inf, f32)
+    unfinished = np.ones((B, n), bool)
+    rows = np.arange(B * n)
+    for t in range(max_len):
+        logits, st, _ = dec.step(tok, st)
+        logp = log_softmax(logits)  # :221
+        pert = logp.reshape(B * n, -1) + gumbel_noise(seed, rows, t, dec.V)
+        it = pert.argmax(axis=1)
+        top2 = np.partition(pert, -2, axis=1)[:, -2:]
+        gaps[:, :, t] = (top2[:, 1] - top2[:, 0]).reshape(B, n)
+        lp = logp.reshape(B * n, -1)[rows, it].reshape(B, n)  # :224
+        it = it.reshape(B, n)
+        unfinished = unfinished & (it != END)  # :226-229
+        it = it * unfinished  # :230
+        seq[:, :, t] = it
+        lps[:, :, t] = lp
+        tok = it.astype(np.int64)
+        if not unfinished.any():  # :233
+            break
+    return seq, lps, gaps
+
+
+def teacher_forced_logprobs(dec, seq_fed: np.ndarray, seq_scored: np.ndarray):
+    """log p(seq_scored[t] | <sta>, seq_fed[:t]) for rows (B,n,T): used to check sampled log-probs
+    independently of which token a near-tie picked."""
+    B, n, T = seq_fed.shape
+    st = dec.init_state(n)
+    tok = np.full((B, n), STA, np.int64)
+    out = np.zeros((B, n, T), f32)
+    for t in range(T):
+        logits, st, _ = dec.step(tok, st)
+        logp = log_softmax(logits)
+        out[:, :, t] = np.take_along_axis(logp, seq_scored[:, :, t, None].astype(np.int64), 2)[..., 0]
+        tok = seq_fed[:, :, t].astype(np.int64)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# the eval driver's id -> word loop
+# ---------------------------------------------------------------------------------------------------
+
+def ids_to_caption(ids, ix2word) -> str:
+    """Engine.py:288-297: words until '<end>', skipping '<sta>'."""
+    words = []
+    for i in ids:
+        w = ix2word[int(i)]
+        if w == "<end>":
+            break
+        if w != "<sta>":
+            words.append(w)
+    return " ".join(words)
+
+
+def agreement(tokens_a, tokens_b, min_gap, tol=1e-4):
+    """Per-image verdict of a decoded caption against the oracle's: 'exact', 'tie' (first
+    divergence happens at a step whose oracle top-(k+1) gap is below ``tol`` -- north_star's
+    tie-justified rule) or 'diff'.  tokens_*: (B,L); min_gap: (B,T) for steps 1..T."""
+    out = []
+    for a, b, g in zip(tokens_a, tokens_b, min_gap):
+        if np.array_equal(a, b):
+            out.append("exact")
+            continue
+        t = int(np.argmax(a != b))  # first differing position; position p is produced at step p
+        # any earlier near-tie can reorder slots and surface later, so accept a tie up to step t
+        ok = bool(np.any(g[:max(t, 1)] < tol))
+        out.append("tie" if ok else "diff")
+    return out
