@@ -1,0 +1,129 @@
+/* capdec -- C ABI of the B200-native batched caption decoder (libcapdec.so).
+ *
+ * Drop-in boundary for the decode loop of zyj0021200/simpleImageCaptionZoo: the library replaces what the
+ * reference runs inside
+ *     DecoderRNN.beam_search_sample / sample / sample_rl      Models/BUTD_Model.py:153-318
+ *     DecoderRNN.beam_search_sample / sample / sample_rl      Models/NIC_Model.py:100-212
+ *     AoA_Decoder.beam_search_sample / sample / sample_rl     Models/AoA_Model.py:295-502
+ * and is called from the Python Engine mirror (simpleimagecaptionzoo_b200/engine.py) the way
+ * Engine.eval_captions_json_generation (Engine.py:274-300) and Engine.SCST_training_epoch (Engine.py:251-272)
+ * call model.beam_search_sampler / model.sampler / model.sampler_rl.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative capdec_status,
+ * with a message available from capdec_last_error().  No C++ exception crosses the boundary.  All GPU work is
+ * enqueued on the caller's stream (a cudaStream_t passed as void*); nothing synchronises the device unless
+ * stated.  One handle per (process, device); a handle is not re-entrant.  The caller owns every input and
+ * output buffer and keeps it alive until the stream work has completed; the library owns its packed weights
+ * and workspace, allocated in capdec_create (no allocation inside the decode loop).
+ */
+#ifndef CAPDEC_H_
+#define CAPDEC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAPDEC_ABI_VERSION 1
+
+typedef enum capdec_status {
+    CAPDEC_OK = 0,
+    CAPDEC_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+    CAPDEC_ERR_CUDA = -2,      /* a CUDA call failed (message has the CUDA error string) */
+    CAPDEC_ERR_STATE = -3,     /* call order violated (e.g. decode before prepare) */
+    CAPDEC_ERR_NOMEM = -4,
+    CAPDEC_ERR_WEIGHT = -5     /* missing / mis-shaped state_dict entry */
+} capdec_status;
+
+typedef enum capdec_arch {
+    CAPDEC_ARCH_NIC = 0,       /* Models/NIC_Model.py  DecoderRNN  (one LSTMCell primed by the image)      */
+    CAPDEC_ARCH_BUTD = 1,      /* Models/BUTD_Model.py DecoderRNN  (top-down attention, two LSTMCells)      */
+    CAPDEC_ARCH_AOA = 2        /* Models/AoA_Model.py  AoA_Decoder (LSTMCell + multi-head AoA)              */
+} capdec_arch;
+
+typedef enum capdec_math {
+    CAPDEC_MATH_F16 = 0,       /* GEMM operands rounded to fp16 (10-bit mantissa, tf32-grade), fp32 accumulate */
+    CAPDEC_MATH_F16X3 = 1      /* operands split hi+lo fp16, three tensor-core passes: fp32-grade products   */
+} capdec_math;
+
+typedef enum capdec_sample_mode {
+    CAPDEC_SAMPLE_GREEDY = 0,      /* DecoderRNN.sample: argmax, max_seq fixed steps, no <end> handling        */
+    CAPDEC_SAMPLE_MULTINOMIAL = 1  /* DecoderRNN.sample_rl: draw ~ softmax, <end> stored as 0, early break     */
+} capdec_sample_mode;
+
+/* Mirrors the model-settings keys read by Utils.model_construction (Utils.py:161-203):
+ * embed_dim, hidden_dim, atten_dim (+ enc_dim = 2048, vocab size = len(caption_vocab), 8 AoA heads). */
+typedef struct capdec_config {
+    int32_t arch;          /* capdec_arch */
+    int32_t hidden_dim;    /* H */
+    int32_t embed_dim;     /* E */
+    int32_t atten_dim;     /* A   (BUTD only) */
+    int32_t enc_dim;       /* D   (BUTD: region feature width, 2048) */
+    int32_t vocab_size;    /* V */
+    int32_t num_heads;     /* AoA only */
+    int32_t max_batch;     /* largest number of images per prepare() */
+    int32_t max_regions;   /* largest R (36 bottom-up boxes, 49/196 grid cells); ignored for NIC */
+    int32_t max_rows;      /* largest beam size / samples per image */
+    int32_t max_seq;       /* largest number of decode steps */
+    int32_t math_mode;     /* capdec_math */
+    int32_t device;        /* CUDA device ordinal */
+} capdec_config;
+
+typedef struct capdec_handle capdec_handle;
+
+int capdec_abi_version(void);
+
+/* Allocate packed-weight storage and the decode workspace on cfg->device. */
+int capdec_create(const capdec_config* cfg, capdec_handle** out);
+void capdec_destroy(capdec_handle* h);
+const char* capdec_last_error(const capdec_handle* h);  /* h may be NULL: error of the last failed create */
+
+/* Hand one tensor of the reference's decoder state_dict to the library, under its reference name without the
+ * "decoder." prefix (e.g. "predict.weight_g", "TD_atten.weight_ih", "embed.0.weight"; the checkpoint layout is
+ * the one Engine.load_from_checkpoint reads, Engine.py:43-70).  data is fp32, row-major, host or device memory;
+ * it is copied before the call returns control of the buffer (stream-ordered for device memory). */
+int capdec_load_weight(capdec_handle* h, const char* name, const float* data, const int64_t* shape, int32_t ndim,
+                       void* stream);
+/* Fold weight-norm (w = g*v/||v||), fuse b_ih+b_hh, split W_ih by input segment, interleave LSTM gates / GLU
+ * halves and convert to the fp16 (hi|lo) operand layout.  Fails with CAPDEC_ERR_WEIGHT if a tensor is missing. */
+int capdec_finalize_weights(capdec_handle* h, void* stream);
+
+/* One-time, step-invariant work for a batch of images (the part the reference recomputes every step):
+ *   BUTD: feats [B,R,D] -> enc_att projection [B,R,A] (BUTD_Model.py:57), mean feature (:251), hoisted
+ *         W_ih[:,mean]*mean + b_ih + b_hh of the top-down LSTM (:265).
+ *   AoA : feats = refined features [B,R,H]; mask [B,R] float {0,1} or NULL -> masked mean (AoA_Model.py:422-425),
+ *         K,V projections (:114-115).
+ *   NIC : feats = image embedding [B,E] (R ignored) -> priming LSTM step (NIC_Model.py:52-56).
+ * feats (and mask) are DEVICE pointers and must stay valid until the following decode call has completed. */
+int capdec_prepare(capdec_handle* h, const float* feats, const float* mask, int32_t batch, int32_t regions, void* stream);
+
+/* Batched beam search with the reference's exact bookkeeping (shrinking beam, best COMPLETED hypothesis wins,
+ * no length normalisation; BUTD_Model.py:236-318) for the prepared batch.  Device outputs:
+ *   tokens      [B, 1+max_seq] int32: <sta>=1 first, words, <end>=2 when completed, then <pad>=0
+ *   seq_logprob [B] fp32 sum of log-probs of the emitted words        (may be NULL)
+ *   lengths     [B] int32 valid entries of tokens incl. <sta>/<end>   (may be NULL)
+ *   alphas      reserved, pass NULL */
+int capdec_beam_search(capdec_handle* h, int32_t beam, int32_t max_seq, int32_t* tokens, float* seq_logprob,
+                       int32_t* lengths, float* alphas, void* stream);
+
+/* Greedy (``sample``) or multinomial (``sample_rl``) rollout, n_per_image rows per prepared image.
+ *   tokens   [B*n_per_image, max_seq] int32 (no <sta>)
+ *   logprobs [B*n_per_image, max_seq] fp32 log-prob of each stored word (multinomial; may be NULL for greedy)
+ * The multinomial draw is the Gumbel-max form of torch.multinomial(exp(logprobs),1) with counter-based noise
+ * keyed by (seed, row, step, word). */
+int capdec_sample(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t seed, int32_t max_seq, int32_t* tokens,
+                  float* logprobs, void* stream);
+
+/* Number of kernels the library launched on behalf of this handle since create (bench.py's gpu_launches). */
+int64_t capdec_launch_count(const capdec_handle* h);
+
+/* Test hook: D[M,N] = A[M,K] * B[N,K]^T (+bias[N]) through the library's tcgen05 GEMM, fp32 device buffers in/out.
+ * K must be a multiple of 64. */
+int capdec_test_gemm(const float* a, const float* b, const float* bias, float* d, int32_t m, int32_t n, int32_t k,
+                     int32_t math_mode, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAPDEC_H_ */

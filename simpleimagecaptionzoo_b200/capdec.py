@@ -1,0 +1,209 @@
+"""ctypes binding of libcapdec.so (include/capdec.h) and the tensor-level decoder object.
+
+PyTorch is plumbing here: device memory, streams, dtype conversion.  Every decode step runs inside the C
+library as hand-written sm_100a kernels; there is NO CPU or eager-PyTorch fallback -- if the shared library
+is missing or no B200 is present the constructors raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Mapping, Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcapdec.so")
+
+ARCH = {"NIC": 0, "BUTD": 1, "AOA": 2}
+MATH = {"f16": 0, "f16x3": 1}
+SAMPLE_GREEDY, SAMPLE_MULTINOMIAL = 0, 1
+
+# every symbol include/capdec.h declares (tests check that the built library exports all of them)
+SYMBOLS = (
+    "capdec_abi_version", "capdec_create", "capdec_destroy", "capdec_last_error", "capdec_load_weight",
+    "capdec_finalize_weights", "capdec_prepare", "capdec_beam_search", "capdec_sample", "capdec_launch_count",
+    "capdec_test_gemm",
+)
+
+
+class CapdecConfig(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "arch", "hidden_dim", "embed_dim", "atten_dim", "enc_dim", "vocab_size", "num_heads", "max_batch",
+        "max_regions", "max_rows", "max_seq", "math_mode", "device")]
+
+
+_lib = None
+
+
+def load_library(path: str = LIB_PATH) -> ctypes.CDLL:
+    """dlopen libcapdec.so and declare the prototypes.  Raises if the library has not been built
+    (``python -c 'import __graft_entry__ as g; g.build()'``)."""
+    global _lib
+    if _lib is not None and path == LIB_PATH:
+        return _lib
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not found: build the CUDA extension first (__graft_entry__.build()); "
+                           "there is no CPU fallback for the caption decoder")
+    lib = ctypes.CDLL(path)
+    vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+    lib.capdec_abi_version.restype = ctypes.c_int
+    lib.capdec_create.argtypes = [ctypes.POINTER(CapdecConfig), ctypes.POINTER(vp)]
+    lib.capdec_destroy.argtypes = [vp]
+    lib.capdec_destroy.restype = None
+    lib.capdec_last_error.argtypes = [vp]
+    lib.capdec_last_error.restype = ctypes.c_char_p
+    lib.capdec_load_weight.argtypes = [vp, ctypes.c_char_p, vp, ctypes.POINTER(i64), i32, vp]
+    lib.capdec_finalize_weights.argtypes = [vp, vp]
+    lib.capdec_prepare.argtypes = [vp, vp, vp, i32, i32, vp]
+    lib.capdec_beam_search.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
+    lib.capdec_sample.argtypes = [vp, i32, i32, ctypes.c_uint64, i32, vp, vp, vp]
+    lib.capdec_launch_count.argtypes = [vp]
+    lib.capdec_launch_count.restype = i64
+    lib.capdec_test_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    if lib.capdec_abi_version() != 1:
+        raise RuntimeError("libcapdec.so ABI version mismatch")
+    if path == LIB_PATH:
+        _lib = lib
+    return lib
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _stream_ptr(device) -> int:
+    torch = _torch()
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def test_gemm(a, b, bias=None, math: str = "f16"):
+    """D = A @ B.T (+ bias) through the library's tcgen05 GEMM (test hook).  a [M,K], b [N,K] fp32 CUDA tensors."""
+    torch = _torch()
+    lib = load_library()
+    a = a.contiguous().float()
+    b = b.contiguous().float()
+    m, k = a.shape
+    n = b.shape[0]
+    d = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        rc = lib.capdec_test_gemm(a.data_ptr(), b.data_ptr(), bias.data_ptr() if bias is not None else None, d.data_ptr(),
+                                  m, n, k, MATH[math], _stream_ptr(a.device))
+    if rc != 0:
+        raise RuntimeError(f"capdec_test_gemm failed ({rc}): {lib.capdec_last_error(None).decode()}")
+    return d
+
+
+class CaptionDecoder:
+    """Batched beam / greedy / multinomial caption decoder for one architecture on one GPU.
+
+    ``state_dict`` is the reference checkpoint's mapping (torch tensors or numpy arrays); entries whose key
+    starts with ``decoder.`` (or that carry no prefix at all) are handed to the library unchanged -- weight-norm
+    folding, gate interleaving and fp16 packing happen inside (capdec_finalize_weights).
+    """
+
+    def __init__(self, arch: str, state_dict: Mapping[str, object], *, hidden_dim: int, embed_dim: int, vocab_size: int,
+                 atten_dim: int = 0, enc_dim: int = 2048, num_heads: int = 8, max_batch: int = 64, max_regions: int = 36,
+                 max_rows: int = 3, max_seq: int = 20, math: str = "f16", device: int = 0):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise RuntimeError("CaptionDecoder needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = load_library()
+        self.arch = arch.upper()
+        self.device = torch.device("cuda", device)
+        self.V, self.H, self.E = vocab_size, hidden_dim, embed_dim
+        self.max_batch, self.max_rows, self.max_seq, self.max_regions = max_batch, max_rows, max_seq, max_regions
+        self.math = math
+        cfg = CapdecConfig(ARCH[self.arch], hidden_dim, embed_dim, atten_dim, enc_dim if self.arch == "BUTD" else 0,
+                           vocab_size, num_heads if self.arch == "AOA" else 0, max_batch,
+                           0 if self.arch == "NIC" else max_regions, max_rows, max_seq, MATH[math], device)
+        handle = ctypes.c_void_p()
+        rc = self.lib.capdec_create(ctypes.byref(cfg), ctypes.byref(handle))
+        if rc != 0:
+            raise RuntimeError(f"capdec_create failed ({rc}): {self.lib.capdec_last_error(None).decode()}")
+        self._h = handle
+        self._keep = None
+        self.B = 0
+        self._load(state_dict)
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self.lib.capdec_last_error(self._h).decode()}")
+
+    def _load(self, state_dict):
+        torch = _torch()
+        stream = _stream_ptr(self.device)
+        n = 0
+        with torch.cuda.device(self.device):
+            for key, val in state_dict.items():
+                if key.startswith("decoder."):
+                    name = key[len("decoder."):]
+                elif "." in key and key.split(".")[0] in ("encoder", "img_feats_porjection", "aoa_refine"):
+                    continue  # encoder-side entries of the full captioner checkpoint are not part of the decode loop
+                else:
+                    name = key
+                if isinstance(val, np.ndarray):
+                    t = torch.from_numpy(np.ascontiguousarray(val, dtype=np.float32))
+                else:
+                    t = val.detach().to(torch.float32).contiguous()
+                shape = (ctypes.c_int64 * t.dim())(*t.shape)
+                self._check(self.lib.capdec_load_weight(self._h, name.encode(), t.data_ptr(), shape, t.dim(), stream),
+                            f"capdec_load_weight({name})")
+                n += 1
+            self._check(self.lib.capdec_finalize_weights(self._h, stream), "capdec_finalize_weights")
+        return n
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.capdec_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.capdec_launch_count(self._h))
+
+    # ------------------------------------------------------------------ decode API (device tensors)
+    def prepare(self, feats, mask=None):
+        """feats: CUDA fp32 [B,R,D] (BUTD), [B,R,H] refined (AoA) or [B,E] (NIC); mask: [B,R] float or None."""
+        torch = _torch()
+        feats = feats.to(self.device, torch.float32).contiguous()
+        if mask is not None:
+            mask = mask.to(self.device, torch.float32).contiguous()
+        B = feats.shape[0]
+        R = feats.shape[1] if feats.dim() == 3 else 0
+        with torch.cuda.device(self.device):
+            self._check(self.lib.capdec_prepare(self._h, feats.data_ptr(), None if mask is None else mask.data_ptr(), B, R,
+                                                _stream_ptr(self.device)), "capdec_prepare")
+        self._keep = (feats, mask)  # the library reads them during decode
+        self.B = B
+
+    def beam_search(self, beam: int, max_seq: int = 20):
+        """-> tokens [B,1+max_seq] int32 (<sta> first), seq_logprob [B] fp32, lengths [B] int32 (CUDA tensors)."""
+        torch = _torch()
+        B = self.B
+        tokens = torch.empty((B, 1 + max_seq), dtype=torch.int32, device=self.device)
+        scores = torch.empty((B,), dtype=torch.float32, device=self.device)
+        lengths = torch.empty((B,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.capdec_beam_search(self._h, beam, max_seq, tokens.data_ptr(), scores.data_ptr(),
+                                                    lengths.data_ptr(), None, _stream_ptr(self.device)), "capdec_beam_search")
+        return tokens, scores, lengths
+
+    def sample(self, mode: int, n_per_image: int = 1, seed: int = 0, max_seq: int = 20):
+        """-> tokens [B*n,max_seq] int32, logprobs [B*n,max_seq] fp32 (CUDA tensors)."""
+        torch = _torch()
+        M = self.B * n_per_image
+        tokens = torch.empty((M, max_seq), dtype=torch.int32, device=self.device)
+        logprobs = torch.empty((M, max_seq), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.capdec_sample(self._h, mode, n_per_image, seed, max_seq, tokens.data_ptr(),
+                                               logprobs.data_ptr(), _stream_ptr(self.device)), "capdec_sample")
+        return tokens, logprobs

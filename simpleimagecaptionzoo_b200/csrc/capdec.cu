@@ -1,0 +1,1028 @@
+// libcapdec.so -- host side of the B200-native caption decoder behind the C ABI of include/capdec.h.
+// Owns packed weights + workspace, builds the TMA tensor maps, and enqueues the per-step kernel sequence
+// (no host synchronisation inside the decode loop).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/capdec.h"
+#include "kernels.cuh"
+
+using namespace capdec;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Act16 {  // fp16 GEMM operand, row-major, hi | lo halves
+    __half* p = nullptr;
+    int rows = 0, cols = 0, ld = 0, lo = 0;
+};
+
+struct Raw {
+    float* d = nullptr;
+    std::vector<int64_t> shape;
+    size_t numel = 0;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+constexpr int BN = 256;  // BLOCK_N of every GEMM instantiation
+
+}  // namespace
+
+struct capdec_handle {
+    capdec_config cfg{};
+    std::string err;
+    int num_sms = 148;
+    bool split = false;
+    bool weights_ready = false;
+    bool prepared = false;
+    int B = 0, R = 0;  // prepared batch
+    const float* feats = nullptr;
+    const float* mask = nullptr;
+    int64_t launches = 0;
+    std::vector<void*> allocs;
+    std::map<std::string, Raw> raw;
+
+    // dims
+    int H = 0, E = 0, A = 0, D = 0, V = 0, NH = 0, Bmax = 0, Rmax = 0, Kmax = 0, Tmax = 0, Mmax = 0;
+    int n_tiles_v = 0;
+
+    // packed weights
+    Act16 W_pred, W_l1, W_l2, W_aux1, W_aux2, W_aux3;
+    float *b_pred = nullptr, *b_l1 = nullptr, *b_l2 = nullptr, *b_aux1 = nullptr, *b_aux2 = nullptr, *b_aux3 = nullptr;
+    float* w_aff = nullptr;
+    float b_aff = 0.f;
+    const float* embed = nullptr;
+    const float *ln_gain = nullptr, *ln_bias = nullptr;
+    double* scale_tmp = nullptr;
+
+    // activations / workspace
+    Act16 feats16, mean16, XA, XB, Hb, Hb2, Xp, H0;
+    float *enc_ctx = nullptr, *G0 = nullptr, *dec_ctx = nullptr, *kv32 = nullptr, *mean32 = nullptr, *q32 = nullptr,
+          *ctx32 = nullptr, *h32 = nullptr, *c0 = nullptr;
+    float* c1[2] = {nullptr, nullptr};
+    float* c2[2] = {nullptr, nullptr};
+    float* part = nullptr;
+    int *tok = nullptr, *parent = nullptr, *n_live = nullptr, *best_seq = nullptr, *best_len = nullptr, *unfinished = nullptr,
+        *live_count = nullptr;
+    int* seqs[2] = {nullptr, nullptr};
+    float *cum = nullptr, *best_score = nullptr;
+};
+
+namespace {
+
+#define CK(h, expr)                                                                                         \
+    do {                                                                                                    \
+        cudaError_t _e = (expr);                                                                            \
+        if (_e != cudaSuccess) {                                                                            \
+            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                                  \
+            return CAPDEC_ERR_CUDA;                                                                         \
+        }                                                                                                   \
+    } while (0)
+
+#define CKS(h, expr)                  \
+    do {                              \
+        int _s = (expr);              \
+        if (_s != CAPDEC_OK) return _s; \
+    } while (0)
+
+int fail(capdec_handle* h, int code, const std::string& msg) {
+    h->err = msg;
+    return code;
+}
+
+template <typename T>
+int dalloc(capdec_handle* h, T** out, size_t n, bool zero = true) {
+    void* p = nullptr;
+    const size_t bytes = (n ? n : 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        h->err = std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e);
+        return CAPDEC_ERR_NOMEM;
+    }
+    if (zero) CK(h, cudaMemset(p, 0, bytes));
+    h->allocs.push_back(p);
+    *out = static_cast<T*>(p);
+    return CAPDEC_OK;
+}
+
+int alloc_act(capdec_handle* h, Act16* a, int rows, int cols) {
+    a->rows = rows;
+    a->cols = cols;
+    a->ld = cols * (h->split ? 2 : 1);
+    a->lo = h->split ? cols : 0;
+    return dalloc(h, &a->p, static_cast<size_t>(rows) * a->ld);
+}
+
+// Tensor map over rows x (ld - col_off) fp16 starting at column col_off; box = 64 (K) x box_rows, 128B swizzle.
+int make_map(capdec_handle* h, CUtensorMap* m, const __half* base, int rows, int ld, int col_off, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(h, CAPDEC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(ld - col_off), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * sizeof(__half)};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(BLOCK_K), static_cast<cuuint32_t>(box_rows)};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base + col_off), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, CAPDEC_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string(static_cast<int>(r)));
+    return CAPDEC_OK;
+}
+int map_a(capdec_handle* h, CUtensorMap* m, const Act16& a, int col_off = 0) {
+    return make_map(h, m, a.p, a.rows, a.ld, col_off, BLOCK_M);
+}
+int map_b(capdec_handle* h, CUtensorMap* m, const Act16& a) { return make_map(h, m, a.p, a.rows, a.ld, 0, BN); }
+
+template <int EPI, int KTOP>
+int launch_gemm_t(capdec_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
+    using Cfg = GemmCfg<BN>;
+    static bool attr_set = false;
+    auto kern = gemm_kernel<BN, EPI, KTOP>;
+    if (!attr_set) {
+        CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int tiles = p.num_m_blocks * p.num_n_blocks;
+    const int grid = tiles < h->num_sms ? tiles : h->num_sms;
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    return CAPDEC_OK;
+}
+
+// D[M,N] = A[M,Kdim] * B[N,Kdim]^T with the chosen epilogue.
+int launch_gemm(capdec_handle* h, int epi, int ktop, const CUtensorMap& ma, int a_lo, const CUtensorMap& mb, int b_lo, int M,
+                int N, int Kdim, const EpiParams& e, cudaStream_t st) {
+    if (Kdim % BLOCK_K) return fail(h, CAPDEC_ERR_INVALID, "GEMM K must be a multiple of 64");
+    if (M <= 0 || N <= 0) return fail(h, CAPDEC_ERR_INVALID, "empty GEMM");
+    GemmParams p{};
+    p.M = M;
+    p.N = N;
+    p.k_blocks = Kdim / BLOCK_K;
+    p.passes = h->split ? 3 : 1;
+    p.a_lo_off = a_lo;
+    p.b_lo_off = b_lo;
+    p.num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+    p.num_n_blocks = (N + BN - 1) / BN;
+    p.epi = e;
+    switch (epi) {
+        case EPI_STORE: return launch_gemm_t<EPI_STORE, 1>(h, ma, mb, p, st);
+        case EPI_LSTM: return launch_gemm_t<EPI_LSTM, 1>(h, ma, mb, p, st);
+        case EPI_GLU: return launch_gemm_t<EPI_GLU, 1>(h, ma, mb, p, st);
+        case EPI_SAMPLE: return launch_gemm_t<EPI_SAMPLE, 1>(h, ma, mb, p, st);
+        case EPI_TOPK:
+            if (ktop <= 4) return launch_gemm_t<EPI_TOPK, 4>(h, ma, mb, p, st);
+            return launch_gemm_t<EPI_TOPK, 8>(h, ma, mb, p, st);
+    }
+    return fail(h, CAPDEC_ERR_INVALID, "unknown epilogue");
+}
+
+int ktop_for(int beam) { return beam <= 4 ? 4 : 8; }
+
+// ------------------------------------------------------------------------------------------------ weights
+const Raw* find_raw(capdec_handle* h, const std::string& name) {
+    auto it = h->raw.find(name);
+    return it == h->raw.end() ? nullptr : &it->second;
+}
+
+int need(capdec_handle* h, const std::string& name, std::vector<int64_t> shape, const Raw** out) {
+    const Raw* r = find_raw(h, name);
+    if (!r) return fail(h, CAPDEC_ERR_WEIGHT, "missing state_dict entry: " + name);
+    if (r->shape != shape) {
+        std::string s = "shape mismatch for " + name + ": got [";
+        for (auto d : r->shape) s += std::to_string(d) + ",";
+        s += "] expected [";
+        for (auto d : shape) s += std::to_string(d) + ",";
+        return fail(h, CAPDEC_ERR_WEIGHT, s + "]");
+    }
+    *out = r;
+    return CAPDEC_OK;
+}
+
+int grid_for(size_t n, int block = 256) {
+    size_t g = (n + block - 1) / block;
+    return static_cast<int>(g > 4096 ? 4096 : (g ? g : 1));
+}
+
+// pack src[:, src_col : src_col+K] (optionally weight-norm scaled by g) into dst[:, dst_col : dst_col+K]
+int pack_segment(capdec_handle* h, const Raw* src, int src_col, int K, const Raw* g, Act16& dst, int dst_col, int mode, int Hh,
+                 cudaStream_t st) {
+    const int N = dst.rows;
+    const int src_ld = static_cast<int>(src->shape[1]);
+    const double* scale = nullptr;
+    if (g) {
+        weightnorm_scale_kernel<<<N, 256, 0, st>>>(g->d, src->d, N, src_ld, h->scale_tmp);
+        CK(h, cudaGetLastError());
+        scale = h->scale_tmp;
+    }
+    pack_weight_kernel<<<grid_for(static_cast<size_t>(N) * K), 256, 0, st>>>(src->d, src_ld, src_col, scale, dst.p, dst.ld, dst.lo,
+                                                                             dst_col, N, K, mode, Hh);
+    CK(h, cudaGetLastError());
+    return CAPDEC_OK;
+}
+
+int pack_bias(capdec_handle* h, const Raw* a, const Raw* b, float* dst, int N, int mode, int Hh, cudaStream_t st) {
+    pack_bias_kernel<<<(N + 255) / 256, 256, 0, st>>>(a->d, b ? b->d : nullptr, dst, N, mode, Hh);
+    CK(h, cudaGetLastError());
+    return CAPDEC_OK;
+}
+
+int finalize_predict(capdec_handle* h, cudaStream_t st) {
+    const Raw *g, *v, *b;
+    CKS(h, need(h, "predict.weight_g", {h->V, 1}, &g));
+    CKS(h, need(h, "predict.weight_v", {h->V, h->H}, &v));
+    CKS(h, need(h, "predict.bias", {h->V}, &b));
+    CKS(h, pack_segment(h, v, 0, h->H, g, h->W_pred, 0, 0, 0, st));
+    CKS(h, pack_bias(h, b, nullptr, h->b_pred, h->V, 0, 0, st));
+    return CAPDEC_OK;
+}
+
+int finalize_butd(capdec_handle* h, cudaStream_t st) {
+    const int H = h->H, E = h->E, A = h->A, D = h->D;
+    const Raw *g, *v, *b, *wih, *whh, *bih, *bhh;
+    // attention projections (weight-normed Linears, BUTD_Model.py:43-45)
+    CKS(h, need(h, "atten.enc_att.weight_g", {A, 1}, &g));
+    CKS(h, need(h, "atten.enc_att.weight_v", {A, D}, &v));
+    CKS(h, need(h, "atten.enc_att.bias", {A}, &b));
+    CKS(h, pack_segment(h, v, 0, D, g, h->W_aux1, 0, 0, 0, st));  // W_aux1 = enc_att [A, D]
+    CKS(h, pack_bias(h, b, nullptr, h->b_aux1, A, 0, 0, st));
+    CKS(h, need(h, "atten.dec_att.weight_g", {A, 1}, &g));
+    CKS(h, need(h, "atten.dec_att.weight_v", {A, H}, &v));
+    CKS(h, need(h, "atten.dec_att.bias", {A}, &b));
+    CKS(h, pack_segment(h, v, 0, H, g, h->W_aux2, 0, 0, 0, st));  // W_aux2 = dec_att [A, H]
+    CKS(h, pack_bias(h, b, nullptr, h->b_aux2, A, 0, 0, st));
+    CKS(h, need(h, "atten.affine.weight_g", {1, 1}, &g));
+    CKS(h, need(h, "atten.affine.weight_v", {1, A}, &v));
+    CKS(h, need(h, "atten.affine.bias", {1}, &b));
+    weightnorm_scale_kernel<<<1, 256, 0, st>>>(g->d, v->d, 1, A, h->scale_tmp);
+    CK(h, cudaGetLastError());
+    fold_vector_kernel<<<(A + 255) / 256, 256, 0, st>>>(v->d, h->scale_tmp, h->w_aff, A);
+    CK(h, cudaGetLastError());
+    CK(h, cudaMemcpyAsync(&h->b_aff, b->d, sizeof(float), cudaMemcpyDeviceToHost, st));
+    // top-down attention LSTM: input cat[h2, mean, emb] (BUTD_Model.py:265) -> operand [h2 | emb | h1]
+    CKS(h, need(h, "TD_atten.weight_ih", {4 * H, H + D + E}, &wih));
+    CKS(h, need(h, "TD_atten.weight_hh", {4 * H, H}, &whh));
+    CKS(h, need(h, "TD_atten.bias_ih", {4 * H}, &bih));
+    CKS(h, need(h, "TD_atten.bias_hh", {4 * H}, &bhh));
+    CKS(h, pack_segment(h, wih, 0, H, nullptr, h->W_l1, 0, 1, H, st));
+    CKS(h, pack_segment(h, wih, H + D, E, nullptr, h->W_l1, H, 1, H, st));
+    CKS(h, pack_segment(h, whh, 0, H, nullptr, h->W_l1, H + E, 1, H, st));
+    CKS(h, pack_segment(h, wih, H, D, nullptr, h->W_aux3, 0, 1, H, st));  // W_aux3 = mean-feature slice [4H, D]
+    CKS(h, pack_bias(h, bih, bhh, h->b_l1, 4 * H, 1, H, st));
+    // language LSTM: input cat[ctx, h1] (BUTD_Model.py:268) -> operand [ctx | h1 | h2]
+    CKS(h, need(h, "language_model.weight_ih", {4 * H, D + H}, &wih));
+    CKS(h, need(h, "language_model.weight_hh", {4 * H, H}, &whh));
+    CKS(h, need(h, "language_model.bias_ih", {4 * H}, &bih));
+    CKS(h, need(h, "language_model.bias_hh", {4 * H}, &bhh));
+    CKS(h, pack_segment(h, wih, 0, D + H, nullptr, h->W_l2, 0, 1, H, st));
+    CKS(h, pack_segment(h, whh, 0, H, nullptr, h->W_l2, D + H, 1, H, st));
+    CKS(h, pack_bias(h, bih, bhh, h->b_l2, 4 * H, 1, H, st));
+    const Raw* emb;
+    CKS(h, need(h, "embed.0.weight", {h->V, E}, &emb));
+    h->embed = emb->d;
+    return CAPDEC_OK;
+}
+
+int finalize_nic(capdec_handle* h, cudaStream_t st) {
+    const int H = h->H, E = h->E;
+    const Raw *wih, *whh, *bih, *bhh, *emb;
+    CKS(h, need(h, "lstm.weight_ih", {4 * H, E}, &wih));
+    CKS(h, need(h, "lstm.weight_hh", {4 * H, H}, &whh));
+    CKS(h, need(h, "lstm.bias_ih", {4 * H}, &bih));
+    CKS(h, need(h, "lstm.bias_hh", {4 * H}, &bhh));
+    CKS(h, pack_segment(h, wih, 0, E, nullptr, h->W_l1, 0, 1, H, st));
+    CKS(h, pack_segment(h, whh, 0, H, nullptr, h->W_l1, E, 1, H, st));
+    CKS(h, pack_bias(h, bih, bhh, h->b_l1, 4 * H, 1, H, st));
+    CKS(h, need(h, "embed.weight", {h->V, E}, &emb));
+    h->embed = emb->d;
+    return CAPDEC_OK;
+}
+
+int finalize_aoa(capdec_handle* h, cudaStream_t st) {
+    const int H = h->H, E = h->E;
+    const Raw *wih, *whh, *bih, *bhh, *w, *b, *emb, *gn, *bs;
+    // lstm input cat[emb, mean+ctx] (AoA_Model.py:441) -> operand [emb | mean+ctx | h]
+    CKS(h, need(h, "lstm.weight_ih", {4 * H, E + H}, &wih));
+    CKS(h, need(h, "lstm.weight_hh", {4 * H, H}, &whh));
+    CKS(h, need(h, "lstm.bias_ih", {4 * H}, &bih));
+    CKS(h, need(h, "lstm.bias_hh", {4 * H}, &bhh));
+    CKS(h, pack_segment(h, wih, 0, E + H, nullptr, h->W_l1, 0, 1, H, st));
+    CKS(h, pack_segment(h, whh, 0, H, nullptr, h->W_l1, E + H, 1, H, st));
+    CKS(h, pack_bias(h, bih, bhh, h->b_l1, 4 * H, 1, H, st));
+    CKS(h, need(h, "aoa_block.linear_Q.weight", {H, H}, &w));
+    CKS(h, need(h, "aoa_block.linear_Q.bias", {H}, &b));
+    CKS(h, pack_segment(h, w, 0, H, nullptr, h->W_aux1, 0, 0, 0, st));  // W_aux1 = linear_Q
+    CKS(h, pack_bias(h, b, nullptr, h->b_aux1, H, 0, 0, st));
+    // W_aux2 = [linear_K ; linear_V] stacked along N -> one projection GEMM, kv [B*R, 2H]
+    CKS(h, need(h, "aoa_block.linear_K.weight", {H, H}, &w));
+    CKS(h, need(h, "aoa_block.linear_K.bias", {H}, &b));
+    {
+        Act16 top = h->W_aux2;
+        top.rows = H;
+        CKS(h, pack_segment(h, w, 0, H, nullptr, top, 0, 0, 0, st));
+        CKS(h, pack_bias(h, b, nullptr, h->b_aux2, H, 0, 0, st));
+    }
+    CKS(h, need(h, "aoa_block.linear_V.weight", {H, H}, &w));
+    CKS(h, need(h, "aoa_block.linear_V.bias", {H}, &b));
+    {
+        Act16 bot = h->W_aux2;
+        bot.rows = H;
+        bot.p = h->W_aux2.p + static_cast<size_t>(H) * h->W_aux2.ld;
+        CKS(h, pack_segment(h, w, 0, H, nullptr, bot, 0, 0, 0, st));
+        CKS(h, pack_bias(h, b, nullptr, h->b_aux2 + H, H, 0, 0, st));
+    }
+    // AoA information/gate Linear(2H -> 2H) + GLU on cat[att, query] (AoA_Model.py:85-88,118)
+    CKS(h, need(h, "aoa_block.aoa_module.0.weight", {2 * H, 2 * H}, &w));
+    CKS(h, need(h, "aoa_block.aoa_module.0.bias", {2 * H}, &b));
+    CKS(h, pack_segment(h, w, 0, 2 * H, nullptr, h->W_aux3, 0, 2, H, st));
+    CKS(h, pack_bias(h, b, nullptr, h->b_aux3, 2 * H, 2, H, st));
+    CKS(h, need(h, "embed.0.weight", {h->V, E}, &emb));
+    h->embed = emb->d;
+    CKS(h, need(h, "h_norm.gain", {H}, &gn));
+    CKS(h, need(h, "h_norm.bias", {H}, &bs));
+    h->ln_gain = gn->d;
+    h->ln_bias = bs->d;
+    return CAPDEC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ per-arch steps
+struct StepCtx {
+    int M = 0;         // rows = B * rows_per_image
+    int K = 0;         // rows per image
+    int t = 0;         // 1-based step
+    int cur = 0;       // cell-state ping-pong index (read cur, write cur^1)
+    int logits_epi = EPI_TOPK;
+    int ktop = 4;
+    uint32_t seed = 0;
+    int use_noise = 0;
+    bool first_from_c0 = false;
+};
+
+int run_logits(capdec_handle* h, const Act16& a, const StepCtx& c, cudaStream_t st) {
+    CUtensorMap ma, mb;
+    CKS(h, map_a(h, &ma, a));
+    CKS(h, map_b(h, &mb, h->W_pred));
+    EpiParams e{};
+    e.bias = h->b_pred;
+    e.part = h->part;
+    e.n_tiles = h->n_tiles_v;
+    e.seed = c.seed;
+    e.step = c.t - 1;
+    e.use_noise = c.use_noise;
+    return launch_gemm(h, c.logits_epi, c.ktop, ma, a.lo, mb, h->W_pred.lo, c.M, h->V, h->H, e, st);
+}
+
+template <int KR>
+int launch_butd_att(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
+    static bool attr_set = false;
+    auto kern = butd_attention_kernel<KR>;
+    const size_t smem = (static_cast<size_t>(KR) * h->A + h->A + static_cast<size_t>(KR) * h->R) * sizeof(float);
+    if (!attr_set) {
+        CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_set = true;
+    }
+    if (smem > 160 * 1024) return fail(h, CAPDEC_ERR_INVALID, "attention tile does not fit shared memory");
+    kern<<<h->B, 256, smem, st>>>(h->enc_ctx, h->feats, h->dec_ctx, h->w_aff, h->b_aff, h->R, h->A, h->D, c.K, h->XB.p, h->XB.ld,
+                                  h->XB.lo, nullptr);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    return CAPDEC_OK;
+}
+
+template <int KR>
+int launch_aoa_att(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
+    static bool attr_set = false;
+    auto kern = aoa_attention_kernel<KR>;
+    const size_t smem = (static_cast<size_t>(KR) * h->H + static_cast<size_t>(KR) * h->NH * h->R) * sizeof(float);
+    if (!attr_set) {
+        CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_set = true;
+    }
+    if (smem > 160 * 1024) return fail(h, CAPDEC_ERR_INVALID, "attention tile does not fit shared memory");
+    kern<<<h->B, 256, smem, st>>>(h->q32, h->kv32, h->mask, h->R, h->H, h->NH, c.K, h->XB.p, h->XB.ld, h->XB.lo);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    return CAPDEC_OK;
+}
+
+// BUTD: XA = [h2 | emb | h1] (top-down LSTM operand), XB = [ctx | h1 | h2] (language LSTM operand), Hb2 = new h2.
+int step_butd(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
+    const int H = h->H, E = h->E, A = h->A, D = h->D;
+    CUtensorMap ma, mb;
+    {  // top-down attention LSTM (BUTD_Model.py:265)
+        CKS(h, map_a(h, &ma, h->XA));
+        CKS(h, map_b(h, &mb, h->W_l1));
+        EpiParams e{};
+        e.rowadd = h->G0;
+        e.rowadd_ld = 4 * H;
+        e.rows_per_group = c.K;
+        e.c_in = h->c1[c.cur];
+        e.c_out = h->c1[c.cur ^ 1];
+        e.ldc = H;
+        e.parent = h->parent;
+        e.out16 = h->XB.p + D;
+        e.ld16 = h->XB.ld;
+        e.lo16 = h->XB.lo;
+        CKS(h, launch_gemm(h, EPI_LSTM, 1, ma, h->XA.lo, mb, h->W_l1.lo, c.M, 4 * H, H + E + H, e, st));
+    }
+    {  // dec_att(h1) (BUTD_Model.py:58)
+        CKS(h, map_a(h, &ma, h->XB, D));
+        CKS(h, map_b(h, &mb, h->W_aux2));
+        EpiParams e{};
+        e.bias = h->b_aux2;
+        e.out32 = h->dec_ctx;
+        e.ld32 = A;
+        CKS(h, launch_gemm(h, EPI_STORE, 1, ma, h->XB.lo, mb, h->W_aux2.lo, c.M, A, H, e, st));
+    }
+    if (c.K <= 1) CKS(h, launch_butd_att<1>(h, c, st));
+    else if (c.K <= 3) CKS(h, launch_butd_att<3>(h, c, st));
+    else if (c.K <= 5) CKS(h, launch_butd_att<5>(h, c, st));
+    else CKS(h, launch_butd_att<8>(h, c, st));
+    {  // language LSTM (BUTD_Model.py:268)
+        CKS(h, map_a(h, &ma, h->XB));
+        CKS(h, map_b(h, &mb, h->W_l2));
+        EpiParams e{};
+        e.bias = h->b_l2;
+        e.c_in = h->c2[c.cur];
+        e.c_out = h->c2[c.cur ^ 1];
+        e.ldc = H;
+        e.parent = h->parent;
+        e.out16 = h->Hb2.p;
+        e.ld16 = h->Hb2.ld;
+        e.lo16 = h->Hb2.lo;
+        CKS(h, launch_gemm(h, EPI_LSTM, 1, ma, h->XB.lo, mb, h->W_l2.lo, c.M, 4 * H, D + H + H, e, st));
+    }
+    return run_logits(h, h->Hb2, c, st);
+}
+
+AdvOp op_copy(const Act16& src, int src_col, const Act16& dst, int dst_col, int n) {
+    AdvOp o{};
+    o.kind = ADV_COPY16;
+    o.src = src.p + src_col;
+    o.src_ld = src.ld;
+    o.src_lo = src.lo;
+    o.dst = dst.p + dst_col;
+    o.dst_ld = dst.ld;
+    o.dst_lo = dst.lo;
+    o.n = n;
+    return o;
+}
+AdvOp op_embed(const float* table, int E, const Act16& dst, int dst_col, int relu) {
+    AdvOp o{};
+    o.kind = ADV_EMBED;
+    o.src = table;
+    o.src_ld = E;
+    o.dst = dst.p + dst_col;
+    o.dst_ld = dst.ld;
+    o.dst_lo = dst.lo;
+    o.n = E;
+    o.flag = relu;
+    return o;
+}
+
+AdvOps adv_butd(capdec_handle* h, bool init) {
+    const int H = h->H, E = h->E, D = h->D;
+    AdvOps a{};
+    a.op[a.n++] = op_embed(h->embed, E, h->XA, H, 1);
+    if (!init) {
+        a.op[a.n++] = op_copy(h->Hb2, 0, h->XA, 0, H);      // h2 -> top-down operand
+        a.op[a.n++] = op_copy(h->Hb2, 0, h->XB, D + H, H);  // h2 -> language operand (recurrent part)
+        a.op[a.n++] = op_copy(h->XB, D, h->XA, H + E, H);   // h1 -> top-down operand (recurrent part)
+    }
+    return a;
+}
+
+// NIC: XA = [emb | h], Hb = new h.
+int step_nic(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
+    const int H = h->H, E = h->E;
+    CUtensorMap ma, mb;
+    CKS(h, map_a(h, &ma, h->XA));
+    CKS(h, map_b(h, &mb, h->W_l1));
+    EpiParams e{};
+    e.bias = h->b_l1;
+    e.c_in = c.first_from_c0 ? h->c0 : h->c1[c.cur];
+    e.c_out = h->c1[c.cur ^ 1];
+    e.ldc = H;
+    e.parent = h->parent;
+    e.out16 = h->Hb.p;
+    e.ld16 = h->Hb.ld;
+    e.lo16 = h->Hb.lo;
+    CKS(h, launch_gemm(h, EPI_LSTM, 1, ma, h->XA.lo, mb, h->W_l1.lo, c.M, 4 * H, E + H, e, st));
+    return run_logits(h, h->Hb, c, st);
+}
+
+AdvOps adv_nic(capdec_handle* h, bool init) {
+    const int H = h->H, E = h->E;
+    AdvOps a{};
+    a.op[a.n++] = op_embed(h->embed, E, h->XA, 0, 0);
+    if (init) {
+        AdvOp o = op_copy(h->H0, 0, h->XA, E, H);  // primed hidden state of the image (NIC_Model.py:164,170)
+        o.kind = ADV_BCAST16;
+        a.op[a.n++] = o;
+    } else {
+        a.op[a.n++] = op_copy(h->Hb, 0, h->XA, E, H);
+    }
+    return a;
+}
+
+// AoA: XA = [emb | mean+ctx | h] (LSTM operand), XB = [att | query] (AoA gate operand), Hb = new h, Hb2 = ctx fp16.
+int step_aoa(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
+    const int H = h->H, E = h->E;
+    CUtensorMap ma, mb;
+    {
+        CKS(h, map_a(h, &ma, h->XA));
+        CKS(h, map_b(h, &mb, h->W_l1));
+        EpiParams e{};
+        e.bias = h->b_l1;
+        e.c_in = h->c1[c.cur];
+        e.c_out = h->c1[c.cur ^ 1];
+        e.ldc = H;
+        e.parent = h->parent;
+        e.out16 = h->Hb.p;
+        e.ld16 = h->Hb.ld;
+        e.lo16 = h->Hb.lo;
+        e.h32 = h->h32;
+        e.ldh32 = H;
+        CKS(h, launch_gemm(h, EPI_LSTM, 1, ma, h->XA.lo, mb, h->W_l1.lo, c.M, 4 * H, E + H + H, e, st));
+    }
+    aoa_layernorm_kernel<<<(c.M + 7) / 8, 256, 0, st>>>(h->h32, c.M, H, h->ln_gain, h->ln_bias, 1e-6f, h->XB.p + H, h->XB.ld,
+                                                        h->XB.lo);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    {  // linear_Q (AoA_Model.py:113)
+        CKS(h, map_a(h, &ma, h->XB, H));
+        CKS(h, map_b(h, &mb, h->W_aux1));
+        EpiParams e{};
+        e.bias = h->b_aux1;
+        e.out32 = h->q32;
+        e.ld32 = H;
+        CKS(h, launch_gemm(h, EPI_STORE, 1, ma, h->XB.lo, mb, h->W_aux1.lo, c.M, H, H, e, st));
+    }
+    if (c.K <= 1) CKS(h, launch_aoa_att<1>(h, c, st));
+    else if (c.K <= 3) CKS(h, launch_aoa_att<3>(h, c, st));
+    else if (c.K <= 5) CKS(h, launch_aoa_att<5>(h, c, st));
+    else CKS(h, launch_aoa_att<8>(h, c, st));
+    {  // AoA gate: GLU(Linear(cat[att, query])) (AoA_Model.py:118)
+        CKS(h, map_a(h, &ma, h->XB));
+        CKS(h, map_b(h, &mb, h->W_aux3));
+        EpiParams e{};
+        e.bias = h->b_aux3;
+        e.out32 = h->ctx32;
+        e.ld32 = H;
+        e.out16 = h->Hb2.p;
+        e.ld16 = h->Hb2.ld;
+        e.lo16 = h->Hb2.lo;
+        CKS(h, launch_gemm(h, EPI_GLU, 1, ma, h->XB.lo, mb, h->W_aux3.lo, c.M, 2 * H, 2 * H, e, st));
+    }
+    return run_logits(h, h->Hb2, c, st);
+}
+
+AdvOps adv_aoa(capdec_handle* h, bool init) {
+    const int H = h->H, E = h->E;
+    AdvOps a{};
+    a.op[a.n++] = op_embed(h->embed, E, h->XA, 0, 1);
+    AdvOp m{};
+    m.kind = ADV_MEAN_PLUS;
+    m.src = init ? nullptr : h->ctx32;
+    m.src_ld = H;
+    m.aux = h->mean32;
+    m.dst = h->XA.p + E;
+    m.dst_ld = h->XA.ld;
+    m.dst_lo = h->XA.lo;
+    m.n = H;
+    a.op[a.n++] = m;
+    if (!init) a.op[a.n++] = op_copy(h->Hb, 0, h->XA, E + H, H);
+    return a;
+}
+
+int run_step(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
+    switch (h->cfg.arch) {
+        case CAPDEC_ARCH_BUTD: return step_butd(h, c, st);
+        case CAPDEC_ARCH_NIC: return step_nic(h, c, st);
+        default: return step_aoa(h, c, st);
+    }
+}
+AdvOps adv_ops(capdec_handle* h, bool init) {
+    switch (h->cfg.arch) {
+        case CAPDEC_ARCH_BUTD: return adv_butd(h, init);
+        case CAPDEC_ARCH_NIC: return adv_nic(h, init);
+        default: return adv_aoa(h, init);
+    }
+}
+
+// zero the recurrent operand slots and the cell state before a decode (states start at 0:
+// BUTD_Model.py:92-95,261-262; AoA_Model.py:223-227)
+int reset_state(capdec_handle* h, int M, cudaStream_t st) {
+    CK(h, cudaMemsetAsync(h->XA.p, 0, static_cast<size_t>(M) * h->XA.ld * sizeof(__half), st));
+    if (h->XB.p) CK(h, cudaMemsetAsync(h->XB.p, 0, static_cast<size_t>(M) * h->XB.ld * sizeof(__half), st));
+    CK(h, cudaMemsetAsync(h->c1[0], 0, static_cast<size_t>(M) * h->H * sizeof(float), st));
+    if (h->c2[0]) CK(h, cudaMemsetAsync(h->c2[0], 0, static_cast<size_t>(M) * h->H * sizeof(float), st));
+    return CAPDEC_OK;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int capdec_abi_version(void) { return CAPDEC_ABI_VERSION; }
+
+const char* capdec_last_error(const capdec_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int64_t capdec_launch_count(const capdec_handle* h) { return h ? h->launches : 0; }
+
+void capdec_destroy(capdec_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    for (void* p : h->allocs) cudaFree(p);
+    for (auto& kv : h->raw) cudaFree(kv.second.d);
+    delete h;
+}
+
+static int create_impl(capdec_handle* h) {
+    const capdec_config& c = h->cfg;
+    if (c.arch < 0 || c.arch > 2) return fail(h, CAPDEC_ERR_INVALID, "unknown arch");
+    h->H = c.hidden_dim, h->E = c.embed_dim, h->A = c.atten_dim, h->D = c.enc_dim, h->V = c.vocab_size, h->NH = c.num_heads;
+    h->Bmax = c.max_batch, h->Rmax = c.max_regions, h->Kmax = c.max_rows, h->Tmax = c.max_seq;
+    h->split = c.math_mode == CAPDEC_MATH_F16X3;
+    if (c.math_mode != CAPDEC_MATH_F16 && c.math_mode != CAPDEC_MATH_F16X3) return fail(h, CAPDEC_ERR_INVALID, "unknown math_mode");
+    const int H = h->H, E = h->E, V = h->V;
+    if (H <= 0 || H % 64 || E <= 0 || E % 64) return fail(h, CAPDEC_ERR_INVALID, "hidden_dim and embed_dim must be multiples of 64");
+    if (V < 4) return fail(h, CAPDEC_ERR_INVALID, "vocab_size must be >= 4");
+    if (h->Bmax <= 0 || h->Tmax <= 0 || h->Kmax <= 0 || h->Kmax > MAX_ROWS)
+        return fail(h, CAPDEC_ERR_INVALID, "max_batch/max_seq must be > 0 and 1 <= max_rows <= 8");
+    if (c.arch == CAPDEC_ARCH_BUTD && (h->A <= 0 || h->A % 64 || h->D <= 0 || h->D % 64 || h->Rmax <= 0))
+        return fail(h, CAPDEC_ERR_INVALID, "BUTD needs atten_dim, enc_dim multiples of 64 and max_regions > 0");
+    if (c.arch == CAPDEC_ARCH_AOA) {
+        if (h->NH <= 0 || H % h->NH || h->Rmax <= 0) return fail(h, CAPDEC_ERR_INVALID, "AoA needs hidden_dim % num_heads == 0");
+        const int d = H / h->NH;
+        if (d % 4 || ((d / 4) & (d / 4 - 1))) return fail(h, CAPDEC_ERR_INVALID, "AoA head dim / 4 must be a power of two");
+    }
+    CK(h, cudaSetDevice(c.device));
+    cudaDeviceProp prop;
+    CK(h, cudaGetDeviceProperties(&prop, c.device));
+    if (prop.major != 10) return fail(h, CAPDEC_ERR_CUDA, "libcapdec needs an sm_100a (B200) device; there is no fallback path");
+    h->num_sms = prop.multiProcessorCount;
+    h->Mmax = h->Bmax * h->Kmax;
+    h->n_tiles_v = (V + BN - 1) / BN;
+    const int M = h->Mmax;
+
+    CKS(h, dalloc(h, &h->scale_tmp, static_cast<size_t>(V > 4 * H ? V : 4 * H)));
+    CKS(h, alloc_act(h, &h->W_pred, V, H));
+    CKS(h, dalloc(h, &h->b_pred, V));
+    CKS(h, dalloc(h, &h->b_l1, 4 * H));
+    const size_t part_stride = topk_part_stride(8) > SAMPLE_PART_STRIDE ? topk_part_stride(8) : SAMPLE_PART_STRIDE;
+    CKS(h, dalloc(h, &h->part, static_cast<size_t>(M) * h->n_tiles_v * part_stride));
+    CKS(h, dalloc(h, &h->c1[0], static_cast<size_t>(M) * H));
+    CKS(h, dalloc(h, &h->c1[1], static_cast<size_t>(M) * H));
+    CKS(h, dalloc(h, &h->tok, M));
+    CKS(h, dalloc(h, &h->parent, M));
+    CKS(h, dalloc(h, &h->cum, M));
+    CKS(h, dalloc(h, &h->unfinished, M));
+    CKS(h, dalloc(h, &h->live_count, h->Tmax + 1));
+    CKS(h, dalloc(h, &h->n_live, h->Bmax));
+    CKS(h, dalloc(h, &h->best_score, h->Bmax));
+    CKS(h, dalloc(h, &h->best_len, h->Bmax));
+    CKS(h, dalloc(h, &h->best_seq, static_cast<size_t>(h->Bmax) * (h->Tmax + 1)));
+    CKS(h, dalloc(h, &h->seqs[0], static_cast<size_t>(M) * (h->Tmax + 1)));
+    CKS(h, dalloc(h, &h->seqs[1], static_cast<size_t>(M) * (h->Tmax + 1)));
+
+    if (c.arch == CAPDEC_ARCH_BUTD) {
+        const int A = h->A, D = h->D;
+        const size_t BR = static_cast<size_t>(h->Bmax) * h->Rmax;
+        CKS(h, alloc_act(h, &h->W_l1, 4 * H, H + E + H));
+        CKS(h, alloc_act(h, &h->W_l2, 4 * H, D + H + H));
+        CKS(h, alloc_act(h, &h->W_aux1, A, D));
+        CKS(h, alloc_act(h, &h->W_aux2, A, H));
+        CKS(h, alloc_act(h, &h->W_aux3, 4 * H, D));
+        CKS(h, dalloc(h, &h->b_l2, 4 * H));
+        CKS(h, dalloc(h, &h->b_aux1, A));
+        CKS(h, dalloc(h, &h->b_aux2, A));
+        CKS(h, dalloc(h, &h->w_aff, A));
+        CKS(h, alloc_act(h, &h->feats16, static_cast<int>(BR), D));
+        CKS(h, alloc_act(h, &h->mean16, h->Bmax, D));
+        CKS(h, dalloc(h, &h->enc_ctx, BR * A));
+        CKS(h, dalloc(h, &h->G0, static_cast<size_t>(h->Bmax) * 4 * H));
+        CKS(h, alloc_act(h, &h->XA, M, H + E + H));
+        CKS(h, alloc_act(h, &h->XB, M, D + H + H));
+        CKS(h, alloc_act(h, &h->Hb2, M, H));
+        CKS(h, dalloc(h, &h->dec_ctx, static_cast<size_t>(M) * A));
+        CKS(h, dalloc(h, &h->c2[0], static_cast<size_t>(M) * H));
+        CKS(h, dalloc(h, &h->c2[1], static_cast<size_t>(M) * H));
+    } else if (c.arch == CAPDEC_ARCH_NIC) {
+        CKS(h, alloc_act(h, &h->W_l1, 4 * H, E + H));
+        CKS(h, alloc_act(h, &h->XA, M, E + H));
+        CKS(h, alloc_act(h, &h->Hb, M, H));
+        CKS(h, alloc_act(h, &h->Xp, h->Bmax, E + H));
+        CKS(h, alloc_act(h, &h->H0, h->Bmax, H));
+        CKS(h, dalloc(h, &h->c0, static_cast<size_t>(h->Bmax) * H));
+    } else {
+        const size_t BR = static_cast<size_t>(h->Bmax) * h->Rmax;
+        CKS(h, alloc_act(h, &h->W_l1, 4 * H, E + H + H));
+        CKS(h, alloc_act(h, &h->W_aux1, H, H));
+        CKS(h, alloc_act(h, &h->W_aux2, 2 * H, H));
+        CKS(h, alloc_act(h, &h->W_aux3, 2 * H, 2 * H));
+        CKS(h, dalloc(h, &h->b_aux1, H));
+        CKS(h, dalloc(h, &h->b_aux2, 2 * H));
+        CKS(h, dalloc(h, &h->b_aux3, 2 * H));
+        CKS(h, alloc_act(h, &h->feats16, static_cast<int>(BR), H));
+        CKS(h, dalloc(h, &h->kv32, BR * 2 * H));
+        CKS(h, dalloc(h, &h->mean32, static_cast<size_t>(h->Bmax) * H));
+        CKS(h, alloc_act(h, &h->XA, M, E + H + H));
+        CKS(h, alloc_act(h, &h->XB, M, 2 * H));
+        CKS(h, alloc_act(h, &h->Hb, M, H));
+        CKS(h, alloc_act(h, &h->Hb2, M, H));
+        CKS(h, dalloc(h, &h->q32, static_cast<size_t>(M) * H));
+        CKS(h, dalloc(h, &h->ctx32, static_cast<size_t>(M) * H));
+        CKS(h, dalloc(h, &h->h32, static_cast<size_t>(M) * H));
+    }
+    return CAPDEC_OK;
+}
+
+int capdec_create(const capdec_config* cfg, capdec_handle** out) {
+    if (!cfg || !out) {
+        g_create_error = "null argument";
+        return CAPDEC_ERR_INVALID;
+    }
+    capdec_handle* h = new capdec_handle();
+    h->cfg = *cfg;
+    const int s = create_impl(h);
+    if (s != CAPDEC_OK) {
+        g_create_error = h->err;
+        capdec_destroy(h);
+        *out = nullptr;
+        return s;
+    }
+    *out = h;
+    return CAPDEC_OK;
+}
+
+int capdec_load_weight(capdec_handle* h, const char* name, const float* data, const int64_t* shape, int32_t ndim, void* stream) {
+    if (!h || !name || !data || !shape || ndim < 1 || ndim > 4) return h ? fail(h, CAPDEC_ERR_INVALID, "bad load_weight argument") : CAPDEC_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(h, cudaSetDevice(h->cfg.device));
+    Raw r;
+    r.numel = 1;
+    for (int i = 0; i < ndim; ++i) {
+        if (shape[i] <= 0) return fail(h, CAPDEC_ERR_INVALID, std::string("bad shape for ") + name);
+        r.shape.push_back(shape[i]);
+        r.numel *= static_cast<size_t>(shape[i]);
+    }
+    auto it = h->raw.find(name);
+    if (it != h->raw.end()) {
+        cudaFree(it->second.d);
+        h->raw.erase(it);
+    }
+    CK(h, cudaMalloc(reinterpret_cast<void**>(&r.d), r.numel * sizeof(float)));
+    cudaError_t e = cudaMemcpyAsync(r.d, data, r.numel * sizeof(float), cudaMemcpyDefault, st);
+    if (e == cudaSuccess) {
+        cudaPointerAttributes pa;
+        // pageable / pinned host memory: make the copy complete before the caller may reuse the buffer
+        if (cudaPointerGetAttributes(&pa, data) != cudaSuccess || pa.type != cudaMemoryTypeDevice) e = cudaStreamSynchronize(st);
+        cudaGetLastError();
+    }
+    if (e != cudaSuccess) {
+        cudaFree(r.d);
+        return fail(h, CAPDEC_ERR_CUDA, std::string("copy of ") + name + ": " + cudaGetErrorString(e));
+    }
+    h->raw[name] = r;
+    h->weights_ready = false;
+    return CAPDEC_OK;
+}
+
+int capdec_finalize_weights(capdec_handle* h, void* stream) {
+    if (!h) return CAPDEC_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(h, cudaSetDevice(h->cfg.device));
+    CKS(h, finalize_predict(h, st));
+    if (h->cfg.arch == CAPDEC_ARCH_BUTD) CKS(h, finalize_butd(h, st));
+    else if (h->cfg.arch == CAPDEC_ARCH_NIC) CKS(h, finalize_nic(h, st));
+    else CKS(h, finalize_aoa(h, st));
+    CK(h, cudaStreamSynchronize(st));  // b_aff is read back; packing is a one-time load cost
+    h->weights_ready = true;
+    return CAPDEC_OK;
+}
+
+int capdec_prepare(capdec_handle* h, const float* feats, const float* mask, int32_t batch, int32_t regions, void* stream) {
+    if (!h) return CAPDEC_ERR_INVALID;
+    if (!h->weights_ready) return fail(h, CAPDEC_ERR_STATE, "capdec_prepare before capdec_finalize_weights");
+    if (!feats || batch <= 0 || batch > h->Bmax) return fail(h, CAPDEC_ERR_INVALID, "prepare: batch out of range or null feats");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(h, cudaSetDevice(h->cfg.device));
+    const int H = h->H, E = h->E;
+    h->prepared = false;
+    CUtensorMap ma, mb;
+    if (h->cfg.arch == CAPDEC_ARCH_NIC) {
+        // priming step: (h,c) = lstm(image_embedding, (0,0))  (NIC_Model.py:52-56)
+        cvt_f16_kernel<<<grid_for(static_cast<size_t>(batch) * E / 4), 256, 0, st>>>(feats, batch, E, h->Xp.p, h->Xp.ld, h->Xp.lo, 0);
+        CK(h, cudaGetLastError());
+        h->launches++;
+        CKS(h, map_a(h, &ma, h->Xp));
+        CKS(h, map_b(h, &mb, h->W_l1));
+        EpiParams e{};
+        e.bias = h->b_l1;
+        e.c_out = h->c0;
+        e.ldc = H;
+        e.out16 = h->H0.p;
+        e.ld16 = h->H0.ld;
+        e.lo16 = h->H0.lo;
+        CKS(h, launch_gemm(h, EPI_LSTM, 1, ma, h->Xp.lo, mb, h->W_l1.lo, batch, 4 * H, E + H, e, st));
+        h->R = 0;
+    } else {
+        if (regions <= 0 || regions > h->Rmax) return fail(h, CAPDEC_ERR_INVALID, "prepare: regions out of range");
+        const size_t BR = static_cast<size_t>(batch) * regions;
+        if (h->cfg.arch == CAPDEC_ARCH_BUTD) {
+            const int A = h->A, D = h->D;
+            if (mask) return fail(h, CAPDEC_ERR_INVALID, "BUTD takes no region mask");
+            cvt_f16_kernel<<<grid_for(BR * D / 4), 256, 0, st>>>(feats, BR, D, h->feats16.p, h->feats16.ld, h->feats16.lo, 0);
+            CK(h, cudaGetLastError());
+            region_mean_kernel<<<batch, 256, 0, st>>>(feats, nullptr, regions, D, nullptr, h->mean16.p, h->mean16.ld, h->mean16.lo);
+            CK(h, cudaGetLastError());
+            h->launches += 2;
+            {  // enc_att(feats): once per image instead of once per step and beam (BUTD_Model.py:57)
+                CKS(h, map_a(h, &ma, h->feats16));
+                CKS(h, map_b(h, &mb, h->W_aux1));
+                EpiParams e{};
+                e.bias = h->b_aux1;
+                e.out32 = h->enc_ctx;
+                e.ld32 = A;
+                CKS(h, launch_gemm(h, EPI_STORE, 1, ma, h->feats16.lo, mb, h->W_aux1.lo, static_cast<int>(BR), A, D, e, st));
+            }
+            {  // hoisted, step-invariant part of the top-down LSTM gates: W_ih[:, mean] * mean + b_ih + b_hh
+                CKS(h, map_a(h, &ma, h->mean16));
+                CKS(h, map_b(h, &mb, h->W_aux3));
+                EpiParams e{};
+                e.bias = h->b_l1;
+                e.out32 = h->G0;
+                e.ld32 = 4 * H;
+                CKS(h, launch_gemm(h, EPI_STORE, 1, ma, h->mean16.lo, mb, h->W_aux3.lo, batch, 4 * H, D, e, st));
+            }
+        } else {
+            cvt_f16_kernel<<<grid_for(BR * H / 4), 256, 0, st>>>(feats, BR, H, h->feats16.p, h->feats16.ld, h->feats16.lo, 0);
+            CK(h, cudaGetLastError());
+            region_mean_kernel<<<batch, 256, 0, st>>>(feats, mask, regions, H, h->mean32, nullptr, 0, 0);
+            CK(h, cudaGetLastError());
+            h->launches += 2;
+            CKS(h, map_a(h, &ma, h->feats16));
+            CKS(h, map_b(h, &mb, h->W_aux2));
+            EpiParams e{};
+            e.bias = h->b_aux2;
+            e.out32 = h->kv32;
+            e.ld32 = 2 * H;
+            CKS(h, launch_gemm(h, EPI_STORE, 1, ma, h->feats16.lo, mb, h->W_aux2.lo, static_cast<int>(BR), 2 * H, H, e, st));
+        }
+        h->R = regions;
+    }
+    h->B = batch;
+    h->feats = feats;
+    h->mask = mask;
+    h->prepared = true;
+    return CAPDEC_OK;
+}
+
+int capdec_beam_search(capdec_handle* h, int32_t beam, int32_t max_seq, int32_t* tokens, float* seq_logprob, int32_t* lengths,
+                       float* alphas, void* stream) {
+    if (!h) return CAPDEC_ERR_INVALID;
+    if (!h->prepared) return fail(h, CAPDEC_ERR_STATE, "capdec_beam_search before capdec_prepare");
+    if (beam <= 0 || beam > h->Kmax || max_seq <= 0 || max_seq > h->Tmax || !tokens)
+        return fail(h, CAPDEC_ERR_INVALID, "beam_search: beam / max_seq out of range or null tokens");
+    if (alphas) return fail(h, CAPDEC_ERR_INVALID, "alphas output is reserved; pass NULL");
+    if (static_cast<int64_t>(beam) * h->V < beam) return fail(h, CAPDEC_ERR_INVALID, "beam larger than vocabulary");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(h, cudaSetDevice(h->cfg.device));
+    const int B = h->B, K = beam, M = B * K;
+    CKS(h, reset_state(h, M, st));
+    BeamState s{};
+    s.B = B, s.K = K, s.V = h->V, s.T = max_seq;
+    s.tok = h->tok, s.cum = h->cum, s.parent = h->parent, s.n_live = h->n_live;
+    s.best_score = h->best_score, s.best_seq = h->best_seq, s.best_len = h->best_len;
+    s.seqs_in = h->seqs[0], s.seqs_out = h->seqs[1];
+    const bool nic = h->cfg.arch == CAPDEC_ARCH_NIC;
+    // NIC: step 1 reads the primed cell state of the image, so parent[row] starts as the image index into c0
+    beam_init_kernel<<<B, 128, 0, st>>>(s, adv_ops(h, true), nic ? 1 : 0);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    StepCtx c{};
+    c.M = M, c.K = K, c.logits_epi = EPI_TOPK, c.ktop = ktop_for(K);
+    const AdvOps ops = adv_ops(h, false);
+    for (int t = 1; t <= max_seq; ++t) {
+        c.t = t;
+        c.cur = (t - 1) & 1;
+        c.first_from_c0 = nic && t == 1;
+        CKS(h, run_step(h, c, st));
+        s.seqs_in = h->seqs[(t + 1) & 1];
+        s.seqs_out = h->seqs[t & 1];
+        if (c.ktop == 4) beam_step_kernel<4><<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t, ops);
+        else beam_step_kernel<8><<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t, ops);
+        CK(h, cudaGetLastError());
+        h->launches++;
+    }
+    beam_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(s, h->seqs[max_seq & 1], tokens, seq_logprob, lengths);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    return CAPDEC_OK;
+}
+
+int capdec_sample(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t seed, int32_t max_seq, int32_t* tokens,
+                  float* logprobs, void* stream) {
+    if (!h) return CAPDEC_ERR_INVALID;
+    if (!h->prepared) return fail(h, CAPDEC_ERR_STATE, "capdec_sample before capdec_prepare");
+    if (n_per_image <= 0 || n_per_image > h->Kmax || max_seq <= 0 || max_seq > h->Tmax || !tokens)
+        return fail(h, CAPDEC_ERR_INVALID, "sample: n_per_image / max_seq out of range or null tokens");
+    if (mode != CAPDEC_SAMPLE_GREEDY && mode != CAPDEC_SAMPLE_MULTINOMIAL) return fail(h, CAPDEC_ERR_INVALID, "unknown sample mode");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(h, cudaSetDevice(h->cfg.device));
+    const int B = h->B, n = n_per_image, M = B * n;
+    CKS(h, reset_state(h, M, st));
+    CK(h, cudaMemsetAsync(tokens, 0, static_cast<size_t>(M) * max_seq * sizeof(int32_t), st));
+    if (logprobs) CK(h, cudaMemsetAsync(logprobs, 0, static_cast<size_t>(M) * max_seq * sizeof(float), st));
+    SampleState s{};
+    s.B = B, s.n = n, s.V = h->V, s.T = max_seq;
+    s.tok = h->tok, s.unfinished = h->unfinished, s.live_count = h->live_count, s.parent = h->parent;
+    s.tokens = tokens, s.logprobs = logprobs;
+    s.multinomial = mode == CAPDEC_SAMPLE_MULTINOMIAL;
+    const bool nic = h->cfg.arch == CAPDEC_ARCH_NIC;
+    sample_init_kernel<<<B, 128, 0, st>>>(s, adv_ops(h, true), nic ? 1 : 0);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    StepCtx c{};
+    c.M = M, c.K = n, c.logits_epi = EPI_SAMPLE, c.ktop = 1;
+    c.seed = static_cast<uint32_t>(seed & 0xFFFFFFFFu);
+    c.use_noise = s.multinomial;
+    const AdvOps ops = adv_ops(h, false);
+    for (int t = 1; t <= max_seq; ++t) {
+        c.t = t;
+        c.cur = (t - 1) & 1;
+        c.first_from_c0 = nic && t == 1;
+        CKS(h, run_step(h, c, st));
+        sample_step_kernel<<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t - 1, ops);
+        CK(h, cudaGetLastError());
+        h->launches++;
+    }
+    return CAPDEC_OK;
+}
+
+int capdec_test_gemm(const float* a, const float* b, const float* bias, float* d, int32_t m, int32_t n, int32_t k, int32_t math_mode,
+                     void* stream) {
+    capdec_handle tmp;
+    capdec_handle* h = &tmp;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) {
+        g_create_error = "capdec_test_gemm needs an sm_100a device";
+        return CAPDEC_ERR_CUDA;
+    }
+    h->cfg.device = dev;
+    h->num_sms = prop.multiProcessorCount;
+    h->split = math_mode == CAPDEC_MATH_F16X3;
+    int status = CAPDEC_OK;
+    Act16 A16, B16;
+    do {
+        if ((status = alloc_act(h, &A16, m, k)) != CAPDEC_OK) break;
+        if ((status = alloc_act(h, &B16, n, k)) != CAPDEC_OK) break;
+        cvt_f16_kernel<<<grid_for(static_cast<size_t>(m) * k / 4), 256, 0, st>>>(a, m, k, A16.p, A16.ld, A16.lo, 0);
+        cvt_f16_kernel<<<grid_for(static_cast<size_t>(n) * k / 4), 256, 0, st>>>(b, n, k, B16.p, B16.ld, B16.lo, 0);
+        CUtensorMap ma, mb;
+        if ((status = map_a(h, &ma, A16)) != CAPDEC_OK) break;
+        if ((status = map_b(h, &mb, B16)) != CAPDEC_OK) break;
+        EpiParams e{};
+        e.bias = bias;
+        e.out32 = d;
+        e.ld32 = n;
+        if ((status = launch_gemm(h, EPI_STORE, 1, ma, A16.lo, mb, B16.lo, m, n, k, e, st)) != CAPDEC_OK) break;
+        cudaError_t ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) {
+            h->err = std::string("test gemm: ") + cudaGetErrorString(ce);
+            status = CAPDEC_ERR_CUDA;
+        }
+    } while (0);
+    for (void* p : h->allocs) cudaFree(p);
+    if (status != CAPDEC_OK) g_create_error = h->err;
+    return status;
+}
+
+}  // extern "C"

@@ -1,0 +1,510 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a with fused decode-step epilogues.
+//
+//   D[M,N] = A[M,K] * B[N,K]^T      A, B fp16 K-major (row-major, K contiguous), fp32 accumulate in TMEM
+//
+// Roles (192 threads, one CTA per SM):  warp 0 = TMA producer, warp 1 = TMEM owner + tcgen05.mma issuer,
+// warps 2-5 = epilogue (each owns one 32-lane quarter of the 128-row accumulator; thread == output row).
+// Pipelines: smem ring full/empty (TMA <-> MMA) and a 2-deep TMEM accumulator ring (MMA <-> epilogue), so
+// the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// "Split" math mode (fp32-grade): every operand is stored as fp16 hi | fp16 lo (lo at +lo_off columns) and
+// the K loop runs three passes hi*hi + hi*lo + lo*hi into the same fp32 accumulator.
+//
+// Epilogues (what the reference computes after each Linear / LSTMCell):
+//   EPI_STORE  bias add -> fp32 (+fp16) store                      (enc_att / dec_att / Q / K,V projections)
+//   EPI_LSTM   gate-interleaved columns -> LSTMCell pointwise      (BUTD_Model.py:265,268; NIC_Model.py:173)
+//   EPI_GLU    (a,gate)-interleaved columns -> a*sigmoid(gate)     (AoA_Model.py:118)
+//   EPI_TOPK   bias add -> per-row running (max, sum-exp) + top-K  (predict + log_softmax + topk, :270-276)
+//   EPI_SAMPLE bias add -> per-row (max, sum-exp) + Gumbel-max     (sample / sample_rl, :183, :221-224)
+#pragma once
+#include "ptx.cuh"
+
+namespace capdec {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 fp16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+
+enum EpiKind { EPI_STORE = 0, EPI_LSTM = 1, EPI_GLU = 2, EPI_TOPK = 3, EPI_SAMPLE = 4 };
+
+struct EpiParams {
+    // common
+    const float* bias;      // [N] (in the packed column order) or null
+    // STORE / GLU
+    float* out32;           // fp32 output or null
+    int ld32;
+    __half* out16;          // fp16 output (hi at col, lo at col+lo16 when lo16 > 0) or null
+    int ld16;
+    int lo16;
+    // LSTM
+    const float* rowadd;    // additive per-row-group term [M/rows_per_group, N] or null (hoisted, step-invariant part)
+    int rowadd_ld;
+    int rows_per_group;
+    const float* c_in;      // [.., H] previous cell state (null = zeros)
+    float* c_out;           // [M, H]
+    int ldc;
+    const int* parent;      // c_in row indirection (beam reorder folded into the read) or null
+    float* h32;             // optional fp32 copy of h
+    int ldh32;
+    // TOPK / SAMPLE
+    float* part;            // [M, n_tiles, PS] per-(row, N-tile) partials
+    int n_tiles;
+    uint32_t seed;          // SAMPLE: counter-based Gumbel noise (0 noise when use_noise == 0)
+    int step;
+    int use_noise;
+};
+
+struct GemmParams {
+    int M, N;
+    int k_blocks;           // K / 64 (per pass)
+    int passes;             // 1 (fp16) or 3 (split)
+    int a_lo_off, b_lo_off; // column offset of the lo halves (elements)
+    int num_m_blocks, num_n_blocks;
+    EpiParams epi;
+};
+
+template <int BLOCK_N>
+struct GemmCfg {
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : 6;
+    static constexpr int TMEM_COLS = (2 * BLOCK_N >= 512) ? 512 : ((2 * BLOCK_N >= 256) ? 256 : 128);
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
+};
+
+__host__ __device__ constexpr int topk_part_stride(int ktop) { return 2 + 2 * ktop; }
+constexpr int SAMPLE_PART_STRIDE = 5;  // max, sumexp, best perturbed, best index, best raw logit
+
+// ------------------------------------------------------------------------------------------------ math helpers
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(x - __half2float(hi));
+}
+
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+    h ^= h >> 16;
+    h *= 0x85EBCA6Bu;
+    h ^= h >> 13;
+    h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    return h;
+}
+// Gumbel(0,1) noise shared bit-for-bit (in the uniforms) with oracle/capdec_oracle.py:gumbel_noise.
+__device__ __forceinline__ float gumbel_from_hash(uint32_t row_step_hash, uint32_t v) {
+    const uint32_t x = fmix32(row_step_hash ^ (v * 0xC2B2AE3Du));
+    const float u = (static_cast<float>(x >> 8) + 0.5f) * 5.9604644775390625e-08f;  // 2^-24
+    return -logf(-logf(u));
+}
+__device__ __forceinline__ uint32_t gumbel_row_step_hash(uint32_t seed, uint32_t row, uint32_t t) {
+    uint32_t h = fmix32(seed ^ (row * 0x9E3779B1u));
+    return fmix32(h ^ (t * 0x85EBCA77u));
+}
+
+__device__ __forceinline__ void store_h16x8(__half* dst, int lo_off, const float (&h)[8]) {
+    __align__(16) __half hi[8];
+    __align__(16) __half lo[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) split_f16(h[u], hi[u], lo[u]);
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
+    if (lo_off > 0) *reinterpret_cast<uint4*>(dst + lo_off) = *reinterpret_cast<const uint4*>(lo);
+}
+
+// ------------------------------------------------------------------------------------------------ epilogues
+// Each epilogue thread owns ONE output row (TMEM lane) and walks the tile's columns in chunks of 32.
+
+template <int BLOCK_N>
+__device__ __forceinline__ void epi_store(uint32_t taddr, int row, int n_base, const GemmParams& p) {
+    const EpiParams& e = p.epi;
+    const bool row_ok = row < p.M;
+    const bool vec_ok = (p.N & 3) == 0;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int n0 = n_base + c * 32;
+        if (n0 >= p.N) break;  // warp-uniform
+        float v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        if (!row_ok) continue;
+        if (e.bias) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (n0 + i < p.N) v[i] += __ldg(e.bias + n0 + i);
+        }
+        if (e.out32) {
+            float* o = e.out32 + static_cast<size_t>(row) * e.ld32 + n0;
+            if (vec_ok) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    if (n0 + i < p.N) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (n0 + i < p.N) o[i] = v[i];
+            }
+        }
+        if (e.out16) {
+            __half* o = e.out16 + static_cast<size_t>(row) * e.ld16 + n0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+                if (n0 + i < p.N) {
+                    float h[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) h[u] = v[i + u];
+                    store_h16x8(o + i, e.lo16, h);
+                }
+            }
+        }
+    }
+}
+
+// Columns are packed gate-interleaved: n = 4*j + g, g in (i, f, g, o) -- torch.nn.LSTMCell gate order.
+template <int BLOCK_N>
+__device__ __forceinline__ void epi_lstm(uint32_t taddr, int row, int n_base, const GemmParams& p) {
+    const EpiParams& e = p.epi;
+    const bool row_ok = row < p.M;
+    int prow = row;
+    const float* radd = nullptr;
+    if (row_ok) {
+        if (e.parent) prow = __ldg(e.parent + row);
+        if (e.rowadd) radd = e.rowadd + static_cast<size_t>(row / e.rows_per_group) * e.rowadd_ld;
+    }
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int n0 = n_base + c * 32;
+        if (n0 >= p.N) break;
+        float v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        if (!row_ok) continue;
+        const int j0 = n0 >> 2;
+        if (e.bias) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + i));
+                v[i] += b.x, v[i + 1] += b.y, v[i + 2] += b.z, v[i + 3] += b.w;
+            }
+        }
+        if (radd) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(radd + n0 + i));
+                v[i] += b.x, v[i + 1] += b.y, v[i + 2] += b.z, v[i + 3] += b.w;
+            }
+        }
+        float cp[8];
+        if (e.c_in) {
+            const float4 c0 = *reinterpret_cast<const float4*>(e.c_in + static_cast<size_t>(prow) * e.ldc + j0);
+            const float4 c1 = *reinterpret_cast<const float4*>(e.c_in + static_cast<size_t>(prow) * e.ldc + j0 + 4);
+            cp[0] = c0.x, cp[1] = c0.y, cp[2] = c0.z, cp[3] = c0.w, cp[4] = c1.x, cp[5] = c1.y, cp[6] = c1.z, cp[7] = c1.w;
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) cp[u] = 0.f;
+        }
+        float cn[8], hn[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float gi = v[4 * u], gf = v[4 * u + 1], gg = v[4 * u + 2], go = v[4 * u + 3];
+            cn[u] = sigmoidf_acc(gf) * cp[u] + sigmoidf_acc(gi) * tanhf(gg);
+            hn[u] = sigmoidf_acc(go) * tanhf(cn[u]);
+        }
+        float* co = e.c_out + static_cast<size_t>(row) * e.ldc + j0;
+        *reinterpret_cast<float4*>(co) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+        *reinterpret_cast<float4*>(co + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+        store_h16x8(e.out16 + static_cast<size_t>(row) * e.ld16 + j0, e.lo16, hn);
+        if (e.h32) {
+            float* ho = e.h32 + static_cast<size_t>(row) * e.ldh32 + j0;
+            *reinterpret_cast<float4*>(ho) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+            *reinterpret_cast<float4*>(ho + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+        }
+    }
+}
+
+// Columns are packed (a_j, gate_j)-interleaved: n = 2*j + s.  nn.GLU: a * sigmoid(gate).
+template <int BLOCK_N>
+__device__ __forceinline__ void epi_glu(uint32_t taddr, int row, int n_base, const GemmParams& p) {
+    const EpiParams& e = p.epi;
+    const bool row_ok = row < p.M;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int n0 = n_base + c * 32;
+        if (n0 >= p.N) break;
+        float v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        if (!row_ok) continue;
+        const int j0 = n0 >> 1;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + i));
+            v[i] += b.x, v[i + 1] += b.y, v[i + 2] += b.z, v[i + 3] += b.w;
+        }
+        float y[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) y[u] = v[2 * u] * sigmoidf_acc(v[2 * u + 1]);
+        if (e.out32) {
+            float* o = e.out32 + static_cast<size_t>(row) * e.ld32 + j0;
+#pragma unroll
+            for (int u = 0; u < 16; u += 4) *reinterpret_cast<float4*>(o + u) = make_float4(y[u], y[u + 1], y[u + 2], y[u + 3]);
+        }
+        if (e.out16) {
+            __half* o = e.out16 + static_cast<size_t>(row) * e.ld16 + j0;
+#pragma unroll
+            for (int u = 0; u < 16; u += 8) {
+                float h[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) h[q] = y[u + q];
+                store_h16x8(o + u, e.lo16, h);
+            }
+        }
+    }
+}
+
+// Per (row, N-tile): running max, sum of exp(x - max), and the KTOP largest logits with their vocabulary
+// indices (ties keep the lower index first).  The full logits row is never written to HBM.
+template <int BLOCK_N, int KTOP>
+__device__ __forceinline__ void epi_topk(uint32_t taddr, int row, int n_base, int n_blk, const GemmParams& p) {
+    const EpiParams& e = p.epi;
+    float m = -INFINITY, s = 0.f;
+    float tv[KTOP];
+    int ti[KTOP];
+#pragma unroll
+    for (int q = 0; q < KTOP; ++q) tv[q] = -INFINITY, ti[q] = 0x7FFFFFFF;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int n0 = n_base + c * 32;
+        if (n0 >= p.N) break;
+        float v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        float cmax = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            if (n0 + i < p.N) {
+                v[i] += __ldg(e.bias + n0 + i);
+                cmax = fmaxf(cmax, v[i]);
+            } else {
+                v[i] = -INFINITY;
+            }
+        }
+        const float mn = fmaxf(m, cmax);
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc += expf(v[i] - mn);  // exp(-inf) = 0 for the padded columns
+        s = s * expf(m - mn) + acc;
+        m = mn;
+        if (cmax > tv[KTOP - 1]) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if (v[i] > tv[KTOP - 1]) {
+                    tv[KTOP - 1] = v[i];
+                    ti[KTOP - 1] = n0 + i;
+#pragma unroll
+                    for (int q = KTOP - 1; q > 0; --q) {
+                        if (tv[q] > tv[q - 1]) {
+                            const float fv = tv[q]; tv[q] = tv[q - 1]; tv[q - 1] = fv;
+                            const int iv = ti[q]; ti[q] = ti[q - 1]; ti[q - 1] = iv;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (row < p.M) {
+        constexpr int PS = topk_part_stride(KTOP);
+        float* o = e.part + (static_cast<size_t>(row) * e.n_tiles + n_blk) * PS;
+        o[0] = m;
+        o[1] = s;
+#pragma unroll
+        for (int q = 0; q < KTOP; ++q) {
+            o[2 + q] = tv[q];
+            o[2 + KTOP + q] = __int_as_float(ti[q]);
+        }
+    }
+}
+
+// Greedy / multinomial draw: argmax over the vocabulary of (logit + Gumbel noise); with use_noise == 0 this is
+// the plain argmax of ``sample``.  Also carries (max, sum-exp) for the log-prob of the drawn word.
+template <int BLOCK_N>
+__device__ __forceinline__ void epi_sample(uint32_t taddr, int row, int n_base, int n_blk, const GemmParams& p) {
+    const EpiParams& e = p.epi;
+    float m = -INFINITY, s = 0.f;
+    float best = -INFINITY, best_raw = 0.f;
+    int best_i = 0x7FFFFFFF;
+    const uint32_t rs = gumbel_row_step_hash(e.seed, static_cast<uint32_t>(row), static_cast<uint32_t>(e.step));
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int n0 = n_base + c * 32;
+        if (n0 >= p.N) break;
+        float v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        float cmax = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            if (n0 + i < p.N) {
+                v[i] += __ldg(e.bias + n0 + i);
+                cmax = fmaxf(cmax, v[i]);
+            } else {
+                v[i] = -INFINITY;
+            }
+        }
+        const float mn = fmaxf(m, cmax);
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc += expf(v[i] - mn);
+        s = s * expf(m - mn) + acc;
+        m = mn;
+        if (e.use_noise) {
+#pragma unroll 4
+            for (int i = 0; i < 32; ++i) {
+                if (n0 + i < p.N) {
+                    const float pv = v[i] + gumbel_from_hash(rs, static_cast<uint32_t>(n0 + i));
+                    if (pv > best) best = pv, best_i = n0 + i, best_raw = v[i];
+                }
+            }
+        } else if (cmax > best) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (v[i] > best) best = v[i], best_i = n0 + i, best_raw = v[i];
+        }
+    }
+    if (row < p.M) {
+        float* o = e.part + (static_cast<size_t>(row) * e.n_tiles + n_blk) * SAMPLE_PART_STRIDE;
+        o[0] = m;
+        o[1] = s;
+        o[2] = best;
+        o[3] = __int_as_float(best_i);
+        o[4] = best_raw;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+template <int BLOCK_N, int EPI, int KTOP>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+    using Cfg = GemmCfg<BLOCK_N>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    const uint32_t full_bar = smem_u32(bars);                     // [STAGES]
+    const uint32_t empty_bar = smem_u32(bars + STAGES);           // [STAGES]
+    const uint32_t tfull_bar = smem_u32(bars + 2 * STAGES);       // [2]
+    const uint32_t tempty_bar = smem_u32(bars + 2 * STAGES + 2);  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    const uint32_t smem_base = smem_u32(smem);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+    const int total_kb = p.k_blocks * p.passes;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar + 8 * s, 1);
+            mbar_init(empty_bar + 8 * s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar + 8 * s, 1);
+            mbar_init(tempty_bar + 8 * s, 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(smem_u32(tmem_slot), Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile % p.num_m_blocks;
+                const int n_blk = tile / p.num_m_blocks;
+                for (int kk = 0; kk < total_kb; ++kk) {
+                    const int pass = kk / p.k_blocks;
+                    const int kb = kk - pass * p.k_blocks;
+                    const int ka = kb * BLOCK_K + (pass == 2 ? p.a_lo_off : 0);
+                    const int kbb = kb * BLOCK_K + (pass == 1 ? p.b_lo_off : 0);
+                    mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t sb = sa + Cfg::A_BYTES;
+                    mbar_arrive_expect_tx(full_bar + 8 * stage, Cfg::STAGE_BYTES);
+                    tma_load_2d(sa, &tma_a, full_bar + 8 * stage, ka, m_blk * BLOCK_M);
+                    tma_load_2d(sb, &tma_b, full_bar + 8 * stage, kbb, n_blk * BLOCK_N);
+                    if (++stage == STAGES) stage = 0, phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(BLOCK_M, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kk = 0; kk < total_kb; ++kk) {
+                    mbar_wait(full_bar + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint64_t da = make_smem_desc_sw128(sa);
+                    const uint64_t db = make_smem_desc_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // advance 16 fp16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
+                        umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kk | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar + 8 * stage);  // frees the smem slot once these MMAs retire
+                    if (++stage == STAGES) stage = 0, phase ^= 1;
+                }
+                umma_commit(tfull_bar + 8 * acc);  // accumulator complete -> epilogue
+                if (++acc == 2) acc = 0, acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ===================== epilogue warps (2..5) =====================
+        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile % p.num_m_blocks;
+            const int n_blk = tile / p.num_m_blocks;
+            mbar_wait(tfull_bar + 8 * acc, acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quarter * 32) << 16);
+            const int row = m_blk * BLOCK_M + quarter * 32 + lane;
+            const int n_base = n_blk * BLOCK_N;
+            if constexpr (EPI == EPI_STORE) epi_store<BLOCK_N>(taddr, row, n_base, p);
+            else if constexpr (EPI == EPI_LSTM) epi_lstm<BLOCK_N>(taddr, row, n_base, p);
+            else if constexpr (EPI == EPI_GLU) epi_glu<BLOCK_N>(taddr, row, n_base, p);
+            else if constexpr (EPI == EPI_TOPK) epi_topk<BLOCK_N, KTOP>(taddr, row, n_base, n_blk, p);
+            else epi_sample<BLOCK_N>(taddr, row, n_base, n_blk, p);
+            __syncwarp();
+            tc_fence_before();
+            mbar_arrive(tempty_bar + 8 * acc);
+            if (++acc == 2) acc = 0, acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+}  // namespace capdec

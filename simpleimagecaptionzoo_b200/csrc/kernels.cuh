@@ -1,0 +1,706 @@
+// Non-GEMM kernels of the caption decoder: weight packing, one-time feature preparation, the per-step
+// attention kernels (HBM-bound), LayerNorm, and the beam / sampling bookkeeping kernels that also assemble
+// the next step's GEMM operands (beam-state reorder by parent index + embedding gather).
+#pragma once
+#include "gemm.cuh"
+
+namespace capdec {
+
+constexpr int TOK_PAD = 0, TOK_STA = 1, TOK_END = 2;  // PreProcess/Build_caption_vocab.py:37-40
+constexpr int MAX_ROWS = 8;                           // beam size / samples per image supported per CTA
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ================================================================================================ weights
+// scale[n] = g[n] / ||v[n,:]||_2 in double (legacy torch weight_norm, dim=0).
+__global__ void weightnorm_scale_kernel(const float* __restrict__ g, const float* __restrict__ v, int N, int K,
+                                        double* __restrict__ scale) {
+    const int n = blockIdx.x;
+    if (n >= N) return;
+    double acc = 0.0;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const double x = v[static_cast<size_t>(n) * K + k];
+        acc += x * x;
+    }
+    __shared__ double red[32];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t += red[w];
+        scale[n] = static_cast<double>(g[n]) / sqrt(t);
+    }
+}
+
+// Row permutations of the packed operand:  0 identity;  1 LSTM gate interleave (dst 4*j+g <- src g*Hh+j);
+// 2 GLU interleave (dst 2*j+s <- src s*Hh+j).
+__host__ __device__ __forceinline__ int packed_src_row(int n_dst, int mode, int Hh) {
+    if (mode == 1) return (n_dst & 3) * Hh + (n_dst >> 2);
+    if (mode == 2) return (n_dst & 1) * Hh + (n_dst >> 1);
+    return n_dst;
+}
+
+// dst[n, dst_col + k] (hi) and dst[n, lo + dst_col + k] (lo) <- src[src_row(n), src_col + k] * scale[src_row]
+__global__ void pack_weight_kernel(const float* __restrict__ src, int src_ld, int src_col, const double* __restrict__ scale,
+                                   __half* __restrict__ dst, int dst_ld, int dst_lo, int dst_col, int N, int K, int mode,
+                                   int Hh) {
+    const size_t total = static_cast<size_t>(N) * K;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int n = static_cast<int>(i / K), k = static_cast<int>(i - static_cast<size_t>(n) * K);
+        const int sr = packed_src_row(n, mode, Hh);
+        float w = src[static_cast<size_t>(sr) * src_ld + src_col + k];
+        if (scale) w = static_cast<float>(static_cast<double>(w) * scale[sr]);
+        __half hi, lo;
+        split_f16(w, hi, lo);
+        dst[static_cast<size_t>(n) * dst_ld + dst_col + k] = hi;
+        if (dst_lo > 0) dst[static_cast<size_t>(n) * dst_ld + dst_lo + dst_col + k] = lo;
+    }
+}
+
+// dst[n] = a[src_row(n)] (+ b[src_row(n)])
+__global__ void pack_bias_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ dst, int N,
+                                 int mode, int Hh) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int sr = packed_src_row(n, mode, Hh);
+    dst[n] = b ? a[sr] + b[sr] : a[sr];
+}
+
+// scaled folded vector (the BUTD ``affine`` layer has one output row): dst[k] = v[k] * scale[0]
+__global__ void fold_vector_kernel(const float* __restrict__ v, const double* __restrict__ scale, float* __restrict__ dst,
+                                   int K) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < K) dst[k] = static_cast<float>(static_cast<double>(v[k]) * scale[0]);
+}
+
+// ================================================================================================ prepare
+// fp32 [rows, cols] -> fp16 hi|lo operand
+__global__ void cvt_f16_kernel(const float* __restrict__ src, size_t rows, int cols, __half* __restrict__ dst, int dst_ld,
+                               int dst_lo, int dst_col) {
+    const size_t total4 = rows * static_cast<size_t>(cols) / 4;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total4;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t e = i * 4;
+        const size_t r = e / cols;
+        const int c = static_cast<int>(e - r * cols);
+        const float4 x = __ldg(reinterpret_cast<const float4*>(src + e));
+        __align__(8) __half hi[4];
+        __align__(8) __half lo[4];
+        split_f16(x.x, hi[0], lo[0]);
+        split_f16(x.y, hi[1], lo[1]);
+        split_f16(x.z, hi[2], lo[2]);
+        split_f16(x.w, hi[3], lo[3]);
+        __half* d = dst + r * dst_ld + dst_col + c;
+        *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(hi);
+        if (dst_lo > 0) *reinterpret_cast<uint2*>(d + dst_lo) = *reinterpret_cast<const uint2*>(lo);
+    }
+}
+
+// mean over regions (optionally masked: sum(f*m)/sum(m), AoA_Model.py:422-425); writes fp32 and/or fp16 operand.
+__global__ void region_mean_kernel(const float* __restrict__ feats, const float* __restrict__ mask, int R, int C,
+                                   float* __restrict__ out32, __half* __restrict__ out16, int ld16, int lo16) {
+    const int b = blockIdx.x;
+    const float* f = feats + static_cast<size_t>(b) * R * C;
+    float msum = static_cast<float>(R);
+    if (mask) {
+        msum = 0.f;
+        for (int r = 0; r < R; ++r) msum += mask[static_cast<size_t>(b) * R + r];
+    }
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float acc = 0.f;
+        for (int r = 0; r < R; ++r) {
+            const float x = f[static_cast<size_t>(r) * C + c];
+            acc += mask ? x * mask[static_cast<size_t>(b) * R + r] : x;
+        }
+        const float m = acc / msum;
+        if (out32) out32[static_cast<size_t>(b) * C + c] = m;
+        if (out16) {
+            __half hi, lo;
+            split_f16(m, hi, lo);
+            out16[static_cast<size_t>(b) * ld16 + c] = hi;
+            if (lo16 > 0) out16[static_cast<size_t>(b) * ld16 + lo16 + c] = lo;
+        }
+    }
+}
+
+__global__ void fill_f16_kernel(__half* p, size_t n, float v) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        p[i] = __float2half_rn(v);
+}
+
+// ================================================================================================ BUTD attention
+// One CTA per image, all K rows (beams / samples) of the image together so that the image's projected
+// features enc_ctx [R,A] and raw features [R,D] are read from HBM once per image-step, not once per row.
+//   e[k,r]   = w_aff . relu(enc_ctx[r,:] + dec_ctx[k,:]) + b_aff      (BUTD_Model.py:58-59, ReLU not tanh)
+//   alpha    = softmax_r(e)                                            (:60)
+//   ctx[k,:] = sum_r alpha[k,r] * feats[r,:]                           (:61)
+// ctx is written straight into the language LSTM's fp16 operand buffer.
+template <int KR>
+__global__ void __launch_bounds__(256) butd_attention_kernel(const float* __restrict__ enc_ctx, const float* __restrict__ feats,
+                                                             const float* __restrict__ dec_ctx, const float* __restrict__ w_aff,
+                                                             float b_aff, int R, int A, int D, int K, __half* __restrict__ ctx16,
+                                                             int ld16, int lo16, float* __restrict__ alphas_out) {
+    extern __shared__ float sm[];
+    float* s_dec = sm;                 // [KR][A]
+    float* s_w = s_dec + KR * A;       // [A]
+    float* s_e = s_w + A;              // [KR][R]
+    const int img = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+
+    for (int i = tid; i < K * A; i += blockDim.x) s_dec[i] = dec_ctx[static_cast<size_t>(img) * K * A + i];
+    for (int i = tid; i < A; i += blockDim.x) s_w[i] = w_aff[i];
+    __syncthreads();
+
+    const float* enc = enc_ctx + static_cast<size_t>(img) * R * A;
+    for (int r = warp; r < R; r += nwarp) {
+        float acc[KR];
+#pragma unroll
+        for (int k = 0; k < KR; ++k) acc[k] = 0.f;
+        for (int a = lane * 4; a < A; a += 128) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(enc + static_cast<size_t>(r) * A + a));
+            const float4 w = *reinterpret_cast<const float4*>(s_w + a);
+#pragma unroll
+            for (int k = 0; k < KR; ++k) {
+                if (k < K) {
+                    const float4 d = *reinterpret_cast<const float4*>(s_dec + k * A + a);
+                    acc[k] += w.x * fmaxf(x.x + d.x, 0.f) + w.y * fmaxf(x.y + d.y, 0.f) + w.z * fmaxf(x.z + d.z, 0.f) +
+                              w.w * fmaxf(x.w + d.w, 0.f);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < KR; ++k) {
+            const float t = warp_sum(acc[k]);
+            if (lane == 0 && k < K) s_e[k * R + r] = t + b_aff;
+        }
+    }
+    __syncthreads();
+
+    for (int k = warp; k < K; k += nwarp) {  // softmax over regions, one warp per row
+        float m = -INFINITY;
+        for (int r = lane; r < R; r += 32) m = fmaxf(m, s_e[k * R + r]);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int r = lane; r < R; r += 32) {
+            const float ex = expf(s_e[k * R + r] - m);
+            s_e[k * R + r] = ex;
+            s += ex;
+        }
+        s = warp_sum(s);
+        for (int r = lane; r < R; r += 32) {
+            const float al = s_e[k * R + r] / s;
+            s_e[k * R + r] = al;
+            if (alphas_out) alphas_out[(static_cast<size_t>(img) * K + k) * R + r] = al;
+        }
+    }
+    __syncthreads();
+
+    const float* f = feats + static_cast<size_t>(img) * R * D;
+    for (int d = tid * 4; d < D; d += blockDim.x * 4) {
+        float4 acc[KR];
+#pragma unroll
+        for (int k = 0; k < KR; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int r = 0; r < R; ++r) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(f + static_cast<size_t>(r) * D + d));
+#pragma unroll
+            for (int k = 0; k < KR; ++k) {
+                if (k < K) {
+                    const float al = s_e[k * R + r];
+                    acc[k].x += al * x.x, acc[k].y += al * x.y, acc[k].z += al * x.z, acc[k].w += al * x.w;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < KR; ++k) {
+            if (k < K) {
+                __align__(8) __half hi[4];
+                __align__(8) __half lo[4];
+                split_f16(acc[k].x, hi[0], lo[0]);
+                split_f16(acc[k].y, hi[1], lo[1]);
+                split_f16(acc[k].z, hi[2], lo[2]);
+                split_f16(acc[k].w, hi[3], lo[3]);
+                __half* o = ctx16 + (static_cast<size_t>(img) * K + k) * ld16 + d;
+                *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(hi);
+                if (lo16 > 0) *reinterpret_cast<uint2*>(o + lo16) = *reinterpret_cast<const uint2*>(lo);
+            }
+        }
+    }
+}
+
+// ================================================================================================ AoA pieces
+// LayerNorm of the reference (AoA_Model.py:14-25): gain*(x-mean)/(std_unbiased + eps) + bias.  One warp per row;
+// writes the fp16 operand (query for linear_Q and for the AoA gate GEMM).
+__global__ void aoa_layernorm_kernel(const float* __restrict__ h, int M, int H, const float* __restrict__ gain,
+                                     const float* __restrict__ bias, float eps, __half* __restrict__ q16, int ld16, int lo16) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float* x = h + static_cast<size_t>(row) * H;
+    float s = 0.f;
+    for (int i = lane; i < H; i += 32) s += x[i];
+    const float mean = warp_sum(s) / static_cast<float>(H);
+    float v = 0.f;
+    for (int i = lane; i < H; i += 32) {
+        const float d = x[i] - mean;
+        v += d * d;
+    }
+    const float sd = sqrtf(warp_sum(v) / static_cast<float>(H - 1));
+    const float inv = 1.0f / (sd + eps);
+    for (int i = lane; i < H; i += 32) {
+        const float y = gain[i] * (x[i] - mean) * inv + bias[i];
+        __half hi, lo;
+        split_f16(y, hi, lo);
+        q16[static_cast<size_t>(row) * ld16 + i] = hi;
+        if (lo16 > 0) q16[static_cast<size_t>(row) * ld16 + lo16 + i] = lo;
+    }
+}
+
+// Multi-head dot-product attention of the decoder AoA block for the K rows of one image (AoA_Model.py:41-69,
+// 90-117) over the one-time K,V projections kv [B*R, 2H] (K in columns [0,H), V in [H,2H)):
+//   s[k,h,r] = Q[k,h,:].K[r,h,:] / sqrt(d), masked_fill(mask==0, -1e9), softmax over r, x[k,h,:] = sum_r p V[r,h,:]
+// Requires (H/heads)/4 to be a power of two.
+template <int KR>
+__global__ void __launch_bounds__(256) aoa_attention_kernel(const float* __restrict__ q, const float* __restrict__ kv,
+                                                            const float* __restrict__ mask, int R, int H, int nh, int K,
+                                                            __half* __restrict__ x16, int ld16, int lo16) {
+    extern __shared__ float sm[];
+    float* s_q = sm;               // [KR][H]
+    float* s_p = s_q + KR * H;     // [KR][nh][R]
+    const int img = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+    const int d = H / nh;
+    const int G = d / 4;  // float4 per head
+    const float inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(d));
+
+    for (int i = tid; i < K * H; i += blockDim.x) s_q[i] = q[static_cast<size_t>(img) * K * H + i];
+    __syncthreads();
+
+    const float* kvb = kv + static_cast<size_t>(img) * R * 2 * H;
+    const int nf4 = H / 4;
+    for (int r = warp; r < R; r += nwarp) {
+        const float* kr = kvb + static_cast<size_t>(r) * 2 * H;
+        const bool masked = mask && mask[static_cast<size_t>(img) * R + r] == 0.f;
+        if (G >= 32) {
+            for (int hd = 0; hd < nh; ++hd) {
+                float acc[KR];
+#pragma unroll
+                for (int k = 0; k < KR; ++k) acc[k] = 0.f;
+                for (int i = hd * G + lane; i < (hd + 1) * G; i += 32) {
+                    const float4 x = __ldg(reinterpret_cast<const float4*>(kr) + i);
+#pragma unroll
+                    for (int k = 0; k < KR; ++k) {
+                        if (k < K) {
+                            const float4 qq = *reinterpret_cast<const float4*>(s_q + k * H + 4 * i);
+                            acc[k] += x.x * qq.x + x.y * qq.y + x.z * qq.z + x.w * qq.w;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < KR; ++k) {
+                    const float t = warp_sum(acc[k]);
+                    if (lane == 0 && k < K) s_p[(k * nh + hd) * R + r] = masked ? -1e9f : t * inv_sqrt_d;
+                }
+            }
+        } else {
+            for (int i0 = 0; i0 < nf4; i0 += 32) {
+                const int i = i0 + lane;
+                float acc[KR];
+#pragma unroll
+                for (int k = 0; k < KR; ++k) acc[k] = 0.f;
+                if (i < nf4) {
+                    const float4 x = __ldg(reinterpret_cast<const float4*>(kr) + i);
+#pragma unroll
+                    for (int k = 0; k < KR; ++k) {
+                        if (k < K) {
+                            const float4 qq = *reinterpret_cast<const float4*>(s_q + k * H + 4 * i);
+                            acc[k] = x.x * qq.x + x.y * qq.y + x.z * qq.z + x.w * qq.w;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < KR; ++k) {
+                    float t = acc[k];
+                    for (int o = G >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                    if (i < nf4 && (lane % G) == 0 && k < K) s_p[(k * nh + i / G) * R + r] = masked ? -1e9f : t * inv_sqrt_d;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    for (int kh = warp; kh < K * nh; kh += nwarp) {  // softmax over regions per (row, head)
+        float* p = s_p + static_cast<size_t>(kh) * R;
+        float m = -INFINITY;
+        for (int r = lane; r < R; r += 32) m = fmaxf(m, p[r]);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int r = lane; r < R; r += 32) {
+            const float ex = expf(p[r] - m);
+            p[r] = ex;
+            s += ex;
+        }
+        s = warp_sum(s);
+        for (int r = lane; r < R; r += 32) p[r] = p[r] / s;
+    }
+    __syncthreads();
+
+    for (int i = tid; i < nf4; i += blockDim.x) {
+        const int hd = i / G;
+        float4 acc[KR];
+#pragma unroll
+        for (int k = 0; k < KR; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int r = 0; r < R; ++r) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(kvb + static_cast<size_t>(r) * 2 * H + H) + i);
+#pragma unroll
+            for (int k = 0; k < KR; ++k) {
+                if (k < K) {
+                    const float pr = s_p[(k * nh + hd) * R + r];
+                    acc[k].x += pr * x.x, acc[k].y += pr * x.y, acc[k].z += pr * x.z, acc[k].w += pr * x.w;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < KR; ++k) {
+            if (k < K) {
+                __align__(8) __half hi[4];
+                __align__(8) __half lo[4];
+                split_f16(acc[k].x, hi[0], lo[0]);
+                split_f16(acc[k].y, hi[1], lo[1]);
+                split_f16(acc[k].z, hi[2], lo[2]);
+                split_f16(acc[k].w, hi[3], lo[3]);
+                __half* o = x16 + (static_cast<size_t>(img) * K + k) * ld16 + 4 * i;
+                *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(hi);
+                if (lo16 > 0) *reinterpret_cast<uint2*>(o + lo16) = *reinterpret_cast<const uint2*>(lo);
+            }
+        }
+    }
+}
+
+// ================================================================================================ operand assembly
+// After the bookkeeping of a step every row's next GEMM operands are rebuilt: recurrent states are gathered
+// by parent row (the beam reorder of BUTD_Model.py:297-300), the chosen word is embedded (:264), AoA's
+// mean + ctx input is formed (AoA_Model.py:441).
+enum AdvKind { ADV_COPY16 = 0, ADV_EMBED = 1, ADV_MEAN_PLUS = 2, ADV_BCAST16 = 3 };
+struct AdvOp {
+    int kind;
+    const void* src;   // COPY16/BCAST16: fp16 operand rows; EMBED: fp32 table [V,n]; MEAN_PLUS: fp32 [M,n] (may be null)
+    int src_ld, src_lo;
+    const float* aux;  // MEAN_PLUS: mean [B,n]
+    __half* dst;
+    int dst_ld, dst_lo;
+    int n;             // elements per row
+    int flag;          // EMBED: 1 = ReLU after the lookup (BUTD / AoA embed = Embedding+ReLU)
+};
+struct AdvOps {
+    int n;
+    AdvOp op[6];
+};
+
+// row = destination row, prow = source (parent) row, img = image index, tok = word fed to the next step
+__device__ __forceinline__ void advance_row(const AdvOps& ops, int row, int prow, int img, int tok, int tid, int nthreads) {
+    for (int q = 0; q < ops.n; ++q) {
+        const AdvOp& o = ops.op[q];
+        __half* dst = o.dst + static_cast<size_t>(row) * o.dst_ld;
+        if (o.kind == ADV_COPY16 || o.kind == ADV_BCAST16) {
+            const int srow = o.kind == ADV_COPY16 ? prow : img;
+            const __half* src = static_cast<const __half*>(o.src) + static_cast<size_t>(srow) * o.src_ld;
+            const int n8 = o.n >> 3;
+            for (int i = tid; i < n8; i += nthreads) {
+                reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+                if (o.dst_lo > 0) reinterpret_cast<uint4*>(dst + o.dst_lo)[i] = reinterpret_cast<const uint4*>(src + o.src_lo)[i];
+            }
+        } else if (o.kind == ADV_EMBED) {
+            const float* src = static_cast<const float*>(o.src) + static_cast<size_t>(tok) * o.src_ld;
+            for (int i = tid; i < o.n; i += nthreads) {
+                float x = __ldg(src + i);
+                if (o.flag) x = fmaxf(x, 0.f);
+                __half hi, lo;
+                split_f16(x, hi, lo);
+                dst[i] = hi;
+                if (o.dst_lo > 0) dst[o.dst_lo + i] = lo;
+            }
+        } else {  // ADV_MEAN_PLUS
+            const float* c = o.src ? static_cast<const float*>(o.src) + static_cast<size_t>(prow) * o.src_ld : nullptr;
+            const float* mn = o.aux + static_cast<size_t>(img) * o.n;
+            for (int i = tid; i < o.n; i += nthreads) {
+                const float x = mn[i] + (c ? c[i] : 0.f);
+                __half hi, lo;
+                split_f16(x, hi, lo);
+                dst[i] = hi;
+                if (o.dst_lo > 0) dst[o.dst_lo + i] = lo;
+            }
+        }
+    }
+}
+
+// ================================================================================================ beam search
+struct BeamState {
+    int B, K, V, T;
+    int* tok;          // [B*K] word fed to the next step
+    float* cum;        // [B*K] cumulative log-prob of live slots (-inf = dead)
+    int* parent;       // [B*K] absolute parent row of each slot (cell-state indirection)
+    int* n_live;       // [B]
+    int* seqs_in;      // [B*K, T+1]
+    int* seqs_out;     // [B*K, T+1]
+    float* best_score; // [B] best COMPLETED hypothesis so far (-inf = none)
+    int* best_seq;     // [B, T+1]
+    int* best_len;     // [B]
+};
+
+// t = 0: initial state (all K slots <sta>, cum 0; BUTD_Model.py:247-250); no partials are read.
+// parent_is_img: the first LSTM step reads a per-IMAGE cell state (NIC's primed c0), so parent[row] = image.
+__global__ void beam_init_kernel(BeamState s, AdvOps ops, int parent_is_img) {
+    const int img = blockIdx.x;
+    const int L = s.T + 1;
+    for (int i = threadIdx.x; i < s.K * L; i += blockDim.x) {
+        const int slot = i / L, pos = i - slot * L;
+        const int v = pos == 0 ? TOK_STA : TOK_PAD;
+        s.seqs_in[(static_cast<size_t>(img) * s.K + slot) * L + pos] = v;
+        s.seqs_out[(static_cast<size_t>(img) * s.K + slot) * L + pos] = v;
+    }
+    for (int i = threadIdx.x; i < L; i += blockDim.x) s.best_seq[static_cast<size_t>(img) * L + i] = TOK_PAD;
+    if (threadIdx.x < s.K) {
+        const int row = img * s.K + threadIdx.x;
+        s.tok[row] = TOK_STA;
+        s.cum[row] = 0.f;
+        s.parent[row] = parent_is_img ? img : row;
+    }
+    if (threadIdx.x == 0) {
+        s.n_live[img] = s.K;
+        s.best_score[img] = -INFINITY;
+        s.best_len[img] = 0;
+    }
+    for (int slot = 0; slot < s.K; ++slot)
+        advance_row(ops, img * s.K + slot, img * s.K + slot, img, TOK_STA, threadIdx.x, blockDim.x);
+}
+
+// One CTA (128 threads) per image.  Merges the per-(row, N-tile) partials of the logit GEMM into log-softmax
+// scores, takes the top-k over (live rows x vocabulary) and applies the reference's bookkeeping
+// (BUTD_Model.py:271-302 == NIC_Model.py:175-202 == AoA_Model.py:456-488):
+//   step 1 looks at row 0 only; selected <end> candidates complete (running best, strict '>' = first max) and
+//   shrink the beam; survivors keep their sorted order; states follow their parent.
+template <int KTOP>
+__global__ void __launch_bounds__(128) beam_step_kernel(const float* __restrict__ part, int n_tiles, BeamState s, int t,
+                                                        AdvOps ops) {
+    constexpr int PS = topk_part_stride(KTOP);
+    __shared__ float c_val[MAX_ROWS][MAX_ROWS];
+    __shared__ int c_idx[MAX_ROWS][MAX_ROWS];
+    __shared__ int s_parent[MAX_ROWS], s_tok[MAX_ROWS];
+    const int img = blockIdx.x;
+    const int K = s.K, V = s.V, L = s.T + 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nl = s.n_live[img];
+    const int rows_considered = (t == 1) ? min(nl, 1) : nl;
+
+    for (int r = warp; r < K; r += 4) {
+        if (r >= rows_considered) {
+            if (lane < K) c_val[r][lane] = -INFINITY, c_idx[r][lane] = 0x7FFFFFFF;
+            continue;
+        }
+        const int row = img * K + r;
+        const float* pr = part + static_cast<size_t>(row) * n_tiles * PS;
+        float m = -INFINITY;
+        for (int j = lane; j < n_tiles; j += 32) m = fmaxf(m, pr[j * PS]);
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int j = lane; j < n_tiles; j += 32) sum += pr[j * PS + 1] * expf(pr[j * PS] - m);
+        sum = warp_sum(sum);
+        const float lse = m + logf(sum);
+        const float base = s.cum[row];
+        // K best (value desc, index asc) of the n_tiles*KTOP candidates, extracted in order
+        float pv = INFINITY;
+        int pi = -1;
+        const int ncand = n_tiles * KTOP;
+        for (int j = 0; j < K; ++j) {
+            float bv = -INFINITY;
+            int bi = 0x7FFFFFFF;
+            for (int c = lane; c < ncand; c += 32) {
+                const int tile = c / KTOP, q = c - tile * KTOP;
+                const float v = pr[tile * PS + 2 + q];
+                const int i = __float_as_int(pr[tile * PS + 2 + KTOP + q]);
+                const bool after_prev = (v < pv) || (v == pv && i > pi);
+                const bool better = (v > bv) || (v == bv && i < bi);
+                if (after_prev && better) bv = v, bi = i;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) bv = ov, bi = oi;
+            }
+            pv = bv, pi = bi;
+            if (lane == 0) {
+                c_val[r][j] = (bi == 0x7FFFFFFF) ? -INFINITY : base + (bv - lse);
+                c_idx[r][j] = bi;
+            }
+        }
+    }
+    __syncthreads();
+
+    if (threadIdx.x == 0) {
+        // global top-nl over rows x K candidates, ordered by (score desc, flat index asc)
+        int taken[MAX_ROWS];  // how many candidates of each row are consumed (rows are sorted already)
+        for (int r = 0; r < K; ++r) taken[r] = 0;
+        int n_new = 0;
+        float best = s.best_score[img];
+        const int* sin = s.seqs_in + static_cast<size_t>(img) * K * L;
+        int* sout = s.seqs_out + static_cast<size_t>(img) * K * L;
+        for (int j = 0; j < nl; ++j) {
+            float bv = -INFINITY;
+            int br = -1;
+            for (int r = 0; r < rows_considered; ++r) {
+                if (taken[r] >= K) continue;
+                const float v = c_val[r][taken[r]];
+                if (c_idx[r][taken[r]] == 0x7FFFFFFF) continue;
+                if (br < 0 || v > bv) bv = v, br = r;  // ties: lower row first == lower flat index
+            }
+            if (br < 0) break;
+            const int word = c_idx[br][taken[br]];
+            taken[br]++;
+            if (word == TOK_END) {
+                if (bv > best) {  // strict: first maximum wins (BUTD_Model.py:307)
+                    best = bv;
+                    int* bs = s.best_seq + static_cast<size_t>(img) * L;
+                    for (int i = 0; i < t; ++i) bs[i] = sin[br * L + i];
+                    bs[t] = TOK_END;
+                    for (int i = t + 1; i < L; ++i) bs[i] = TOK_PAD;
+                    s.best_len[img] = t + 1;
+                }
+            } else {
+                for (int i = 0; i < t; ++i) sout[n_new * L + i] = sin[br * L + i];
+                sout[n_new * L + t] = word;
+                s_parent[n_new] = br;
+                s_tok[n_new] = word;
+                s.cum[img * K + n_new] = bv;
+                ++n_new;
+            }
+        }
+        s.best_score[img] = best;
+        s.n_live[img] = n_new;
+        for (int q = n_new; q < K; ++q) {
+            s_parent[q] = 0;
+            s_tok[q] = TOK_PAD;
+            s.cum[img * K + q] = -INFINITY;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        s.parent[img * K + threadIdx.x] = img * K + s_parent[threadIdx.x];
+        s.tok[img * K + threadIdx.x] = s_tok[threadIdx.x];
+    }
+    for (int slot = 0; slot < K; ++slot)
+        advance_row(ops, img * K + slot, img * K + s_parent[slot], img, s_tok[slot], threadIdx.x, blockDim.x);
+}
+
+// Result selection (BUTD_Model.py:306-315): the best COMPLETED hypothesis if any, else live slot 0 (slots stay
+// sorted by score).  seqs = the buffer written by the last step.
+__global__ void beam_finalize_kernel(BeamState s, const int* __restrict__ seqs, int* __restrict__ tokens,
+                                     float* __restrict__ seq_logprob, int* __restrict__ lengths) {
+    const int img = blockIdx.x * blockDim.x + threadIdx.x;
+    if (img >= s.B) return;
+    const int L = s.T + 1;
+    const bool done = s.best_score[img] > -INFINITY;
+    const int* src = done ? s.best_seq + static_cast<size_t>(img) * L : seqs + static_cast<size_t>(img) * s.K * L;
+    for (int i = 0; i < L; ++i) tokens[static_cast<size_t>(img) * L + i] = src[i];
+    if (seq_logprob) seq_logprob[img] = done ? s.best_score[img] : s.cum[img * s.K];
+    if (lengths) lengths[img] = done ? s.best_len[img] : L;
+}
+
+// ================================================================================================ sampling
+struct SampleState {
+    int B, n, V, T;
+    int* tok;          // [B*n]
+    int* unfinished;   // [B*n]
+    int* parent;       // [B*n] cell-state row indirection (identity after the first step)
+    int* live_count;   // [T+1] rows still unfinished after step t (the reference's batch-wide early break)
+    int* tokens;       // [B*n, T] output
+    float* logprobs;   // [B*n, T] output or null
+    int multinomial;
+};
+
+__global__ void sample_init_kernel(SampleState s, AdvOps ops, int parent_is_img) {
+    const int img = blockIdx.x;
+    if (threadIdx.x < s.n) {
+        const int row = img * s.n + threadIdx.x;
+        s.tok[row] = TOK_STA;
+        s.unfinished[row] = 1;
+        s.parent[row] = parent_is_img ? img : row;
+    }
+    if (img == 0)
+        for (int i = threadIdx.x; i <= s.T; i += blockDim.x) s.live_count[i] = 0;
+    for (int j = 0; j < s.n; ++j) advance_row(ops, img * s.n + j, img * s.n + j, img, TOK_STA, threadIdx.x, blockDim.x);
+}
+
+// One CTA per image, one warp per row.  sample (BUTD_Model.py:183-188): word = argmax; sample_rl (:221-233):
+// word ~ multinomial via Gumbel-max, logprob gathered, <end> and everything after it stored as 0, 0 fed back.
+__global__ void __launch_bounds__(128) sample_step_kernel(const float* __restrict__ part, int n_tiles, SampleState s, int t,
+                                                          AdvOps ops) {
+    __shared__ int s_tok[MAX_ROWS];
+    const int img = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int PS = SAMPLE_PART_STRIDE;
+    const bool stopped = s.multinomial && t > 0 && s.live_count[t - 1] == 0;  // reference broke out of the loop
+    for (int r = warp; r < s.n; r += 4) {
+        const int row = img * s.n + r;
+        const float* pr = part + static_cast<size_t>(row) * n_tiles * PS;
+        float m = -INFINITY;
+        for (int j = lane; j < n_tiles; j += 32) m = fmaxf(m, pr[j * PS]);
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int j = lane; j < n_tiles; j += 32) sum += pr[j * PS + 1] * expf(pr[j * PS] - m);
+        sum = warp_sum(sum);
+        const float lse = m + logf(sum);
+        float bv = -INFINITY, braw = 0.f;
+        int bi = 0x7FFFFFFF;
+        for (int j = lane; j < n_tiles; j += 32) {
+            const float v = pr[j * PS + 2];
+            const int i = __float_as_int(pr[j * PS + 3]);
+            if (v > bv || (v == bv && i < bi)) bv = v, bi = i, braw = pr[j * PS + 4];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            const float orw = __shfl_xor_sync(0xffffffffu, braw, o);
+            if (ov > bv || (ov == bv && oi < bi)) bv = ov, bi = oi, braw = orw;
+        }
+        if (lane == 0) {
+            int word = bi;
+            if (s.multinomial) {
+                int unf = s.unfinished[row];
+                unf = unf && (word != TOK_END);
+                word = unf ? word : 0;
+                s.unfinished[row] = unf;
+                if (!stopped) {
+                    s.tokens[static_cast<size_t>(row) * s.T + t] = word;
+                    if (s.logprobs) s.logprobs[static_cast<size_t>(row) * s.T + t] = braw - lse;
+                    if (unf) atomicAdd(s.live_count + t, 1);
+                }
+            } else {
+                s.tokens[static_cast<size_t>(row) * s.T + t] = word;
+                if (s.logprobs) s.logprobs[static_cast<size_t>(row) * s.T + t] = braw - lse;
+            }
+            s.tok[row] = word;
+            s.parent[row] = row;
+            s_tok[r] = word;
+        }
+    }
+    __syncthreads();
+    for (int j = 0; j < s.n; ++j) advance_row(ops, img * s.n + j, img * s.n + j, img, s_tok[j], threadIdx.x, blockDim.x);
+}
+
+}  // namespace capdec
