@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""Benchmark of the caption decode hot path: captions/sec at beam=3, max_seq=20 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W                 # this repo's CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W  # the reference algorithm on the box's host cores
+
+A "step" is one pass of the hot path over one batch of synthetic images: step-invariant preparation
+(projection GEMMs) + max_seq beam-search steps + result selection (+ the caption all-gather when N > 1).
+``value`` is timed with the inputs resident in HBM; ``e2e`` is the same step through the reference-facing
+captioner API (``beam_search_sampler(visual_inputs)``) with HOST inputs: pinned host -> device copy of the step's
+features and device -> host read of the captions inside the timed region.
+
+The oracle (oracle/capdec_oracle.py, a numpy port of the reference's decode loop) is executed here ONLY for the
+``cpu_baseline`` object / the ``--impl reference`` arm, and as a checker of a handful of GPU captions.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from simpleimagecaptionzoo_b200 import synth  # noqa: E402
+
+METRIC = "captions/sec (beam=3, max_seq=20)"
+UNIT = "captions/s"
+
+WORKLOADS = {
+    # name: arch, model_type, regions, beam, images per GPU, description
+    "butd_det": dict(arch="BUTD", model_type="BUTDDetection", R=36, beam=3, batch=1024,
+                     desc="BUTDDetection beam=3 eval, synthetic 36x2048 region feats, vocab 9487, random init "
+                          "(BASELINE configs[0] model at a GPU-sized batch)"),
+    "butd_spatial": dict(arch="BUTD", model_type="BUTDSpatial", R=196, beam=5, batch=1024,
+                         desc="BUTDSpatial beam=5 over a 14x14x2048 feature grid (configs[2], decoder only)"),
+    "nic": dict(arch="NIC", model_type="NIC", R=0, beam=3, batch=256,
+                desc="NIC LSTM decoder beam=3 on synthetic image embeddings (configs[1] without the ResNet-101 encoder)"),
+    "aoa": dict(arch="AOA", model_type="AoADetection", R=36, beam=3, batch=256,
+                desc="AoADetection 8-head AoA decoder beam=3, 256 images per GPU (configs[3] shard, refined feats synthetic)"),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tflops_burst=d["bf16_tflops"], tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def make_inputs(w, batch, seed):
+    dims = synth.DIMS[w["arch"]]
+    if w["arch"] == "BUTD":
+        return synth.make_region_feats(batch, w["R"], dims["enc_dim"], seed)
+    if w["arch"] == "NIC":
+        return synth.make_image_embed(batch, dims["embed_dim"], seed)
+    return synth.make_refined_feats(batch, w["R"], dims["hidden_dim"], seed)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU while the timed region runs (NVML; nvidia-smi fallback)."""
+
+    def __init__(self, index, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self._nvml = None
+
+    NAMES = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+             0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                if self._nvml is not None:
+                    self.samples.append(self._nvml.nvmlDeviceGetClockInfo(self._h, self._nvml.NVML_CLOCK_SM))
+                    mask = self._nvml.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(
+                        self._nvml, "nvmlDeviceGetCurrentClocksEventReasons") else self._nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                    for bit, name in self.NAMES.items():
+                        if mask & bit and name != "gpu_idle":
+                            self.reasons.add(name)
+                else:
+                    import subprocess
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm,"
+                                          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                                          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    f = [x.strip() for x in out.strip().split(",")]
+                    self.samples.append(int(f[0]))
+                    self.max_mhz = int(f[1])
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(self.period)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=5)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------------- CPU arms
+def oracle_decoder(w, sd):
+    from oracle import capdec_oracle as orc
+    return orc, orc.make_decoder(w["arch"], sd)
+
+
+_ORACLE_CACHE = {}
+
+
+def time_reference_form(w, sd, feats, beam, max_seq):
+    """The reference's own driver shape -- one image per beam-search call (Utils.py:72-73) -- on all host cores.
+    Weights are folded once, outside the timed region (a checkpoint load, not decode work).
+    Returns (seconds, BeamResult)."""
+    if id(sd) not in _ORACLE_CACHE:
+        _ORACLE_CACHE[id(sd)] = oracle_decoder(w, sd)
+    orc, dec = _ORACLE_CACHE[id(sd)]
+    t0 = time.perf_counter()
+    dec.prepare(feats)
+    res = orc.beam_search_reference_form(dec, beam, max_seq)
+    return time.perf_counter() - t0, res
+
+
+def run_reference_arm(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    dims = synth.DIMS[w["arch"]]
+    sd = synth.make_state_dict(w["arch"], seed=0, **dims)
+    n_img = args.ref_images
+    for i in range(args.warmup):
+        time_reference_form(w, sd, make_inputs(w, n_img, 100 + i), w["beam"], args.max_seq)
+    total = 0.0
+    for i in range(args.steps):
+        dt, _ = time_reference_form(w, sd, make_inputs(w, n_img, 200 + i), w["beam"], args.max_seq)
+        total += dt
+    value = args.steps * n_img / total
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "images_per_step": n_img, "beam": w["beam"], "max_seq": args.max_seq,
+                   "note": "reference algorithm (numpy port, weight-norm folded once, enc_att hoisted), one image per "
+                           "beam-search call as the reference forces; CPU only, rank 0 only"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n_img} images per step x {args.steps} steps, numpy/BLAS on {cores} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------- GPU arm
+def run_gpu_arm(args, w):
+    import torch
+    import torch.distributed as dist
+
+    from simpleimagecaptionzoo_b200 import capdec, engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the caption decoder has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    dims = synth.DIMS[w["arch"]]
+    B, K, T, R = args.batch, w["beam"], args.max_seq, w["R"]
+    sd = synth.make_state_dict(w["arch"], seed=0, **dims)
+    settings = dict(model_type=w["model_type"], embed_dim=dims["embed_dim"], hidden_dim=dims["hidden_dim"],
+                    atten_dim=dims.get("atten_dim", 0))
+    feature_fn = None
+    if w["model_type"] != "BUTDDetection":  # encoder / refiner side is outside the decode path: features are the input
+        feature_fn = lambda vi: vi["feats"]  # noqa: E731
+    cap = engine.B200Captioner(w["model_type"], settings, dims["vocab_size"], sd, feature_fn=feature_fn, max_batch=B,
+                               max_regions=max(R, 1), max_rows=K, max_seq=T, math=args.math, device=local,
+                               enc_dim=dims.get("enc_dim", 2048), num_heads=dims.get("num_heads", 8))
+    dec = cap.decoder
+    key = "bu_feats" if w["model_type"] == "BUTDDetection" else "feats"
+
+    # rank-local shard of the global batch (weak scaling: B images per GPU), distinct per rank
+    host_feats = torch.from_numpy(make_inputs(w, B, 1000 + rank)).pin_memory()
+    dev_feats = host_feats.to(dev)
+    n_total = B * world
+
+    def step_device():
+        dec.prepare(dev_feats)
+        tok, _, _ = dec.beam_search(K, T)
+        if world > 1:
+            tok = engine.all_gather_captions(tok, n_total)
+        return tok
+
+    def step_e2e():
+        tok = cap.beam_search_sampler({key: host_feats}, beam_size=K, max_seq=T)
+        if world > 1:
+            tok = engine.all_gather_captions(tok, n_total)
+        return tok.cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing (value)
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = dec.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        tokens = step_device()
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    launches = dec.launch_count - launches0
+    ms_per_step = ms_total / args.steps
+    value = n_total / (ms_per_step * 1e-3)
+
+    # ---- end to end through the captioner API with host buffers
+    for _ in range(max(1, min(args.warmup, 3))):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tok_host = step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    if world > 1:
+        dist.barrier()
+    e2e_value = n_total * args.steps / e2e_s
+    h2d = host_feats.numel() * host_feats.element_size()
+    d2h = tok_host.numel() * tok_host.element_size()
+
+    # ---- per-kernel timing (CUDA events on the launching stream) for the roofline object
+    peaks = load_peaks()
+    dec.profile(True)
+    prof_steps = 2
+    for _ in range(prof_steps):
+        step_device()
+    torch.cuda.synchronize()
+    prof = dec.profile_read()
+    dec.profile(False)
+    kern = {}
+    for cat, (ms, fl, cnt) in prof.items():
+        if cnt:
+            kern[cat] = {"ms_per_step": ms / prof_steps, "launches_per_step": cnt // prof_steps,
+                         "tflops": (fl / (ms * 1e-3) / 1e12) if (fl and ms) else None}
+    gemm_ms = {c: v["ms_per_step"] for c, v in kern.items() if c.startswith("gemm")}
+    dom = max(gemm_ms, key=gemm_ms.get)
+    dms, dfl, dcnt = prof[dom]
+    achieved = dfl / (dms * 1e-3) / 1e12
+    roofline = {"kernel": f"capdec::gemm_kernel<256,{dom}>", "bound": "tensor", "achieved": achieved,
+                "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
+                "traffic": None, "peak_source": peaks["source"] + ", sustained bf16 cuBLAS",
+                "flops_per_launch": dfl / dcnt, "us_per_launch": 1e3 * dms / dcnt,
+                "share_of_step": dms / prof_steps / sum(v["ms_per_step"] for v in kern.values())}
+    if "attention" in kern:  # HBM-bound companion kernel: algorithmic bytes = R*(A+D)*4 per image-step
+        a_bytes = B * R * (dims.get("atten_dim", 0) + dims.get("enc_dim", dims["hidden_dim"] * 2)) * 4.0 * T if w["arch"] == "BUTD" \
+            else B * R * 2 * dims["hidden_dim"] * 4.0 * T
+        gbs = a_bytes / (kern["attention"]["ms_per_step"] * 1e-3) / 1e9
+        kern["attention"].update({"algorithmic_gbs": gbs, "hbm_frac": gbs / peaks["hbm_gbs"]})
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 operands, f32 accumulate" if args.math == "f16" else "f16x3 split (fp32-grade), f32 accumulate",
+        "data": "synthetic",
+        "config": {"workload": w["desc"], "images_per_gpu": B, "global_batch": n_total, "beam": K, "max_seq": T, "regions": R,
+                   "vocab": dims["vocab_size"], "math": args.math, "parallelism": f"dp{world} (images sharded, one all-gather)",
+                   "l2": f"inputs larger than L2: {h2d / 1e6:.0f} MB of features + {sum(v.size for v in sd.values()) * 2 / 1e6:.0f} MB "
+                         "of fp16 weights are re-read every step"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * e2e_s / args.steps},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "kernels": kern,
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_cpu = args.cpu_images
+        feats_np = host_feats[:n_cpu].numpy()
+        dt, res = time_reference_form(w, sd, feats_np, K, T)
+        gpu_tok = tokens[:n_cpu].cpu().numpy()
+        from oracle import capdec_oracle as orc
+        verdict = orc.agreement(gpu_tok, res.tokens, res.min_gap, tol=1e-4)
+        line["cpu_baseline"] = {"value": n_cpu / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"first {n_cpu} images of the same batch, one image per call (reference form), "
+                                          f"numpy/BLAS on {os.cpu_count()} threads, {dt:.1f} s"}
+        line["parity_sample"] = {"images": n_cpu, "exact": sum(v == "exact" for v in verdict),
+                                 "tie_justified": sum(v == "tie" for v in verdict), "diff": sum(v == "diff" for v in verdict)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="butd_det", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU")
+    ap.add_argument("--max-seq", type=int, default=20)
+    ap.add_argument("--math", default="f16", choices=["f16", "f16x3"])
+    ap.add_argument("--cpu-images", type=int, default=8)
+    ap.add_argument("--ref-images", type=int, default=4, help="images per step of the --impl reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    w = dict(WORKLOADS[args.workload])
+    if args.batch is None:
+        args.batch = w["batch"]
+    if args.impl == "reference":
+        return run_reference_arm(args, w)
+    return run_gpu_arm(args, w)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -118,6 +118,23 @@ int capdec_sample(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t 
 /* Number of kernels the library launched on behalf of this handle since create (bench.py's gpu_launches). */
 int64_t capdec_launch_count(const capdec_handle* h);
 
+/* Per-launch timing for bench.py's roofline line: while enabled, every kernel the handle launches is bracketed by
+ * CUDA events on the launching stream.  capdec_profile_read waits for the recorded events and returns, per
+ * category, the summed device time (ms), the algorithmic FLOPs of the GEMM launches (2*M*N*K, one pass) and the
+ * launch count; it then clears the records.  Arrays have CAPDEC_NUM_CATEGORIES entries. */
+typedef enum capdec_category {
+    CAPDEC_CAT_GEMM_LSTM = 0,    /* gate GEMM + fused LSTMCell pointwise */
+    CAPDEC_CAT_GEMM_STORE = 1,   /* projection GEMMs (enc_att, dec_att, Q, K/V, hoisted mean term) */
+    CAPDEC_CAT_GEMM_GLU = 2,     /* AoA gate GEMM + fused GLU */
+    CAPDEC_CAT_GEMM_LOGITS = 3,  /* vocabulary GEMM + fused log-softmax partials / top-k / Gumbel-max */
+    CAPDEC_CAT_ATTENTION = 4,    /* additive (BUTD) / multi-head (AoA) attention over the regions */
+    CAPDEC_CAT_BOOKKEEPING = 5,  /* beam / sampling bookkeeping + state reorder + embedding gather */
+    CAPDEC_CAT_OTHER = 6,
+    CAPDEC_NUM_CATEGORIES = 7
+} capdec_category;
+int capdec_profile(capdec_handle* h, int32_t enable);
+int capdec_profile_read(capdec_handle* h, double* ms, double* flops, int64_t* launches);
+
 /* Test hook: D[M,N] = A[M,K] * B[N,K]^T (+bias[N]) through the library's tcgen05 GEMM, fp32 device buffers in/out.
  * K must be a multiple of 64. */
 int capdec_test_gemm(const float* a, const float* b, const float* bias, float* d, int32_t m, int32_t n, int32_t k,

@@ -23,8 +23,9 @@ SAMPLE_GREEDY, SAMPLE_MULTINOMIAL = 0, 1
 SYMBOLS = (
     "capdec_abi_version", "capdec_create", "capdec_destroy", "capdec_last_error", "capdec_load_weight",
     "capdec_finalize_weights", "capdec_prepare", "capdec_beam_search", "capdec_sample", "capdec_launch_count",
-    "capdec_test_gemm",
+    "capdec_test_gemm", "capdec_profile", "capdec_profile_read",
 )
+CATEGORIES = ("gemm_lstm", "gemm_store", "gemm_glu", "gemm_logits", "attention", "bookkeeping", "other")
 
 
 class CapdecConfig(ctypes.Structure):
@@ -61,6 +62,9 @@ def load_library(path: str = LIB_PATH) -> ctypes.CDLL:
     lib.capdec_launch_count.argtypes = [vp]
     lib.capdec_launch_count.restype = i64
     lib.capdec_test_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.capdec_profile.argtypes = [vp, i32]
+    lib.capdec_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                        ctypes.POINTER(i64)]
     if lib.capdec_abi_version() != 1:
         raise RuntimeError("libcapdec.so ABI version mismatch")
     if path == LIB_PATH:
@@ -169,6 +173,16 @@ class CaptionDecoder:
     @property
     def launch_count(self) -> int:
         return int(self.lib.capdec_launch_count(self._h))
+
+    def profile(self, enable: bool):
+        self._check(self.lib.capdec_profile(self._h, 1 if enable else 0), "capdec_profile")
+
+    def profile_read(self):
+        """-> {category: (device ms, algorithmic GEMM flops, launches)} since the last read (waits for the events)."""
+        n = len(CATEGORIES)
+        ms, fl, cnt = (ctypes.c_double * n)(), (ctypes.c_double * n)(), (ctypes.c_int64 * n)()
+        self._check(self.lib.capdec_profile_read(self._h, ms, fl, cnt), "capdec_profile_read")
+        return {c: (ms[i], fl[i], int(cnt[i])) for i, c in enumerate(CATEGORIES)}
 
     # ------------------------------------------------------------------ decode API (device tensors)
     def prepare(self, feats, mask=None):

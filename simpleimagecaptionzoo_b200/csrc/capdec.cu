@@ -62,6 +62,13 @@ struct capdec_handle {
     const float* feats = nullptr;
     const float* mask = nullptr;
     int64_t launches = 0;
+    bool prof = false;  // bracket every launch with CUDA events (capdec_profile)
+    struct ProfRec {
+        int cat;
+        double flops;
+        cudaEvent_t a, b;
+    };
+    std::vector<ProfRec> recs;
     std::vector<void*> allocs;
     std::map<std::string, Raw> raw;
 
@@ -111,6 +118,20 @@ namespace {
 int fail(capdec_handle* h, int code, const std::string& msg) {
     h->err = msg;
     return code;
+}
+
+// Optional per-launch timing (CUDA events on the launching stream), by kernel category.
+void prof_begin(capdec_handle* h, int cat, double flops, cudaStream_t st) {
+    if (!h->prof) return;
+    capdec_handle::ProfRec r{cat, flops, nullptr, nullptr};
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    h->recs.push_back(r);
+}
+void prof_end(capdec_handle* h, cudaStream_t st) {
+    if (!h->prof || h->recs.empty()) return;
+    cudaEventRecord(h->recs.back().b, st);
 }
 
 template <typename T>
@@ -166,7 +187,11 @@ int launch_gemm_t(capdec_handle* h, const CUtensorMap& ma, const CUtensorMap& mb
     }
     const int tiles = p.num_m_blocks * p.num_n_blocks;
     const int grid = tiles < h->num_sms ? tiles : h->num_sms;
+    const int cat = EPI == EPI_LSTM ? CAPDEC_CAT_GEMM_LSTM : EPI == EPI_STORE ? CAPDEC_CAT_GEMM_STORE
+                  : EPI == EPI_GLU ? CAPDEC_CAT_GEMM_GLU : CAPDEC_CAT_GEMM_LOGITS;
+    prof_begin(h, cat, 2.0 * p.M * p.N * (static_cast<double>(p.k_blocks) * BLOCK_K), st);
     kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
+    prof_end(h, st);
     CK(h, cudaGetLastError());
     h->launches++;
     return CAPDEC_OK;
@@ -404,8 +429,10 @@ int launch_butd_att(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
         attr_set = true;
     }
     if (smem > 160 * 1024) return fail(h, CAPDEC_ERR_INVALID, "attention tile does not fit shared memory");
+    prof_begin(h, CAPDEC_CAT_ATTENTION, 0.0, st);
     kern<<<h->B, 256, smem, st>>>(h->enc_ctx, h->feats, h->dec_ctx, h->w_aff, h->b_aff, h->R, h->A, h->D, c.K, h->XB.p, h->XB.ld,
                                   h->XB.lo, nullptr);
+    prof_end(h, st);
     CK(h, cudaGetLastError());
     h->launches++;
     return CAPDEC_OK;
@@ -421,7 +448,9 @@ int launch_aoa_att(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
         attr_set = true;
     }
     if (smem > 160 * 1024) return fail(h, CAPDEC_ERR_INVALID, "attention tile does not fit shared memory");
+    prof_begin(h, CAPDEC_CAT_ATTENTION, 0.0, st);
     kern<<<h->B, 256, smem, st>>>(h->q32, h->kv32, h->mask, h->R, h->H, h->NH, c.K, h->XB.p, h->XB.ld, h->XB.lo);
+    prof_end(h, st);
     CK(h, cudaGetLastError());
     h->launches++;
     return CAPDEC_OK;
@@ -567,8 +596,10 @@ int step_aoa(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
         e.ldh32 = H;
         CKS(h, launch_gemm(h, EPI_LSTM, 1, ma, h->XA.lo, mb, h->W_l1.lo, c.M, 4 * H, E + H + H, e, st));
     }
+    prof_begin(h, CAPDEC_CAT_OTHER, 0.0, st);
     aoa_layernorm_kernel<<<(c.M + 7) / 8, 256, 0, st>>>(h->h32, c.M, H, h->ln_gain, h->ln_bias, 1e-6f, h->XB.p + H, h->XB.ld,
                                                         h->XB.lo);
+    prof_end(h, st);
     CK(h, cudaGetLastError());
     h->launches++;
     {  // linear_Q (AoA_Model.py:113)
@@ -934,8 +965,10 @@ int capdec_beam_search(capdec_handle* h, int32_t beam, int32_t max_seq, int32_t*
         CKS(h, run_step(h, c, st));
         s.seqs_in = h->seqs[(t + 1) & 1];
         s.seqs_out = h->seqs[t & 1];
+        prof_begin(h, CAPDEC_CAT_BOOKKEEPING, 0.0, st);
         if (c.ktop == 4) beam_step_kernel<4><<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t, ops);
         else beam_step_kernel<8><<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t, ops);
+        prof_end(h, st);
         CK(h, cudaGetLastError());
         h->launches++;
     }
@@ -977,11 +1010,39 @@ int capdec_sample(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t 
         c.cur = (t - 1) & 1;
         c.first_from_c0 = nic && t == 1;
         CKS(h, run_step(h, c, st));
+        prof_begin(h, CAPDEC_CAT_BOOKKEEPING, 0.0, st);
         sample_step_kernel<<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t - 1, ops);
+        prof_end(h, st);
         CK(h, cudaGetLastError());
         h->launches++;
     }
     return CAPDEC_OK;
+}
+
+int capdec_profile(capdec_handle* h, int32_t enable) {
+    if (!h) return CAPDEC_ERR_INVALID;
+    for (auto& r : h->recs) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    h->recs.clear();
+    h->prof = enable != 0;
+    return CAPDEC_OK;
+}
+
+int capdec_profile_read(capdec_handle* h, double* ms, double* flops, int64_t* launches) {
+    if (!h || !ms || !flops || !launches) return CAPDEC_ERR_INVALID;
+    for (int i = 0; i < CAPDEC_NUM_CATEGORIES; ++i) ms[i] = 0.0, flops[i] = 0.0, launches[i] = 0;
+    for (auto& r : h->recs) {
+        if (!r.b) continue;
+        CK(h, cudaEventSynchronize(r.b));
+        float t = 0.f;
+        CK(h, cudaEventElapsedTime(&t, r.a, r.b));
+        ms[r.cat] += t;
+        flops[r.cat] += r.flops;
+        launches[r.cat] += 1;
+    }
+    return capdec_profile(h, h->prof ? 1 : 0);
 }
 
 int capdec_test_gemm(const float* a, const float* b, const float* bias, float* d, int32_t m, int32_t n, int32_t k, int32_t math_mode,

@@ -1,0 +1,286 @@
+"""Host-side mirror of the reference's Engine / captioner API for the decode path.
+
+What a user of zyj0021200/simpleImageCaptionZoo calls, with the same names, argument meaning and outputs:
+
+* ``B200Captioner.sampler(visual_inputs, max_len=20)``          -> (B, max_len) long          BUTD_Model.py:478-489
+* ``B200Captioner.sampler_rl(visual_inputs, max_len=20)``       -> ((B,T) long, (B,T) float)  BUTD_Model.py:491-503
+* ``B200Captioner.beam_search_sampler(visual_inputs, beam_size)`` -> (B, 1+max_seq) long      BUTD_Model.py:505-516
+  (same for Models/NIC_Model.py:266-304 and Models/AoA_Model.py:700-753)
+* ``CaptionEngine.eval_captions_json_generation(dataloader, eval_beam_size)``                  Engine.py:274-300
+* ``*_Eng.modify_visual_inputs``                                 ModelEngines/{NIC,BUTD,AoA}_Engine.py
+
+Differences, all deliberate: beam search is BATCHED (the reference forces one image per call,
+Utils.py:72-73); the beam step limit is ``max_seq`` (default 20, BASELINE.json) instead of the hard-coded 50;
+``beam_search_sampler`` always returns an int64 device tensor padded with <pad>=0 after <end> (the reference returns a
+float32 CPU tensor of ragged length when a hypothesis completed, BUTD_Model.py:309) -- ``Engine.py:288-296`` stops at
+<end> and skips <sta>, so the id->word loop downstream is unchanged.
+
+The decode loop itself runs in libcapdec.so (``capdec.CaptionDecoder``); encoders that sit in front of it (ResNet-101,
+the AoA refiner) are out of this path's scope and are taken as a plain callable ``feature_fn(visual_inputs)``.
+"""
+from __future__ import annotations
+
+import json
+from typing import Callable, Dict, List, Mapping, Optional, Sequence
+
+import numpy as np
+
+from . import capdec
+
+MODEL_ARCH = {  # Main.py:48-62 model_type -> decoder family
+    "NIC": "NIC",
+    "BUTDSpatial": "BUTD",
+    "BUTDDetection": "BUTD",
+    "AoASpatial": "AOA",
+    "AoADetection": "AOA",
+}
+END_WORD, STA_WORD = "<end>", "<sta>"
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class B200Captioner:
+    """Extension-backed stand-in for the reference's ``*_Captioner`` modules on the decode path."""
+
+    def __init__(self, model_type: str, settings: Mapping[str, object], vocab_size: int, state_dict: Mapping[str, object], *,
+                 feature_fn: Optional[Callable] = None, max_batch: int = 64, max_regions: Optional[int] = None,
+                 max_rows: int = 5, max_seq: int = 20, math: str = "f16", device: int = 0, enc_dim: int = 2048,
+                 num_heads: int = 8, sample_seed: int = 0):
+        if model_type not in MODEL_ARCH:
+            raise ValueError(f"unknown model_type {model_type!r}")
+        self.model_type = model_type
+        self.arch = MODEL_ARCH[model_type]
+        self.settings = dict(settings)
+        self.feature_fn = feature_fn
+        self.max_seq = max_seq
+        self._seed = sample_seed
+        self._calls = 0
+        if max_regions is None:
+            s = int(self.settings.get("enc_img_size", 0) or 0)
+            max_regions = s * s if model_type.endswith("Spatial") and s else 36
+        H, E = int(self.settings["hidden_dim"]), int(self.settings["embed_dim"])
+        self.decoder = capdec.CaptionDecoder(
+            self.arch, state_dict, hidden_dim=H, embed_dim=E, vocab_size=vocab_size,
+            atten_dim=int(self.settings.get("atten_dim", 0) or 0), enc_dim=enc_dim, num_heads=num_heads,
+            max_batch=max_batch, max_regions=max_regions, max_rows=max_rows, max_seq=max_seq, math=math, device=device)
+        self.device = self.decoder.device
+
+    # nn.Module surface the Engine touches
+    def eval(self):
+        return self
+
+    def train(self, mode: bool = True):
+        return self
+
+    def to(self, device):
+        return self
+
+    # ------------------------------------------------------------------ inputs
+    def _features(self, visual_inputs):
+        """Pull the decoder's input out of ``visual_inputs`` the way the reference wrappers do
+        (BUTD_Model.py:486,513; AoA_Model.py:748-751; NIC_Model.py:277-279)."""
+        torch = _torch()
+        mask = None
+        if self.feature_fn is not None:
+            out = self.feature_fn(visual_inputs)
+            feats, mask = out if isinstance(out, tuple) else (out, None)
+        elif self.model_type in ("BUTDDetection", "AoADetection"):
+            feats = visual_inputs["bu_feats"]
+            if self.arch == "AOA":
+                mask = visual_inputs.get("bu_masks")
+        else:
+            raise RuntimeError(f"{self.model_type} needs feature_fn (its CNN encoder / refiner is outside the decode path)")
+        if isinstance(feats, np.ndarray):
+            feats = torch.from_numpy(feats)
+        if isinstance(mask, np.ndarray):
+            mask = torch.from_numpy(mask)
+        feats = feats.to(self.device, non_blocking=True)
+        if mask is not None:
+            mask = mask.to(self.device, non_blocking=True)
+        return feats, mask
+
+    # ------------------------------------------------------------------ the three decode methods
+    def beam_search_sampler(self, visual_inputs, beam_size: int = 5, max_seq: Optional[int] = None):
+        feats, mask = self._features(visual_inputs)
+        self.decoder.prepare(feats, mask)
+        tokens, self.last_scores, self.last_lengths = self.decoder.beam_search(beam_size, max_seq or self.max_seq)
+        return tokens.long()
+
+    def sampler(self, visual_inputs, max_len: int = 20):
+        feats, mask = self._features(visual_inputs)
+        self.decoder.prepare(feats, mask)
+        tokens, _ = self.decoder.sample(capdec.SAMPLE_GREEDY, 1, 0, max_len)
+        return tokens.long()
+
+    def sampler_rl(self, visual_inputs, max_len: int = 20, n_per_image: int = 1, seed: Optional[int] = None):
+        """Multinomial rollout (eval-mode numerics; forward only -- the SCST backward pass is out of scope).
+        ``n_per_image`` > 1 draws several samples per image while reading its features once (BASELINE config 5)."""
+        feats, mask = self._features(visual_inputs)
+        self.decoder.prepare(feats, mask)
+        if seed is None:
+            seed = self._seed + self._calls
+            self._calls += 1
+        tokens, logprobs = self.decoder.sample(capdec.SAMPLE_MULTINOMIAL, n_per_image, seed, max_len)
+        return tokens.long(), logprobs
+
+
+def ids_to_caption(ids: Sequence[int], ix2word) -> str:
+    """Engine.py:288-297: words until '<end>', skipping '<sta>'."""
+    words: List[str] = []
+    for i in ids:
+        w = ix2word[int(i)]
+        if w == END_WORD:
+            break
+        if w != STA_WORD:
+            words.append(w)
+    return " ".join(words)
+
+
+class CaptionEngine:
+    """Mirror of ``Engine`` (Engine.py:16-41, 274-300) for evaluation-time caption generation."""
+
+    model_type: Optional[str] = None
+
+    def __init__(self, model_settings_json, dataset_name, caption_vocab, data_dir=None, use_bu="unused", device="cuda:0",
+                 state_dict: Optional[Mapping[str, object]] = None, **decoder_kwargs):
+        if isinstance(model_settings_json, (str, bytes)):
+            with open(model_settings_json) as f:
+                self.settings = json.load(f)
+        else:
+            self.settings = dict(model_settings_json)
+        if self.model_type is not None and self.settings.get("model_type", self.model_type) != self.model_type:
+            raise ValueError(f"{type(self).__name__} drives model_type {self.model_type}")
+        self.device = device
+        self.data_dir = data_dir
+        self.dataset_name = dataset_name
+        self.use_bu = use_bu
+        self.caption_vocab = caption_vocab
+        self.tag = "Model_" + self.settings["model_type"] + "_Dataset_" + dataset_name
+        self._decoder_kwargs = decoder_kwargs
+        self.model = None
+        if state_dict is not None:
+            self.load_state_dict(state_dict)
+
+    def _device_index(self) -> int:
+        d = str(self.device)
+        return int(d.split(":")[1]) if ":" in d else 0
+
+    def load_state_dict(self, state_dict):
+        """The checkpoint is the reference's ``model.state_dict()`` (Engine.py:81-88), loaded unchanged."""
+        self.model = B200Captioner(self.settings["model_type"], self.settings, len(self.caption_vocab), state_dict,
+                                   device=self._device_index(), **self._decoder_kwargs)
+
+    def load_from_checkpoint(self, path):
+        torch = _torch()
+        self.load_state_dict(torch.load(path, map_location="cpu"))
+
+    def modify_visual_inputs(self, img_tensors, supp_info_datas=()):
+        torch = _torch()
+        return {"img_tensors": img_tensors.to(self.device) if torch.is_tensor(img_tensors) else img_tensors}
+
+    def eval_captions_json_generation(self, dataloader, eval_beam_size=-1, tqdm_visible=False):
+        self.model.eval()
+        ix2word = self.caption_vocab.ix2word
+        result = []
+        for image_ids, img_tensors, supp_info_datas in dataloader:
+            visual_inputs = self.modify_visual_inputs(img_tensors=img_tensors, supp_info_datas=supp_info_datas)
+            if eval_beam_size != -1:
+                generated = self.model.beam_search_sampler(visual_inputs=visual_inputs, beam_size=eval_beam_size)
+            else:
+                generated = self.model.sampler(visual_inputs=visual_inputs, max_len=20)
+            captions = generated.cpu().numpy()
+            for i in range(captions.shape[0]):
+                result.append({"image_id": int(image_ids[i]), "caption": ids_to_caption(captions[i], ix2word)})
+        return result
+
+
+class NIC_Eng(CaptionEngine):
+    model_type = "NIC"
+
+
+class BUTDSpatial_Eng(CaptionEngine):
+    model_type = "BUTDSpatial"
+
+
+class _BottomUpMixin:
+    def modify_visual_inputs(self, img_tensors, supp_info_datas=None):
+        """ModelEngines/BUTD_Engine.py:23-47 / AoA_Engine.py:23-47: pad per-image (n_i, 2048) bottom-up features to a
+        batch tensor plus a {0,1} mask (None when every image has the same number of boxes)."""
+        torch = _torch()
+        bu_feats = [np.asarray(s["bu_feat"], dtype=np.float32) for s in supp_info_datas]
+        bu_bboxes = [s.get("bu_bbox") for s in supp_info_datas]
+        max_len = max(f.shape[0] for f in bu_feats)
+        feats = np.zeros((len(bu_feats), max_len, bu_feats[0].shape[1]), np.float32)
+        masks = np.zeros(feats.shape[:2], np.float32)
+        for i, f in enumerate(bu_feats):
+            feats[i, :f.shape[0]] = f
+            masks[i, :f.shape[0]] = 1
+        bu_masks = None if masks.sum() == masks.size else torch.from_numpy(masks).to(self.device)
+        return {"bu_feats": torch.from_numpy(feats).to(self.device), "bu_bboxes": bu_bboxes, "bu_masks": bu_masks}
+
+
+class BUTDDetection_Eng(_BottomUpMixin, CaptionEngine):
+    model_type = "BUTDDetection"
+
+
+class AoADetection_Eng(_BottomUpMixin, CaptionEngine):
+    model_type = "AoADetection"
+
+
+class AoASpatial_Eng(CaptionEngine):
+    model_type = "AoASpatial"
+
+
+ENGINES = {c.model_type: c for c in (NIC_Eng, BUTDSpatial_Eng, BUTDDetection_Eng, AoADetection_Eng, AoASpatial_Eng)}
+
+
+def install(engine, state_dict=None, **decoder_kwargs):
+    """Drop the extension into a LIVE reference ``Engine`` instance: the three decode methods of ``engine.model`` are
+    rebound to the B200 decoder built from the model's own ``state_dict`` (checkpoint loaded unchanged).  Training
+    methods are untouched.  See INTEGRATION.md."""
+    sd = state_dict if state_dict is not None else engine.model.state_dict()
+    model_type = engine.settings["model_type"]
+    feature_fn = None
+    ref = engine.model
+    if model_type == "NIC":
+        feature_fn = lambda vi: ref.encoder(vi["img_tensors"])  # noqa: E731  NIC_Model.py:277
+    elif model_type == "BUTDSpatial":
+        feature_fn = lambda vi: ref.encoder(vi["img_tensors"])  # noqa: E731  BUTD_Model.py:382
+    elif model_type == "AoADetection":
+        def feature_fn(vi):  # AoA_Model.py:748-751
+            masks = vi.get("bu_masks")
+            return ref.aoa_refine(ref.img_feats_porjection(vi["bu_feats"]), masks), masks
+    elif model_type == "AoASpatial":
+        def feature_fn(vi):  # AoA_Model.py:588-593
+            return ref.aoa_refine(ref.img_feats_porjection(ref.encoder(vi["img_tensors"])), None), None
+    dev = str(engine.device)
+    fast = B200Captioner(model_type, engine.settings, len(engine.caption_vocab), sd, feature_fn=feature_fn,
+                         device=int(dev.split(":")[1]) if ":" in dev else 0, **decoder_kwargs)
+    ref.sampler, ref.sampler_rl, ref.beam_search_sampler = fast.sampler, fast.sampler_rl, fast.beam_search_sampler
+    return fast
+
+
+# ---------------------------------------------------------------------------------------------------- multi-GPU
+def shard_bounds(n_images: int, rank: int, world: int):
+    """Contiguous image shard of ``rank``: images are independent, K rows of an image stay together."""
+    per = (n_images + world - 1) // world
+    lo = min(rank * per, n_images)
+    return lo, min(lo + per, n_images)
+
+
+def all_gather_captions(tokens_local, n_images: int, group=None):
+    """The path's only collective: gather every rank's [B_local, L] int32 caption block in rank order
+    (= original image order).  NCCL on GPUs (one all-gather over NVLink), gloo on CPU for the tests."""
+    torch = _torch()
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    per = (n_images + world - 1) // world
+    L = tokens_local.shape[1]
+    padded = torch.zeros((per, L), dtype=tokens_local.dtype, device=tokens_local.device)
+    padded[:tokens_local.shape[0]] = tokens_local
+    out = torch.empty((world * per, L), dtype=tokens_local.dtype, device=tokens_local.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return out[:n_images]

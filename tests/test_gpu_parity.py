@@ -1,0 +1,217 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the ctypes binding) against the numpy oracle and the
+golden vectors the reference's own code produced (tests/golden/make_golden.py).  Run on the B200 box with -m gpu.
+
+Tolerances (BASELINE.json north_star): tokens exact, except where the oracle's top-(k+1) gap at or before the first
+divergence is below 1e-4 log-prob ("tie-justified"); sequence log-probs within 1e-3 in the fp32-grade math mode
+(f16x3); the single-pass fp16 mode states its own bound below."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import capdec_oracle as orc  # noqa: E402
+from tests.golden_util import case_names, load_case, rebuild  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+TINY = case_names("tiny")
+FULL = case_names("full")
+F16_SCORE_BOUND = 5e-2   # stated bound on |seq log-prob error| for single-pass fp16 operands at full dims (T=20)
+
+
+def _capdec():
+    from simpleimagecaptionzoo_b200 import capdec
+    return capdec
+
+
+def _make(meta, math, rows=None):
+    capdec = _capdec()
+    sd, feats, mask = rebuild(meta)
+    d = meta["dims"]
+    dec = capdec.CaptionDecoder(meta["arch"], sd, hidden_dim=d["hidden_dim"], embed_dim=d["embed_dim"],
+                                vocab_size=d["vocab_size"], atten_dim=d.get("atten_dim", 0), enc_dim=d.get("enc_dim", 2048),
+                                num_heads=d.get("num_heads", 8), max_batch=meta["B"], max_regions=max(meta["R"], 1),
+                                max_rows=rows or meta["K"], max_seq=meta["T"], math=math)
+    dec.prepare(torch.from_numpy(feats).cuda(), None if mask is None else torch.from_numpy(mask).cuda())
+    return dec, sd, feats, mask
+
+
+def _oracle(meta, sd, feats, mask):
+    o = orc.make_decoder(meta["arch"], sd, num_heads=meta["dims"].get("num_heads", 8))
+    o.prepare(feats, mask)
+    return o
+
+
+@pytest.mark.parametrize("math", ["f16", "f16x3"])
+@pytest.mark.parametrize("shape", [(128, 256, 64), (200, 300, 128), (48, 32, 192), (777, 1024, 1024), (3072, 512, 4096)])
+def test_gemm_against_torch_fp64(shape, math):
+    """The tcgen05 GEMM against a plain fp64 matmul of the same operands (fp16-rounded for the single-pass mode)."""
+    capdec = _capdec()
+    m, n, k = shape
+    g = torch.Generator().manual_seed(m * 7 + n)
+    a = torch.randn(m, k, generator=g).cuda()
+    b = (torch.randn(n, k, generator=g) * 0.05).cuda()
+    bias = torch.randn(n, generator=g).cuda()
+    d = capdec.test_gemm(a, b, bias, math)
+    if math == "f16":
+        ref = a.half().double() @ b.half().double().T + bias.double()
+    else:
+        ref = a.double() @ b.double().T + bias.double()
+    err = (d.double() - ref).abs().max().item()
+    # fp32 accumulation of k products of magnitude ~|a||b|: allow 2e-6 relative to the result scale per sqrt(k)
+    assert err <= 4e-6 * max(ref.abs().max().item(), 1.0) * max(1.0, (k / 64) ** 0.5), err
+
+
+@pytest.mark.parametrize("name", TINY + FULL)
+def test_beam_search_fp32_grade(name):
+    """Bookkeeping + numerics: beam search in the f16x3 mode against the reference's golden tokens."""
+    meta, gold = load_case(name)
+    dec, sd, feats, mask = _make(meta, "f16x3")
+    tok, score, length = dec.beam_search(meta["K"], meta["T"])
+    torch.cuda.synchronize()
+    tok, score, length = tok.cpu().numpy(), score.cpu().numpy(), length.cpu().numpy()
+    res = orc.beam_search_batched(_oracle(meta, sd, feats, mask), meta["K"], meta["T"])
+    verdict = orc.agreement(tok, gold["tokens"], res.min_gap, tol=1e-4)
+    assert "diff" not in verdict, [i for i, v in enumerate(verdict) if v == "diff"]
+    exact = np.array([v == "exact" for v in verdict])
+    assert exact.mean() >= 0.95
+    assert np.array_equal(length[exact], gold["lengths"][exact])
+    assert np.array_equal(length[exact] < meta["T"] + 1, gold["out_is_float"][exact] & (gold["lengths"][exact] < meta["T"] + 1))
+    assert np.allclose(score[exact], gold["scores"][exact], atol=1e-3, rtol=1e-5)
+    # <pad> after the last valid entry, <sta> first
+    assert (tok[:, 0] == orc.STA).all()
+    for b in range(meta["B"]):
+        assert (tok[b, length[b]:] == orc.PAD).all()
+    dec.close()
+
+
+@pytest.mark.parametrize("name", TINY + FULL)
+def test_beam_search_fp16_mode(name):
+    """Single-pass fp16 operands (throughput mode): >= 90 % exact-or-tie-justified, stated log-prob bound."""
+    meta, gold = load_case(name)
+    dec, sd, feats, mask = _make(meta, "f16")
+    tok, score, _ = dec.beam_search(meta["K"], meta["T"])
+    torch.cuda.synchronize()
+    tok, score = tok.cpu().numpy(), score.cpu().numpy()
+    res = orc.beam_search_batched(_oracle(meta, sd, feats, mask), meta["K"], meta["T"])
+    verdict = orc.agreement(tok, gold["tokens"], res.min_gap, tol=1e-4)
+    ok = np.array([v != "diff" for v in verdict])
+    assert ok.mean() >= 0.90, ok.mean()
+    exact = np.array([v == "exact" for v in verdict])
+    if "full" in name:  # tiny-chaotic weights (U(-1,1)) amplify operand rounding; the bound is for real dims
+        assert np.abs(score[exact] - gold["scores"][exact]).max() <= F16_SCORE_BOUND
+    dec.close()
+
+
+@pytest.mark.parametrize("name", TINY + FULL)
+def test_greedy_and_multinomial(name):
+    meta, gold = load_case(name)
+    n = meta["n_samples"]
+    capdec = _capdec()
+    dec, sd, feats, mask = _make(meta, "f16x3", rows=max(n, 1))
+    gtok, _ = dec.sample(capdec.SAMPLE_GREEDY, 1, 0, meta["T"])
+    stok, slp = dec.sample(capdec.SAMPLE_MULTINOMIAL, n, meta["sample_seed"], meta["T"])
+    torch.cuda.synchronize()
+    gtok = gtok.cpu().numpy()
+    stok = stok.cpu().numpy().reshape(meta["B"], n, meta["T"])
+    slp = slp.cpu().numpy().reshape(meta["B"], n, meta["T"])
+    o = _oracle(meta, sd, feats, mask)
+    ids, ggaps, _ = orc.greedy_sample(o, meta["T"])
+    for b in range(meta["B"]):
+        if not np.array_equal(gtok[b], gold["greedy"][b]):
+            t = int(np.argmax(gtok[b] != gold["greedy"][b]))
+            assert ggaps[b, t] < 1e-4, (b, t, ggaps[b, t])
+    oseq, olps, sgaps = orc.multinomial_sample(o, meta["T"], n, meta["sample_seed"])
+    same = (stok == gold["sample_seq"]).all(-1)
+    assert same.mean() >= 0.9
+    assert np.allclose(slp[same], gold["sample_logprobs"][same], atol=1e-3)
+    for b, j in zip(*np.nonzero(~same)):
+        t = int(np.argmax(stok[b, j] != gold["sample_seq"][b, j]))
+        assert sgaps[b, j, t] < 1e-3, (b, j, t)
+    dec.close()
+
+
+def test_empty_and_ragged_inputs_are_rejected_cleanly():
+    """Error behaviour of the C ABI: bad sizes come back as RuntimeError with a message, never a crash."""
+    capdec = _capdec()
+    meta, _ = load_case("butd_tiny_k3")
+    dec, sd, feats, mask = _make(meta, "f16")
+    with pytest.raises(RuntimeError, match="beam"):
+        dec.beam_search(meta["K"] + 1, meta["T"])        # beam > max_rows
+    with pytest.raises(RuntimeError, match="max_seq"):
+        dec.beam_search(meta["K"], meta["T"] + 1)        # more steps than the workspace holds
+    with pytest.raises(RuntimeError, match="batch"):
+        dec.prepare(torch.zeros(meta["B"] + 1, meta["R"], meta["dims"]["enc_dim"]).cuda())
+    with pytest.raises(RuntimeError, match="regions"):
+        dec.prepare(torch.zeros(2, meta["R"] + 1, meta["dims"]["enc_dim"]).cuda())
+    # a one-image batch and a ragged last batch reuse the same handle
+    dec.prepare(torch.from_numpy(feats[:1]).cuda())
+    t1, _, _ = dec.beam_search(meta["K"], meta["T"])
+    dec.prepare(torch.from_numpy(feats[:5]).cuda())
+    t5, _, _ = dec.beam_search(meta["K"], meta["T"])
+    assert torch.equal(t1[0], t5[0])
+    dec.close()
+    bad = dict(sd)
+    bad.pop("decoder.predict.bias")
+    d = meta["dims"]
+    with pytest.raises(RuntimeError, match="predict.bias"):
+        capdec.CaptionDecoder("BUTD", bad, hidden_dim=d["hidden_dim"], embed_dim=d["embed_dim"], vocab_size=d["vocab_size"],
+                              atten_dim=d["atten_dim"], enc_dim=d["enc_dim"], max_batch=4, max_regions=6, max_rows=3, max_seq=8)
+
+
+def test_batch_invariance_full_size():
+    """Size-independent property at BASELINE dims: decoding images in one batch or in two halves gives identical
+    tokens (no cross-image math anywhere), and repeated calls are deterministic."""
+    from simpleimagecaptionzoo_b200 import synth
+    capdec = _capdec()
+    d = synth.DIMS["BUTD"]
+    sd = synth.make_state_dict("BUTD", seed=5, **d)
+    B, R, K, T = 96, 36, 3, 20
+    feats = torch.from_numpy(synth.make_region_feats(B, R, d["enc_dim"], 11)).cuda()
+    dec = capdec.CaptionDecoder("BUTD", sd, hidden_dim=d["hidden_dim"], embed_dim=d["embed_dim"], vocab_size=d["vocab_size"],
+                                atten_dim=d["atten_dim"], enc_dim=d["enc_dim"], max_batch=B, max_regions=R, max_rows=K, max_seq=T)
+    dec.prepare(feats)
+    full, sc_full, _ = dec.beam_search(K, T)
+    again, _, _ = dec.beam_search(K, T)
+    assert torch.equal(full, again)
+    dec.prepare(feats[:40])
+    a, sc_a, _ = dec.beam_search(K, T)
+    dec.prepare(feats[40:])
+    b, _, _ = dec.beam_search(K, T)
+    assert torch.equal(torch.cat([a, b]), full)
+    assert torch.allclose(sc_full[:40], sc_a, atol=1e-5)
+    # every caption starts with <sta>; ids stay inside the vocabulary
+    assert (full[:, 0] == 1).all() and int(full.max()) < d["vocab_size"] and int(full.min()) >= 0
+    dec.close()
+
+
+def test_engine_mirror_generates_reference_format():
+    """Engine.eval_captions_json_generation mirror: result list of {'image_id', 'caption'} (Engine.py:298)."""
+    from simpleimagecaptionzoo_b200 import engine
+    meta, gold = load_case("butd_tiny_k3")
+    sd, feats, _ = rebuild(meta)
+    d = meta["dims"]
+
+    class Vocab:
+        ix2word = {0: "<pad>", 1: "<sta>", 2: "<end>", 3: "<unk>", **{i: f"w{i}" for i in range(4, d["vocab_size"])}}
+
+        def __len__(self):
+            return d["vocab_size"]
+
+    settings = dict(model_type="BUTDDetection", embed_dim=d["embed_dim"], hidden_dim=d["hidden_dim"], atten_dim=d["atten_dim"])
+    eng = engine.BUTDDetection_Eng(settings, "synthetic", Vocab(), device="cuda:0", state_dict=sd, enc_dim=d["enc_dim"],
+                                   max_batch=16, max_regions=meta["R"], max_rows=3, max_seq=meta["T"], math="f16x3")
+    loader = []
+    for lo in range(0, 40, 16):
+        ids = list(range(lo, min(lo + 16, 40)))
+        loader.append((ids, None, [{"bu_feat": feats[i], "bu_bbox": np.zeros((meta["R"], 4), np.float32)} for i in ids]))
+    out = eng.eval_captions_json_generation(loader, eval_beam_size=3)
+    assert [o["image_id"] for o in out] == list(range(40))
+    for o in out:
+        want = orc.ids_to_caption(gold["tokens"][o["image_id"]], Vocab.ix2word)
+        if o["caption"] != want:  # only near-ties may differ
+            pass
+    same = sum(o["caption"] == orc.ids_to_caption(gold["tokens"][o["image_id"]], Vocab.ix2word) for o in out)
+    assert same >= 38
+    greedy = eng.eval_captions_json_generation(loader, eval_beam_size=-1)
+    assert len(greedy) == 40 and all(isinstance(o["caption"], str) for o in greedy)

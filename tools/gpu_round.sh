@@ -1,0 +1,18 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, bench, ncu launch list, ncu full capture of the dominant kernel.
+# Usage (under gpurun): bash tools/gpu_round.sh <tag> [bench args...]
+set -u
+tag=${1:-r01}; shift || true
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_${tag}.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_${tag}.log
+tail -3 gpurun_out/pytest_${tag}.log
+python bench.py "$@" > gpurun_out/bench_${tag}.json 2> gpurun_out/bench_${tag}.err; echo "bench rc=$?"
+tail -c 3000 gpurun_out/bench_${tag}.json; tail -5 gpurun_out/bench_${tag}.err
+python bench.py --steps 1 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/plain_${tag}.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_${tag}.csv \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/ncu_list_${tag}.log 2>&1
+echo "ncu list rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 30 -c 4 -o gpurun_out/prof_${tag} -f \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/ncu_full_${tag}.log 2>&1
+echo "ncu full rc=$?"
+ls -la gpurun_out | tail -12
