@@ -70,7 +70,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self._nvml = None
         try:
             import pynvml
@@ -85,7 +85,7 @@ class ClockSampler(threading.Thread):
              0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 if self._nvml is not None:
                     self.samples.append(self._nvml.nvmlDeviceGetClockInfo(self._h, self._nvml.NVML_CLOCK_SM))
@@ -108,10 +108,10 @@ class ClockSampler(threading.Thread):
                             self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(self.period)
+            self._halt.wait(self.period)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=5)
         s = sorted(self.samples)
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
