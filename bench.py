@@ -66,7 +66,7 @@ def make_inputs(w, batch, seed):
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons of one GPU while the timed region runs (NVML; nvidia-smi fallback)."""
 
-    def __init__(self, index, period=0.1):
+    def __init__(self, index, period=0.02):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -292,7 +292,8 @@ def run_gpu_arm(args, w):
                 "flops_per_launch": dfl / dcnt, "us_per_launch": 1e3 * dms / dcnt,
                 "share_of_step": dms / prof_steps / sum(v["ms_per_step"] for v in kern.values())}
     if "attention" in kern:  # HBM-bound companion kernel: algorithmic bytes = R*(A+D)*4 per image-step
-        a_bytes = B * R * (dims.get("atten_dim", 0) + dims.get("enc_dim", dims["hidden_dim"] * 2)) * 4.0 * T if w["arch"] == "BUTD" \
+        esz = 2.0 if (args.math == "f16" and w["arch"] == "BUTD") else 4.0  # fp16 mode reads the fp16 feature copies
+        a_bytes = B * R * (dims.get("atten_dim", 0) + dims.get("enc_dim", dims["hidden_dim"] * 2)) * esz * T if w["arch"] == "BUTD" \
             else B * R * 2 * dims["hidden_dim"] * 4.0 * T
         gbs = a_bytes / (kern["attention"]["ms_per_step"] * 1e-3) / 1e9
         kern["attention"].update({"algorithmic_gbs": gbs, "hbm_frac": gbs / peaks["hbm_gbs"]})
@@ -336,7 +337,7 @@ def run_gpu_arm(args, w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="butd_det", choices=sorted(WORKLOADS))

@@ -140,6 +140,10 @@ int capdec_profile_read(capdec_handle* h, double* ms, double* flops, int64_t* la
 int capdec_test_gemm(const float* a, const float* b, const float* bias, float* d, int32_t m, int32_t n, int32_t k,
                      int32_t math_mode, void* stream);
 
+/* Test hook: mean device time (us) of `iters` back-to-back launches of one GEMM shape with epilogue `epi`
+ * (0 = store, 1 = LSTM with N = 4*H gate-interleaved columns, 3 = logits top-k) on synthetic operands. */
+int capdec_test_gemm_time(int32_t m, int32_t n, int32_t k, int32_t epi, int32_t math_mode, int32_t iters, float* us_per_launch);
+
 #ifdef __cplusplus
 }
 #endif

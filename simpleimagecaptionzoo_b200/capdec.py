@@ -23,7 +23,7 @@ SAMPLE_GREEDY, SAMPLE_MULTINOMIAL = 0, 1
 SYMBOLS = (
     "capdec_abi_version", "capdec_create", "capdec_destroy", "capdec_last_error", "capdec_load_weight",
     "capdec_finalize_weights", "capdec_prepare", "capdec_beam_search", "capdec_sample", "capdec_launch_count",
-    "capdec_test_gemm", "capdec_profile", "capdec_profile_read",
+    "capdec_test_gemm", "capdec_profile", "capdec_profile_read", "capdec_test_gemm_time",
 )
 CATEGORIES = ("gemm_lstm", "gemm_store", "gemm_glu", "gemm_logits", "attention", "bookkeeping", "other")
 
@@ -65,6 +65,7 @@ def load_library(path: str = LIB_PATH) -> ctypes.CDLL:
     lib.capdec_profile.argtypes = [vp, i32]
     lib.capdec_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                         ctypes.POINTER(i64)]
+    lib.capdec_test_gemm_time.argtypes = [i32, i32, i32, i32, i32, i32, ctypes.POINTER(ctypes.c_float)]
     if lib.capdec_abi_version() != 1:
         raise RuntimeError("libcapdec.so ABI version mismatch")
     if path == LIB_PATH:
@@ -97,6 +98,16 @@ def test_gemm(a, b, bias=None, math: str = "f16"):
     if rc != 0:
         raise RuntimeError(f"capdec_test_gemm failed ({rc}): {lib.capdec_last_error(None).decode()}")
     return d
+
+
+def gemm_time_us(m: int, n: int, k: int, epi: int = 0, math: str = "f16", iters: int = 20) -> float:
+    """Mean device time of one GEMM launch of the given shape / epilogue (test + tuning hook)."""
+    lib = load_library()
+    us = ctypes.c_float()
+    rc = lib.capdec_test_gemm_time(m, n, k, epi, MATH[math], iters, ctypes.byref(us))
+    if rc != 0:
+        raise RuntimeError(f"capdec_test_gemm_time failed ({rc}): {lib.capdec_last_error(None).decode()}")
+    return float(us.value)
 
 
 class CaptionDecoder:

@@ -86,7 +86,7 @@ struct capdec_handle {
     double* scale_tmp = nullptr;
 
     // activations / workspace
-    Act16 feats16, mean16, XA, XB, Hb, Hb2, Xp, H0;
+    Act16 feats16, enc16, mean16, XA, XB, Hb, Hb2, Xp, H0;
     float *enc_ctx = nullptr, *G0 = nullptr, *dec_ctx = nullptr, *kv32 = nullptr, *mean32 = nullptr, *q32 = nullptr,
           *ctx32 = nullptr, *h32 = nullptr, *c0 = nullptr;
     float* c1[2] = {nullptr, nullptr};
@@ -419,10 +419,10 @@ int run_logits(capdec_handle* h, const Act16& a, const StepCtx& c, cudaStream_t 
     return launch_gemm(h, c.logits_epi, c.ktop, ma, a.lo, mb, h->W_pred.lo, c.M, h->V, h->H, e, st);
 }
 
-template <int KR>
-int launch_butd_att(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
+template <int KR, typename T>
+int launch_butd_att_t(capdec_handle* h, const StepCtx& c, const T* enc, const T* feats, int feats_ld, cudaStream_t st) {
     static bool attr_set = false;
-    auto kern = butd_attention_kernel<KR>;
+    auto kern = butd_attention_kernel<KR, T>;
     const size_t smem = (static_cast<size_t>(KR) * h->A + h->A + static_cast<size_t>(KR) * h->R) * sizeof(float);
     if (!attr_set) {
         CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -430,12 +430,20 @@ int launch_butd_att(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
     }
     if (smem > 160 * 1024) return fail(h, CAPDEC_ERR_INVALID, "attention tile does not fit shared memory");
     prof_begin(h, CAPDEC_CAT_ATTENTION, 0.0, st);
-    kern<<<h->B, 256, smem, st>>>(h->enc_ctx, h->feats, h->dec_ctx, h->w_aff, h->b_aff, h->R, h->A, h->D, c.K, h->XB.p, h->XB.ld,
+    kern<<<h->B, 256, smem, st>>>(enc, feats, feats_ld, h->dec_ctx, h->w_aff, h->b_aff, h->R, h->A, h->D, c.K, h->XB.p, h->XB.ld,
                                   h->XB.lo, nullptr);
     prof_end(h, st);
     CK(h, cudaGetLastError());
     h->launches++;
     return CAPDEC_OK;
+}
+
+// fp16 mode reads the fp16 copies (projected features written by the projection GEMM, raw features converted for
+// it); the fp32-grade mode reads the caller's fp32 features and the fp32 projection.
+template <int KR>
+int launch_butd_att(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
+    if (h->split) return launch_butd_att_t<KR, float>(h, c, h->enc_ctx, h->feats, h->D, st);
+    return launch_butd_att_t<KR, __half>(h, c, h->enc16.p, h->feats16.p, h->feats16.ld, st);
 }
 
 template <int KR>
@@ -717,7 +725,7 @@ static int create_impl(capdec_handle* h) {
     if (prop.major != 10) return fail(h, CAPDEC_ERR_CUDA, "libcapdec needs an sm_100a (B200) device; there is no fallback path");
     h->num_sms = prop.multiProcessorCount;
     h->Mmax = h->Bmax * h->Kmax;
-    h->n_tiles_v = (V + BN - 1) / BN;
+    h->n_tiles_v = ((V + BN - 1) / BN) * EPI_SPLIT;  // partial slots per row: (N tile, column share)
     const int M = h->Mmax;
 
     CKS(h, dalloc(h, &h->scale_tmp, static_cast<size_t>(V > 4 * H ? V : 4 * H)));
@@ -754,7 +762,8 @@ static int create_impl(capdec_handle* h) {
         CKS(h, dalloc(h, &h->w_aff, A));
         CKS(h, alloc_act(h, &h->feats16, static_cast<int>(BR), D));
         CKS(h, alloc_act(h, &h->mean16, h->Bmax, D));
-        CKS(h, dalloc(h, &h->enc_ctx, BR * A));
+        if (h->split) CKS(h, dalloc(h, &h->enc_ctx, BR * A));
+        else CKS(h, alloc_act(h, &h->enc16, static_cast<int>(BR), A));
         CKS(h, dalloc(h, &h->G0, static_cast<size_t>(h->Bmax) * 4 * H));
         CKS(h, alloc_act(h, &h->XA, M, H + E + H));
         CKS(h, alloc_act(h, &h->XB, M, D + H + H));
@@ -897,8 +906,13 @@ int capdec_prepare(capdec_handle* h, const float* feats, const float* mask, int3
                 CKS(h, map_b(h, &mb, h->W_aux1));
                 EpiParams e{};
                 e.bias = h->b_aux1;
-                e.out32 = h->enc_ctx;
-                e.ld32 = A;
+                if (h->split) {
+                    e.out32 = h->enc_ctx;
+                    e.ld32 = A;
+                } else {
+                    e.out16 = h->enc16.p;
+                    e.ld16 = h->enc16.ld;
+                }
                 CKS(h, launch_gemm(h, EPI_STORE, 1, ma, h->feats16.lo, mb, h->W_aux1.lo, static_cast<int>(BR), A, D, e, st));
             }
             {  // hoisted, step-invariant part of the top-down LSTM gates: W_ih[:, mean] * mean + b_ih + b_hh
@@ -1081,6 +1095,77 @@ int capdec_test_gemm(const float* a, const float* b, const float* bias, float* d
             status = CAPDEC_ERR_CUDA;
         }
     } while (0);
+    for (void* p : h->allocs) cudaFree(p);
+    if (status != CAPDEC_OK) g_create_error = h->err;
+    return status;
+}
+
+// Test hook: time `iters` back-to-back launches of one GEMM shape with the given epilogue on synthetic operands.
+int capdec_test_gemm_time(int32_t m, int32_t n, int32_t k, int32_t epi, int32_t math_mode, int32_t iters, float* us_per_launch) {
+    capdec_handle tmp;
+    capdec_handle* h = &tmp;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) {
+        g_create_error = "capdec_test_gemm_time needs an sm_100a device";
+        return CAPDEC_ERR_CUDA;
+    }
+    h->cfg.device = dev;
+    h->num_sms = prop.multiProcessorCount;
+    h->split = math_mode == CAPDEC_MATH_F16X3;
+    int status = CAPDEC_OK;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    do {
+        Act16 A16, B16, H16;
+        float *bias = nullptr, *c0 = nullptr, *c1 = nullptr, *out = nullptr, *part = nullptr;
+        if ((status = alloc_act(h, &A16, m, k)) != CAPDEC_OK) break;
+        if ((status = alloc_act(h, &B16, n, k)) != CAPDEC_OK) break;
+        fill_f16_kernel<<<1024, 256>>>(A16.p, static_cast<size_t>(m) * A16.ld, 0.01f);
+        fill_f16_kernel<<<1024, 256>>>(B16.p, static_cast<size_t>(n) * B16.ld, 0.01f);
+        if ((status = dalloc(h, &bias, n)) != CAPDEC_OK) break;
+        CUtensorMap ma, mb;
+        if ((status = map_a(h, &ma, A16)) != CAPDEC_OK) break;
+        if ((status = map_b(h, &mb, B16)) != CAPDEC_OK) break;
+        EpiParams e{};
+        e.bias = bias;
+        if (epi == EPI_STORE) {
+            if ((status = dalloc(h, &out, static_cast<size_t>(m) * n)) != CAPDEC_OK) break;
+            e.out32 = out;
+            e.ld32 = n;
+        } else if (epi == EPI_LSTM) {
+            if ((status = dalloc(h, &c0, static_cast<size_t>(m) * n / 4)) != CAPDEC_OK) break;
+            if ((status = dalloc(h, &c1, static_cast<size_t>(m) * n / 4)) != CAPDEC_OK) break;
+            if ((status = alloc_act(h, &H16, m, n / 4)) != CAPDEC_OK) break;
+            e.c_in = c0, e.c_out = c1, e.ldc = n / 4;
+            e.out16 = H16.p, e.ld16 = H16.ld, e.lo16 = H16.lo;
+        } else if (epi == EPI_TOPK) {
+            const int nt = ((n + BN - 1) / BN) * EPI_SPLIT;
+            if ((status = dalloc(h, &part, static_cast<size_t>(m) * nt * topk_part_stride(4))) != CAPDEC_OK) break;
+            e.part = part;
+            e.n_tiles = nt;
+        } else {
+            status = fail(h, CAPDEC_ERR_INVALID, "unsupported epilogue for the timing hook");
+            break;
+        }
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        for (int i = 0; i < 3 && status == CAPDEC_OK; ++i) status = launch_gemm(h, epi, 4, ma, A16.lo, mb, B16.lo, m, n, k, e, nullptr);
+        if (status != CAPDEC_OK) break;
+        cudaEventRecord(e0, nullptr);
+        for (int i = 0; i < iters && status == CAPDEC_OK; ++i) status = launch_gemm(h, epi, 4, ma, A16.lo, mb, B16.lo, m, n, k, e, nullptr);
+        cudaEventRecord(e1, nullptr);
+        cudaError_t ce = cudaEventSynchronize(e1);
+        if (ce != cudaSuccess) {
+            status = fail(h, CAPDEC_ERR_CUDA, std::string("gemm timing: ") + cudaGetErrorString(ce));
+            break;
+        }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *us_per_launch = 1e3f * ms / iters;
+    } while (0);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
     for (void* p : h->allocs) cudaFree(p);
     if (status != CAPDEC_OK) g_create_error = h->err;
     return status;

@@ -2,8 +2,8 @@
 //
 //   D[M,N] = A[M,K] * B[N,K]^T      A, B fp16 K-major (row-major, K contiguous), fp32 accumulate in TMEM
 //
-// Roles (192 threads, one CTA per SM):  warp 0 = TMA producer, warp 1 = TMEM owner + tcgen05.mma issuer,
-// warps 2-5 = epilogue (each owns one 32-lane quarter of the 128-row accumulator; thread == output row).
+// Roles (320 threads, one CTA per SM):  warp 0 = TMA producer, warp 1 = TMEM owner + tcgen05.mma issuer,
+// warps 2-9 = epilogue (thread == output row == TMEM lane; two warps share a 32-lane quarter and split the columns).
 // Pipelines: smem ring full/empty (TMA <-> MMA) and a 2-deep TMEM accumulator ring (MMA <-> epilogue), so
 // the epilogue of tile i overlaps the MMAs of tile i+1.
 //
@@ -24,7 +24,9 @@ namespace capdec {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 fp16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;                      // 2 warps per TMEM lane quarter, each owns half of the tile's columns
+constexpr int EPI_SPLIT = EPI_WARPS / 4;
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
 
 enum EpiKind { EPI_STORE = 0, EPI_LSTM = 1, EPI_GLU = 2, EPI_TOPK = 3, EPI_SAMPLE = 4 };
 
@@ -79,7 +81,11 @@ __host__ __device__ constexpr int topk_part_stride(int ktop) { return 2 + 2 * kt
 constexpr int SAMPLE_PART_STRIDE = 5;  // max, sumexp, best perturbed, best index, best raw logit
 
 // ------------------------------------------------------------------------------------------------ math helpers
-__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+// sigmoid / tanh from ex2.approx + fast division: absolute error ~1e-7 (fp32 noise level), ~6 instructions each.
+__device__ __forceinline__ float sigmoidf_acc(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_acc(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
 
 __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
     hi = __float2half_rn(x);
@@ -115,15 +121,16 @@ __device__ __forceinline__ void store_h16x8(__half* dst, int lo_off, const float
 }
 
 // ------------------------------------------------------------------------------------------------ epilogues
-// Each epilogue thread owns ONE output row (TMEM lane) and walks the tile's columns in chunks of 32.
+// Each epilogue thread owns ONE output row (TMEM lane) and walks its share of the tile's columns -- chunks
+// [c0, c1) of 32 columns -- so row-wise statistics (softmax max / sum, top-k) need no cross-thread traffic.
 
 template <int BLOCK_N>
-__device__ __forceinline__ void epi_store(uint32_t taddr, int row, int n_base, const GemmParams& p) {
+__device__ __forceinline__ void epi_store(uint32_t taddr, int row, int n_base, int c0, int c1, const GemmParams& p) {
     const EpiParams& e = p.epi;
     const bool row_ok = row < p.M;
     const bool vec_ok = (p.N & 3) == 0;
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
+    for (int c = c0; c < c1; ++c) {
         const int n0 = n_base + c * 32;
         if (n0 >= p.N) break;  // warp-uniform
         float v[32];
@@ -162,53 +169,44 @@ __device__ __forceinline__ void epi_store(uint32_t taddr, int row, int n_base, c
 }
 
 // Columns are packed gate-interleaved: n = 4*j + g, g in (i, f, g, o) -- torch.nn.LSTMCell gate order.
+// The additive terms (bias or the hoisted per-image vector) and the previous cell state are fetched BEFORE the
+// accumulator chunk is read from TMEM, so their L2 latency overlaps the TMEM load.
 template <int BLOCK_N>
-__device__ __forceinline__ void epi_lstm(uint32_t taddr, int row, int n_base, const GemmParams& p) {
+__device__ __forceinline__ void epi_lstm(uint32_t taddr, int row, int n_base, int c0, int c1, const GemmParams& p) {
     const EpiParams& e = p.epi;
     const bool row_ok = row < p.M;
     int prow = row;
-    const float* radd = nullptr;
+    const float* add = e.bias;  // [N] shared by all rows ...
     if (row_ok) {
         if (e.parent) prow = __ldg(e.parent + row);
-        if (e.rowadd) radd = e.rowadd + static_cast<size_t>(row / e.rows_per_group) * e.rowadd_ld;
+        if (e.rowadd) add = e.rowadd + static_cast<size_t>(row / e.rows_per_group) * e.rowadd_ld;  // ... or per image
     }
+    const float* cin = e.c_in ? e.c_in + static_cast<size_t>(prow) * e.ldc : nullptr;
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
+    for (int c = c0; c < c1; ++c) {
         const int n0 = n_base + c * 32;
         if (n0 >= p.N) break;
+        const int j0 = n0 >> 2;
+        float4 ad[8];
+        float4 cp0 = make_float4(0.f, 0.f, 0.f, 0.f), cp1 = cp0;
+        if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ad[i] = __ldg(reinterpret_cast<const float4*>(add + n0) + i);
+            if (cin) {
+                cp0 = *reinterpret_cast<const float4*>(cin + j0);
+                cp1 = *reinterpret_cast<const float4*>(cin + j0 + 4);
+            }
+        }
         float v[32];
         tmem_ld_32x32(taddr + c * 32, v);
         if (!row_ok) continue;
-        const int j0 = n0 >> 2;
-        if (e.bias) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + i));
-                v[i] += b.x, v[i + 1] += b.y, v[i + 2] += b.z, v[i + 3] += b.w;
-            }
-        }
-        if (radd) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(radd + n0 + i));
-                v[i] += b.x, v[i + 1] += b.y, v[i + 2] += b.z, v[i + 3] += b.w;
-            }
-        }
-        float cp[8];
-        if (e.c_in) {
-            const float4 c0 = *reinterpret_cast<const float4*>(e.c_in + static_cast<size_t>(prow) * e.ldc + j0);
-            const float4 c1 = *reinterpret_cast<const float4*>(e.c_in + static_cast<size_t>(prow) * e.ldc + j0 + 4);
-            cp[0] = c0.x, cp[1] = c0.y, cp[2] = c0.z, cp[3] = c0.w, cp[4] = c1.x, cp[5] = c1.y, cp[6] = c1.z, cp[7] = c1.w;
-        } else {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) cp[u] = 0.f;
-        }
+        const float cp[8] = {cp0.x, cp0.y, cp0.z, cp0.w, cp1.x, cp1.y, cp1.z, cp1.w};
         float cn[8], hn[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const float gi = v[4 * u], gf = v[4 * u + 1], gg = v[4 * u + 2], go = v[4 * u + 3];
-            cn[u] = sigmoidf_acc(gf) * cp[u] + sigmoidf_acc(gi) * tanhf(gg);
-            hn[u] = sigmoidf_acc(go) * tanhf(cn[u]);
+            const float gi = v[4 * u] + ad[u].x, gf = v[4 * u + 1] + ad[u].y, gg = v[4 * u + 2] + ad[u].z, go = v[4 * u + 3] + ad[u].w;
+            cn[u] = sigmoidf_acc(gf) * cp[u] + sigmoidf_acc(gi) * tanhf_acc(gg);
+            hn[u] = sigmoidf_acc(go) * tanhf_acc(cn[u]);
         }
         float* co = e.c_out + static_cast<size_t>(row) * e.ldc + j0;
         *reinterpret_cast<float4*>(co) = make_float4(cn[0], cn[1], cn[2], cn[3]);
@@ -224,11 +222,11 @@ __device__ __forceinline__ void epi_lstm(uint32_t taddr, int row, int n_base, co
 
 // Columns are packed (a_j, gate_j)-interleaved: n = 2*j + s.  nn.GLU: a * sigmoid(gate).
 template <int BLOCK_N>
-__device__ __forceinline__ void epi_glu(uint32_t taddr, int row, int n_base, const GemmParams& p) {
+__device__ __forceinline__ void epi_glu(uint32_t taddr, int row, int n_base, int c0, int c1, const GemmParams& p) {
     const EpiParams& e = p.epi;
     const bool row_ok = row < p.M;
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
+    for (int c = c0; c < c1; ++c) {
         const int n0 = n_base + c * 32;
         if (n0 >= p.N) break;
         float v[32];
@@ -261,10 +259,43 @@ __device__ __forceinline__ void epi_glu(uint32_t taddr, int row, int n_base, con
     }
 }
 
-// Per (row, N-tile): running max, sum of exp(x - max), and the KTOP largest logits with their vocabulary
+// One 32-column chunk of logits: add the bias, mask the padded vocabulary tail, fold into the running
+// (max, sum of exp(x - max)) pair.  exp via ex2.approx on log2e-prescaled arguments (one FFMA + one MUFU per element).
+__device__ __forceinline__ float logits_chunk_stats(float (&v)[32], int n0, int N, const float* __restrict__ bias, float& m,
+                                                    float& s) {
+    float cmax = -INFINITY;
+    if (n0 + 32 <= N) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            float b0 = __ldg(bias + n0 + i), b1 = __ldg(bias + n0 + i + 1), b2 = __ldg(bias + n0 + i + 2), b3 = __ldg(bias + n0 + i + 3);
+            v[i] += b0, v[i + 1] += b1, v[i + 2] += b2, v[i + 3] += b3;
+            cmax = fmaxf(cmax, fmaxf(fmaxf(v[i], v[i + 1]), fmaxf(v[i + 2], v[i + 3])));
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            if (n0 + i < N) {
+                v[i] += __ldg(bias + n0 + i);
+                cmax = fmaxf(cmax, v[i]);
+            } else {
+                v[i] = -INFINITY;
+            }
+        }
+    }
+    const float mn = fmaxf(m, cmax);
+    const float mn2 = mn * LOG2E;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc += exp2f(fmaf(v[i], LOG2E, -mn2));  // exp2(-inf) = 0 for the padded columns
+    s = s * exp2f(fmaf(m, LOG2E, -mn2)) + acc;
+    m = mn;
+    return cmax;
+}
+
+// Per (row, partial slot): running max, sum of exp(x - max), and the KTOP largest logits with their vocabulary
 // indices (ties keep the lower index first).  The full logits row is never written to HBM.
 template <int BLOCK_N, int KTOP>
-__device__ __forceinline__ void epi_topk(uint32_t taddr, int row, int n_base, int n_blk, const GemmParams& p) {
+__device__ __forceinline__ void epi_topk(uint32_t taddr, int row, int n_base, int c0, int c1, int slot, const GemmParams& p) {
     const EpiParams& e = p.epi;
     float m = -INFINITY, s = 0.f;
     float tv[KTOP];
@@ -272,27 +303,12 @@ __device__ __forceinline__ void epi_topk(uint32_t taddr, int row, int n_base, in
 #pragma unroll
     for (int q = 0; q < KTOP; ++q) tv[q] = -INFINITY, ti[q] = 0x7FFFFFFF;
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
+    for (int c = c0; c < c1; ++c) {
         const int n0 = n_base + c * 32;
         if (n0 >= p.N) break;
         float v[32];
         tmem_ld_32x32(taddr + c * 32, v);
-        float cmax = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            if (n0 + i < p.N) {
-                v[i] += __ldg(e.bias + n0 + i);
-                cmax = fmaxf(cmax, v[i]);
-            } else {
-                v[i] = -INFINITY;
-            }
-        }
-        const float mn = fmaxf(m, cmax);
-        float acc = 0.f;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc += expf(v[i] - mn);  // exp(-inf) = 0 for the padded columns
-        s = s * expf(m - mn) + acc;
-        m = mn;
+        const float cmax = logits_chunk_stats(v, n0, p.N, e.bias, m, s);
         if (cmax > tv[KTOP - 1]) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -312,7 +328,7 @@ __device__ __forceinline__ void epi_topk(uint32_t taddr, int row, int n_base, in
     }
     if (row < p.M) {
         constexpr int PS = topk_part_stride(KTOP);
-        float* o = e.part + (static_cast<size_t>(row) * e.n_tiles + n_blk) * PS;
+        float* o = e.part + (static_cast<size_t>(row) * e.n_tiles + slot) * PS;
         o[0] = m;
         o[1] = s;
 #pragma unroll
@@ -326,34 +342,19 @@ __device__ __forceinline__ void epi_topk(uint32_t taddr, int row, int n_base, in
 // Greedy / multinomial draw: argmax over the vocabulary of (logit + Gumbel noise); with use_noise == 0 this is
 // the plain argmax of ``sample``.  Also carries (max, sum-exp) for the log-prob of the drawn word.
 template <int BLOCK_N>
-__device__ __forceinline__ void epi_sample(uint32_t taddr, int row, int n_base, int n_blk, const GemmParams& p) {
+__device__ __forceinline__ void epi_sample(uint32_t taddr, int row, int n_base, int c0, int c1, int slot, const GemmParams& p) {
     const EpiParams& e = p.epi;
     float m = -INFINITY, s = 0.f;
     float best = -INFINITY, best_raw = 0.f;
     int best_i = 0x7FFFFFFF;
     const uint32_t rs = gumbel_row_step_hash(e.seed, static_cast<uint32_t>(row), static_cast<uint32_t>(e.step));
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
+    for (int c = c0; c < c1; ++c) {
         const int n0 = n_base + c * 32;
         if (n0 >= p.N) break;
         float v[32];
         tmem_ld_32x32(taddr + c * 32, v);
-        float cmax = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            if (n0 + i < p.N) {
-                v[i] += __ldg(e.bias + n0 + i);
-                cmax = fmaxf(cmax, v[i]);
-            } else {
-                v[i] = -INFINITY;
-            }
-        }
-        const float mn = fmaxf(m, cmax);
-        float acc = 0.f;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc += expf(v[i] - mn);
-        s = s * expf(m - mn) + acc;
-        m = mn;
+        const float cmax = logits_chunk_stats(v, n0, p.N, e.bias, m, s);
         if (e.use_noise) {
 #pragma unroll 4
             for (int i = 0; i < 32; ++i) {
@@ -369,7 +370,7 @@ __device__ __forceinline__ void epi_sample(uint32_t taddr, int row, int n_base, 
         }
     }
     if (row < p.M) {
-        float* o = e.part + (static_cast<size_t>(row) * e.n_tiles + n_blk) * SAMPLE_PART_STRIDE;
+        float* o = e.part + (static_cast<size_t>(row) * e.n_tiles + slot) * SAMPLE_PART_STRIDE;
         o[0] = m;
         o[1] = s;
         o[2] = best;
@@ -408,7 +409,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar + 8 * s, 1);
-            mbar_init(tempty_bar + 8 * s, 128);
+            mbar_init(tempty_bar + 8 * s, 32 * EPI_WARPS);
         }
         fence_barrier_init();
     }
@@ -475,8 +476,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             }
         }
     } else {
-        // ===================== epilogue warps (2..5) =====================
-        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        // ===================== epilogue warps (2 .. 2+EPI_WARPS) =====================
+        const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+        const int split = (warp - 2) >> 2;       // which share of the tile's columns
+        constexpr int CHUNKS = BLOCK_N / 32;
+        const int c0 = split * (CHUNKS / EPI_SPLIT), c1 = c0 + CHUNKS / EPI_SPLIT;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -487,11 +491,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quarter * 32) << 16);
             const int row = m_blk * BLOCK_M + quarter * 32 + lane;
             const int n_base = n_blk * BLOCK_N;
-            if constexpr (EPI == EPI_STORE) epi_store<BLOCK_N>(taddr, row, n_base, p);
-            else if constexpr (EPI == EPI_LSTM) epi_lstm<BLOCK_N>(taddr, row, n_base, p);
-            else if constexpr (EPI == EPI_GLU) epi_glu<BLOCK_N>(taddr, row, n_base, p);
-            else if constexpr (EPI == EPI_TOPK) epi_topk<BLOCK_N, KTOP>(taddr, row, n_base, n_blk, p);
-            else epi_sample<BLOCK_N>(taddr, row, n_base, n_blk, p);
+            if constexpr (EPI == EPI_STORE) epi_store<BLOCK_N>(taddr, row, n_base, c0, c1, p);
+            else if constexpr (EPI == EPI_LSTM) epi_lstm<BLOCK_N>(taddr, row, n_base, c0, c1, p);
+            else if constexpr (EPI == EPI_GLU) epi_glu<BLOCK_N>(taddr, row, n_base, c0, c1, p);
+            else if constexpr (EPI == EPI_TOPK) epi_topk<BLOCK_N, KTOP>(taddr, row, n_base, c0, c1, n_blk * EPI_SPLIT + split, p);
+            else epi_sample<BLOCK_N>(taddr, row, n_base, c0, c1, n_blk * EPI_SPLIT + split, p);
             __syncwarp();
             tc_fence_before();
             mbar_arrive(tempty_bar + 8 * acc);

@@ -141,17 +141,34 @@ __global__ void fill_f16_kernel(__half* p, size_t n, float v) {
 }
 
 // ================================================================================================ BUTD attention
+__device__ __forceinline__ void load8(const float* p, float (&x)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    x[0] = a.x, x[1] = a.y, x[2] = a.z, x[3] = a.w, x[4] = b.x, x[5] = b.y, x[6] = b.z, x[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __half* p, float (&x)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        x[2 * i] = f.x, x[2 * i + 1] = f.y;
+    }
+}
+
 // One CTA per image, all K rows (beams / samples) of the image together so that the image's projected
 // features enc_ctx [R,A] and raw features [R,D] are read from HBM once per image-step, not once per row.
 //   e[k,r]   = w_aff . relu(enc_ctx[r,:] + dec_ctx[k,:]) + b_aff      (BUTD_Model.py:58-59, ReLU not tanh)
 //   alpha    = softmax_r(e)                                            (:60)
 //   ctx[k,:] = sum_r alpha[k,r] * feats[r,:]                           (:61)
-// ctx is written straight into the language LSTM's fp16 operand buffer.
-template <int KR>
-__global__ void __launch_bounds__(256) butd_attention_kernel(const float* __restrict__ enc_ctx, const float* __restrict__ feats,
-                                                             const float* __restrict__ dec_ctx, const float* __restrict__ w_aff,
-                                                             float b_aff, int R, int A, int D, int K, __half* __restrict__ ctx16,
-                                                             int ld16, int lo16, float* __restrict__ alphas_out) {
+// ctx is written straight into the language LSTM's fp16 operand buffer.  T = float (fp32-grade mode) or __half
+// (fp16 mode: the projected and raw features are read in the fp16 form the projection GEMM already uses --
+// half the HBM bytes; A and D must be multiples of 8).
+template <int KR, typename T>
+__global__ void __launch_bounds__(256) butd_attention_kernel(const T* __restrict__ enc_ctx, const T* __restrict__ feats,
+                                                             int feats_ld, const float* __restrict__ dec_ctx,
+                                                             const float* __restrict__ w_aff, float b_aff, int R, int A, int D,
+                                                             int K, __half* __restrict__ ctx16, int ld16, int lo16,
+                                                             float* __restrict__ alphas_out) {
     extern __shared__ float sm[];
     float* s_dec = sm;                 // [KR][A]
     float* s_w = s_dec + KR * A;       // [A]
@@ -163,20 +180,23 @@ __global__ void __launch_bounds__(256) butd_attention_kernel(const float* __rest
     for (int i = tid; i < A; i += blockDim.x) s_w[i] = w_aff[i];
     __syncthreads();
 
-    const float* enc = enc_ctx + static_cast<size_t>(img) * R * A;
+    const T* enc = enc_ctx + static_cast<size_t>(img) * R * A;
     for (int r = warp; r < R; r += nwarp) {
         float acc[KR];
 #pragma unroll
         for (int k = 0; k < KR; ++k) acc[k] = 0.f;
-        for (int a = lane * 4; a < A; a += 128) {
-            const float4 x = __ldg(reinterpret_cast<const float4*>(enc + static_cast<size_t>(r) * A + a));
-            const float4 w = *reinterpret_cast<const float4*>(s_w + a);
+        for (int a = lane * 8; a < A; a += 256) {
+            float x[8];
+            load8(enc + static_cast<size_t>(r) * A + a, x);
+            const float4 w0 = *reinterpret_cast<const float4*>(s_w + a), w1 = *reinterpret_cast<const float4*>(s_w + a + 4);
 #pragma unroll
             for (int k = 0; k < KR; ++k) {
                 if (k < K) {
-                    const float4 d = *reinterpret_cast<const float4*>(s_dec + k * A + a);
-                    acc[k] += w.x * fmaxf(x.x + d.x, 0.f) + w.y * fmaxf(x.y + d.y, 0.f) + w.z * fmaxf(x.z + d.z, 0.f) +
-                              w.w * fmaxf(x.w + d.w, 0.f);
+                    const float4 d0 = *reinterpret_cast<const float4*>(s_dec + k * A + a);
+                    const float4 d1 = *reinterpret_cast<const float4*>(s_dec + k * A + a + 4);
+                    acc[k] += w0.x * fmaxf(x[0] + d0.x, 0.f) + w0.y * fmaxf(x[1] + d0.y, 0.f) + w0.z * fmaxf(x[2] + d0.z, 0.f) +
+                              w0.w * fmaxf(x[3] + d0.w, 0.f) + w1.x * fmaxf(x[4] + d1.x, 0.f) + w1.y * fmaxf(x[5] + d1.y, 0.f) +
+                              w1.z * fmaxf(x[6] + d1.z, 0.f) + w1.w * fmaxf(x[7] + d1.w, 0.f);
                 }
             }
         }
@@ -207,35 +227,29 @@ __global__ void __launch_bounds__(256) butd_attention_kernel(const float* __rest
     }
     __syncthreads();
 
-    const float* f = feats + static_cast<size_t>(img) * R * D;
-    for (int d = tid * 4; d < D; d += blockDim.x * 4) {
-        float4 acc[KR];
+    const T* f = feats + static_cast<size_t>(img) * R * feats_ld;
+    for (int d = tid * 8; d < D; d += blockDim.x * 8) {
+        float acc[KR][8];
 #pragma unroll
-        for (int k = 0; k < KR; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < KR; ++k)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
 #pragma unroll 4
         for (int r = 0; r < R; ++r) {
-            const float4 x = __ldg(reinterpret_cast<const float4*>(f + static_cast<size_t>(r) * D + d));
+            float x[8];
+            load8(f + static_cast<size_t>(r) * feats_ld + d, x);
 #pragma unroll
             for (int k = 0; k < KR; ++k) {
                 if (k < K) {
                     const float al = s_e[k * R + r];
-                    acc[k].x += al * x.x, acc[k].y += al * x.y, acc[k].z += al * x.z, acc[k].w += al * x.w;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[k][i] = fmaf(al, x[i], acc[k][i]);
                 }
             }
         }
 #pragma unroll
         for (int k = 0; k < KR; ++k) {
-            if (k < K) {
-                __align__(8) __half hi[4];
-                __align__(8) __half lo[4];
-                split_f16(acc[k].x, hi[0], lo[0]);
-                split_f16(acc[k].y, hi[1], lo[1]);
-                split_f16(acc[k].z, hi[2], lo[2]);
-                split_f16(acc[k].w, hi[3], lo[3]);
-                __half* o = ctx16 + (static_cast<size_t>(img) * K + k) * ld16 + d;
-                *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(hi);
-                if (lo16 > 0) *reinterpret_cast<uint2*>(o + lo16) = *reinterpret_cast<const uint2*>(lo);
-            }
+            if (k < K) store_h16x8(ctx16 + (static_cast<size_t>(img) * K + k) * ld16 + d, lo16, acc[k]);
         }
     }
 }
@@ -501,7 +515,7 @@ __global__ void __launch_bounds__(128) beam_step_kernel(const float* __restrict_
     __shared__ int c_idx[MAX_ROWS][MAX_ROWS];
     __shared__ int s_parent[MAX_ROWS], s_tok[MAX_ROWS];
     const int img = blockIdx.x;
-    const int K = s.K, V = s.V, L = s.T + 1;
+    const int K = s.K, L = s.T + 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nl = s.n_live[img];
     const int rows_considered = (t == 1) ? min(nl, 1) : nl;
