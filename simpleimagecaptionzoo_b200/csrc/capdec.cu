@@ -423,7 +423,7 @@ template <int KR, typename T>
 int launch_butd_att_t(capdec_handle* h, const StepCtx& c, const T* enc, const T* feats, int feats_ld, cudaStream_t st) {
     static bool attr_set = false;
     auto kern = butd_attention_kernel<KR, T>;
-    const size_t smem = (static_cast<size_t>(KR) * h->A + h->A + static_cast<size_t>(KR) * h->R) * sizeof(float);
+    const size_t smem = (static_cast<size_t>(KR) * h->R + 2 * 8 * AttCfg<KR>::NP) * sizeof(float);
     if (!attr_set) {
         CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         attr_set = true;

@@ -141,74 +141,161 @@ __global__ void fill_f16_kernel(__half* p, size_t n, float v) {
 }
 
 // ================================================================================================ BUTD attention
-__device__ __forceinline__ void load8(const float* p, float (&x)[8]) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-    x[0] = a.x, x[1] = a.y, x[2] = a.z, x[3] = a.w, x[4] = b.x, x[5] = b.y, x[6] = b.z, x[7] = b.w;
-}
-__device__ __forceinline__ void load8(const __half* p, float (&x)[8]) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
-    const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float2 f = __half22float2(h[i]);
-        x[2 * i] = f.x, x[2 * i + 1] = f.y;
+// 8 consecutive elements as raw 16-byte vectors (issued as independent loads first, converted later, so that
+// several loads per thread are in flight: the kernel is HBM-bound only if memory-level parallelism is high).
+template <typename T> struct Raw8;
+template <> struct Raw8<float> {
+    float4 a, b;
+    __device__ __forceinline__ void load(const float* p) {
+        a = __ldg(reinterpret_cast<const float4*>(p));
+        b = __ldg(reinterpret_cast<const float4*>(p) + 1);
     }
+    __device__ __forceinline__ void zero() { a = make_float4(0.f, 0.f, 0.f, 0.f), b = a; }
+    __device__ __forceinline__ void get(float (&x)[8]) const {
+        x[0] = a.x, x[1] = a.y, x[2] = a.z, x[3] = a.w, x[4] = b.x, x[5] = b.y, x[6] = b.z, x[7] = b.w;
+    }
+};
+template <> struct Raw8<__half> {
+    uint4 u;
+    __device__ __forceinline__ void load(const __half* p) { u = __ldg(reinterpret_cast<const uint4*>(p)); }
+    __device__ __forceinline__ void zero() { u = make_uint4(0u, 0u, 0u, 0u); }
+    __device__ __forceinline__ void get(float (&x)[8]) const {
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(h[i]);
+            x[2 * i] = f.x, x[2 * i + 1] = f.y;
+        }
+    }
+};
+
+// Sum NP (power of two <= 32) per-lane values across the 32 lanes of a warp with NP-1 (+ log2(32/NP)) shuffles
+// instead of 5*NP: at every step each lane keeps one half of its values and hands the other half to its partner.
+// Returns the fully reduced value of output index `out_idx`; lanes with (lane & (32/NP - 1)) == 0 are the writers.
+template <int NP>
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[NP], int lane, int& out_idx) {
+    int idx = 0;
+#pragma unroll
+    for (int st = 0; st < 5; ++st) {
+        const int o = 16 >> st;
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int cnt = NP >> st;  // values still held per lane before this step (compile-time after unrolling)
+        if (cnt > 1) {
+            const int half = cnt >> 1;
+            const bool upper = (lane & o) != 0;
+#pragma unroll
+            for (int i = 0; i < NP / 2; ++i) {
+                if (i < half) {
+                    const float send = upper ? v[i] : v[i + half];
+                    const float keep = upper ? v[i + half] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                }
+            }
+            idx += upper ? half : 0;
+        } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+        }
+    }
+    out_idx = idx;
+    return v[0];
 }
 
-// One CTA per image, all K rows (beams / samples) of the image together so that the image's projected
-// features enc_ctx [R,A] and raw features [R,D] are read from HBM once per image-step, not once per row.
+template <int KR> struct AttCfg {
+    static constexpr int GR = KR <= 1 ? 8 : (KR <= 3 ? 6 : (KR <= 5 ? 4 : 2));  // regions per thread per group
+    static constexpr int NV = KR * GR;                                          // partial sums per thread per group
+    static constexpr int NP = NV <= 8 ? 8 : (NV <= 16 ? 16 : 32);
+    static constexpr int LB = KR <= 3 ? 9 : (KR <= 5 ? 6 : 4);                  // feature loads in flight (phase 3)
+};
+
+// One CTA (256 threads) per image, all K rows (beams / samples) of the image together so that the image's
+// projected features enc_ctx [R,A] and raw features [R,D] are read from HBM once per image-step, not per row.
 //   e[k,r]   = w_aff . relu(enc_ctx[r,:] + dec_ctx[k,:]) + b_aff      (BUTD_Model.py:58-59, ReLU not tanh)
 //   alpha    = softmax_r(e)                                            (:60)
 //   ctx[k,:] = sum_r alpha[k,r] * feats[r,:]                           (:61)
 // ctx is written straight into the language LSTM's fp16 operand buffer.  T = float (fp32-grade mode) or __half
-// (fp16 mode: the projected and raw features are read in the fp16 form the projection GEMM already uses --
-// half the HBM bytes; A and D must be multiples of 8).
+// (fp16 mode: projected and raw features are read in the fp16 form the projection GEMM already uses -- half the
+// HBM bytes).  Phase 1: a thread owns 8 columns of A (w and dec stay in registers) and GR regions of one parity
+// per group; partial dot products are reduced with a transposing butterfly + one smem hop across the 4 warps of a
+// parity.  A, D multiples of 8.
 template <int KR, typename T>
 __global__ void __launch_bounds__(256) butd_attention_kernel(const T* __restrict__ enc_ctx, const T* __restrict__ feats,
                                                              int feats_ld, const float* __restrict__ dec_ctx,
                                                              const float* __restrict__ w_aff, float b_aff, int R, int A, int D,
                                                              int K, __half* __restrict__ ctx16, int ld16, int lo16,
                                                              float* __restrict__ alphas_out) {
+    using C = AttCfg<KR>;
+    constexpr int GR = C::GR, NV = C::NV, NP = C::NP, LB = C::LB;
     extern __shared__ float sm[];
-    float* s_dec = sm;                 // [KR][A]
-    float* s_w = s_dec + KR * A;       // [A]
-    float* s_e = s_w + A;              // [KR][R]
+    float* s_e = sm;                    // [KR][R] scores, then alphas
+    float* s_red = s_e + KR * R;        // [2][8 warps][NP]
     const int img = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+    const int parity = tid >> 7;        // which of the two interleaved region streams
+    const int tcol = tid & 127;
 
-    for (int i = tid; i < K * A; i += blockDim.x) s_dec[i] = dec_ctx[static_cast<size_t>(img) * K * A + i];
-    for (int i = tid; i < A; i += blockDim.x) s_w[i] = w_aff[i];
-    __syncthreads();
-
+    // ---------------- phase 1: attention scores
     const T* enc = enc_ctx + static_cast<size_t>(img) * R * A;
-    for (int r = warp; r < R; r += nwarp) {
-        float acc[KR];
+    const float* dec = dec_ctx + static_cast<size_t>(img) * K * A;
+    const int n_groups = (R + 2 * GR - 1) / (2 * GR);
+    for (int g = 0; g < n_groups; ++g) {
+        float p[NP];
 #pragma unroll
-        for (int k = 0; k < KR; ++k) acc[k] = 0.f;
-        for (int a = lane * 8; a < A; a += 256) {
-            float x[8];
-            load8(enc + static_cast<size_t>(r) * A + a, x);
-            const float4 w0 = *reinterpret_cast<const float4*>(s_w + a), w1 = *reinterpret_cast<const float4*>(s_w + a + 4);
+        for (int i = 0; i < NP; ++i) p[i] = 0.f;
+        for (int a0 = tcol * 8; a0 < A; a0 += 1024) {
+            Raw8<T> raw[GR];
+#pragma unroll
+            for (int i = 0; i < GR; ++i) {
+                const int r = g * 2 * GR + parity + 2 * i;
+                if (r < R) raw[i].load(enc + static_cast<size_t>(r) * A + a0);
+                else raw[i].zero();
+            }
+            float w[8];
+            Raw8<float> t;
+            t.load(w_aff + a0);
+            t.get(w);
+            float d[KR][8];
 #pragma unroll
             for (int k = 0; k < KR; ++k) {
                 if (k < K) {
-                    const float4 d0 = *reinterpret_cast<const float4*>(s_dec + k * A + a);
-                    const float4 d1 = *reinterpret_cast<const float4*>(s_dec + k * A + a + 4);
-                    acc[k] += w0.x * fmaxf(x[0] + d0.x, 0.f) + w0.y * fmaxf(x[1] + d0.y, 0.f) + w0.z * fmaxf(x[2] + d0.z, 0.f) +
-                              w0.w * fmaxf(x[3] + d0.w, 0.f) + w1.x * fmaxf(x[4] + d1.x, 0.f) + w1.y * fmaxf(x[5] + d1.y, 0.f) +
-                              w1.z * fmaxf(x[6] + d1.z, 0.f) + w1.w * fmaxf(x[7] + d1.w, 0.f);
+                    t.load(dec + k * A + a0);
+                    t.get(d[k]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) d[k][q] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < GR; ++i) {
+                float x[8];
+                raw[i].get(x);
+#pragma unroll
+                for (int k = 0; k < KR; ++k) {
+                    float acc = p[k * GR + i];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) acc = fmaf(w[q], fmaxf(x[q] + d[k][q], 0.f), acc);
+                    p[k * GR + i] = acc;
                 }
             }
         }
-#pragma unroll
-        for (int k = 0; k < KR; ++k) {
-            const float t = warp_sum(acc[k]);
-            if (lane == 0 && k < K) s_e[k * R + r] = t + b_aff;
+        int oidx;
+        const float tot = warp_transpose_reduce<NP>(p, lane, oidx);
+        float* red = s_red + (g & 1) * 8 * NP;
+        if ((lane & (32 / NP - 1)) == 0) red[warp * NP + oidx] = tot;
+        __syncthreads();
+        if (tid < 2 * NV) {
+            const int par = tid / NV, v = tid - par * NV;
+            const float sum = red[(par * 4 + 0) * NP + v] + red[(par * 4 + 1) * NP + v] + red[(par * 4 + 2) * NP + v] +
+                              red[(par * 4 + 3) * NP + v];
+            const int k = v / GR, i = v - k * GR;
+            const int r = g * 2 * GR + par + 2 * i;
+            if (r < R && k < K) s_e[k * R + r] = sum + b_aff;
         }
     }
     __syncthreads();
 
-    for (int k = warp; k < K; k += nwarp) {  // softmax over regions, one warp per row
+    // ---------------- phase 2: softmax over regions, one warp per row
+    for (int k = warp; k < K; k += nwarp) {
         float m = -INFINITY;
         for (int r = lane; r < R; r += 32) m = fmaxf(m, s_e[k * R + r]);
         m = warp_max(m);
@@ -227,29 +314,40 @@ __global__ void __launch_bounds__(256) butd_attention_kernel(const T* __restrict
     }
     __syncthreads();
 
+    // ---------------- phase 3: attention-weighted feature sum
     const T* f = feats + static_cast<size_t>(img) * R * feats_ld;
-    for (int d = tid * 8; d < D; d += blockDim.x * 8) {
+    for (int d0 = tid * 8; d0 < D; d0 += blockDim.x * 8) {
         float acc[KR][8];
 #pragma unroll
         for (int k = 0; k < KR; ++k)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
-#pragma unroll 4
-        for (int r = 0; r < R; ++r) {
-            float x[8];
-            load8(f + static_cast<size_t>(r) * feats_ld + d, x);
+            for (int q = 0; q < 8; ++q) acc[k][q] = 0.f;
+        for (int r0 = 0; r0 < R; r0 += LB) {
+            Raw8<T> raw[LB];
 #pragma unroll
-            for (int k = 0; k < KR; ++k) {
-                if (k < K) {
-                    const float al = s_e[k * R + r];
+            for (int i = 0; i < LB; ++i) {
+                if (r0 + i < R) raw[i].load(f + static_cast<size_t>(r0 + i) * feats_ld + d0);
+                else raw[i].zero();
+            }
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) acc[k][i] = fmaf(al, x[i], acc[k][i]);
+            for (int i = 0; i < LB; ++i) {
+                if (r0 + i < R) {
+                    float x[8];
+                    raw[i].get(x);
+#pragma unroll
+                    for (int k = 0; k < KR; ++k) {
+                        if (k < K) {
+                            const float al = s_e[k * R + r0 + i];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) acc[k][q] = fmaf(al, x[q], acc[k][q]);
+                        }
+                    }
                 }
             }
         }
 #pragma unroll
         for (int k = 0; k < KR; ++k) {
-            if (k < K) store_h16x8(ctx16 + (static_cast<size_t>(img) * K + k) * ld16 + d, lo16, acc[k]);
+            if (k < K) store_h16x8(ctx16 + (static_cast<size_t>(img) * K + k) * ld16 + d0, lo16, acc[k]);
         }
     }
 }

@@ -85,22 +85,38 @@ def test_beam_search_fp32_grade(name):
     dec.close()
 
 
-@pytest.mark.parametrize("name", TINY + FULL)
-def test_beam_search_fp16_mode(name):
-    """Single-pass fp16 operands (throughput mode): >= 90 % exact-or-tie-justified, stated log-prob bound."""
+def _fp16_verdicts(name):
     meta, gold = load_case(name)
     dec, sd, feats, mask = _make(meta, "f16")
     tok, score, _ = dec.beam_search(meta["K"], meta["T"])
     torch.cuda.synchronize()
     tok, score = tok.cpu().numpy(), score.cpu().numpy()
+    dec.close()
     res = orc.beam_search_batched(_oracle(meta, sd, feats, mask), meta["K"], meta["T"])
     verdict = orc.agreement(tok, gold["tokens"], res.min_gap, tol=1e-4)
-    ok = np.array([v != "diff" for v in verdict])
-    assert ok.mean() >= 0.90, ok.mean()
     exact = np.array([v == "exact" for v in verdict])
-    if "full" in name:  # tiny-chaotic weights (U(-1,1)) amplify operand rounding; the bound is for real dims
-        assert np.abs(score[exact] - gold["scores"][exact]).max() <= F16_SCORE_BOUND
-    dec.close()
+    err = np.abs(score[exact] - gold["scores"][exact]).max() if exact.any() else 0.0
+    return verdict, float(err)
+
+
+@pytest.mark.parametrize("name", TINY)
+def test_beam_search_fp16_mode_tiny(name):
+    """Single-pass fp16 operands (throughput mode) on the bookkeeping cases: >= 90 % exact-or-tie-justified."""
+    verdict, _ = _fp16_verdicts(name)
+    assert np.mean([v != "diff" for v in verdict]) >= 0.90
+
+
+def test_beam_search_fp16_mode_full_dims():
+    """Single-pass fp16 operands at BASELINE dims: >= 90 % exact-or-tie-justified over all full-size golden images
+    (north_star's agreement target; tools/agreement.py measures it on thousands of images) and the stated bound on
+    the sequence log-prob."""
+    verdicts, worst = [], 0.0
+    for name in FULL:
+        v, err = _fp16_verdicts(name)
+        verdicts += v
+        worst = max(worst, err)
+    assert np.mean([v != "diff" for v in verdicts]) >= 0.90, verdicts
+    assert worst <= F16_SCORE_BOUND, worst
 
 
 @pytest.mark.parametrize("name", TINY + FULL)
