@@ -79,7 +79,7 @@ class B200Captioner:
         return self
 
     # ------------------------------------------------------------------ inputs
-    def _features(self, visual_inputs):
+    def _features(self, visual_inputs, to_device: bool = True):
         """Pull the decoder's input out of ``visual_inputs`` the way the reference wrappers do
         (BUTD_Model.py:486,513; AoA_Model.py:748-751; NIC_Model.py:277-279)."""
         torch = _torch()
@@ -97,9 +97,10 @@ class B200Captioner:
             feats = torch.from_numpy(feats)
         if isinstance(mask, np.ndarray):
             mask = torch.from_numpy(mask)
-        feats = feats.to(self.device, non_blocking=True)
-        if mask is not None:
-            mask = mask.to(self.device, non_blocking=True)
+        if to_device:
+            feats = feats.to(self.device, non_blocking=True)
+            if mask is not None:
+                mask = mask.to(self.device, non_blocking=True)
         return feats, mask
 
     # ------------------------------------------------------------------ the three decode methods
@@ -108,6 +109,71 @@ class B200Captioner:
         self.decoder.prepare(feats, mask)
         tokens, self.last_scores, self.last_lengths = self.decoder.beam_search(beam_size, max_seq or self.max_seq)
         return tokens.long()
+
+    def beam_search_stream(self, batches, beam_size: int = 5, max_seq: Optional[int] = None):
+        """Pipelined form of ``beam_search_sampler`` for a sequence of batches (what an evaluation loop feeds):
+        yields one HOST int32 array [B, 1+max_seq] per input batch, in order.  The host->device copy of batch i+1
+        runs on a copy stream while batch i decodes, and the captions of batch i are read back (pinned buffer,
+        asynchronous) while batch i+1 is already enqueued -- the GPU never waits for the host.
+        ``batches`` yields ``visual_inputs`` dicts whose feature tensors may live on the host (ideally pinned)."""
+        import collections
+        torch = _torch()
+        T = max_seq or self.max_seq
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._slots = [dict(buf=None, mask=None, free=None, ready=None) for _ in range(2)]
+        copy = self._copy_stream
+
+        def stage(i, visual_inputs):
+            slot = self._slots[i % 2]
+            feats, mask = self._features(visual_inputs, to_device=False)
+            with torch.cuda.stream(copy):
+                if slot["free"] is not None:
+                    copy.wait_event(slot["free"])  # the decode that last read this buffer has finished
+                if feats.is_cuda:
+                    slot["buf"] = feats
+                else:
+                    if slot["buf"] is None or slot["buf"].shape != feats.shape or slot["buf"].dtype != feats.dtype:
+                        slot["buf"] = torch.empty(feats.shape, dtype=feats.dtype, device=self.device)
+                    slot["buf"].copy_(feats, non_blocking=True)
+                slot["mask"] = None if mask is None else mask.to(self.device, non_blocking=True)
+                slot["ready"] = torch.cuda.Event()
+                slot["ready"].record(copy)
+            return slot
+
+        it = iter(batches)
+        pending = collections.deque()
+        try:
+            nxt = stage(0, next(it))
+        except StopIteration:
+            return
+        i = 0
+        while nxt is not None:
+            cur = nxt
+            try:
+                nxt = stage(i + 1, next(it))
+            except StopIteration:
+                nxt = None
+            main.wait_event(cur["ready"])
+            self.decoder.prepare(cur["buf"], cur["mask"])
+            tokens, _, _ = self.decoder.beam_search(beam_size, T)
+            cur["free"] = torch.cuda.Event()
+            cur["free"].record(main)
+            host = torch.empty(tokens.shape, dtype=tokens.dtype, pin_memory=True)
+            host.copy_(tokens, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(main)
+            pending.append((host, done))
+            if len(pending) > 1:
+                h, e = pending.popleft()
+                e.synchronize()
+                yield h.numpy()
+            i += 1
+        while pending:
+            h, e = pending.popleft()
+            e.synchronize()
+            yield h.numpy()
 
     def sampler(self, visual_inputs, max_len: int = 20):
         feats, mask = self._features(visual_inputs)
@@ -177,14 +243,29 @@ class CaptionEngine:
         torch = _torch()
         self.load_state_dict(torch.load(path, map_location="cpu"))
 
-    def modify_visual_inputs(self, img_tensors, supp_info_datas=()):
+    def modify_visual_inputs(self, img_tensors, supp_info_datas=(), device=None):
         torch = _torch()
-        return {"img_tensors": img_tensors.to(self.device) if torch.is_tensor(img_tensors) else img_tensors}
+        dev = device or self.device
+        return {"img_tensors": img_tensors.to(dev) if torch.is_tensor(img_tensors) else img_tensors}
 
     def eval_captions_json_generation(self, dataloader, eval_beam_size=-1, tqdm_visible=False):
         self.model.eval()
         ix2word = self.caption_vocab.ix2word
         result = []
+        if eval_beam_size != -1 and hasattr(self.model, "beam_search_stream"):
+            # pipelined: copy of batch i+1 and caption read-back of batch i overlap the decode
+            ids_q = []
+
+            def inputs():
+                for image_ids, img_tensors, supp_info_datas in dataloader:
+                    ids_q.append(image_ids)
+                    yield self.modify_visual_inputs(img_tensors=img_tensors, supp_info_datas=supp_info_datas, device="cpu")
+
+            for captions in self.model.beam_search_stream(inputs(), beam_size=eval_beam_size):
+                image_ids = ids_q.pop(0)
+                for i in range(captions.shape[0]):
+                    result.append({"image_id": int(image_ids[i]), "caption": ids_to_caption(captions[i], ix2word)})
+            return result
         for image_ids, img_tensors, supp_info_datas in dataloader:
             visual_inputs = self.modify_visual_inputs(img_tensors=img_tensors, supp_info_datas=supp_info_datas)
             if eval_beam_size != -1:
@@ -206,10 +287,12 @@ class BUTDSpatial_Eng(CaptionEngine):
 
 
 class _BottomUpMixin:
-    def modify_visual_inputs(self, img_tensors, supp_info_datas=None):
+    def modify_visual_inputs(self, img_tensors, supp_info_datas=None, device=None):
         """ModelEngines/BUTD_Engine.py:23-47 / AoA_Engine.py:23-47: pad per-image (n_i, 2048) bottom-up features to a
-        batch tensor plus a {0,1} mask (None when every image has the same number of boxes)."""
+        batch tensor plus a {0,1} mask (None when every image has the same number of boxes).  ``device="cpu"`` keeps
+        the batch in (pinned) host memory for the pipelined eval loop, which copies it on its own stream."""
         torch = _torch()
+        dev = device or self.device
         bu_feats = [np.asarray(s["bu_feat"], dtype=np.float32) for s in supp_info_datas]
         bu_bboxes = [s.get("bu_bbox") for s in supp_info_datas]
         max_len = max(f.shape[0] for f in bu_feats)
@@ -218,8 +301,11 @@ class _BottomUpMixin:
         for i, f in enumerate(bu_feats):
             feats[i, :f.shape[0]] = f
             masks[i, :f.shape[0]] = 1
-        bu_masks = None if masks.sum() == masks.size else torch.from_numpy(masks).to(self.device)
-        return {"bu_feats": torch.from_numpy(feats).to(self.device), "bu_bboxes": bu_bboxes, "bu_masks": bu_masks}
+        bu_masks = None if masks.sum() == masks.size else torch.from_numpy(masks).to(dev)
+        t = torch.from_numpy(feats)
+        if str(dev) == "cpu" and torch.cuda.is_available():
+            t = t.pin_memory()
+        return {"bu_feats": t.to(dev), "bu_bboxes": bu_bboxes, "bu_masks": bu_masks}
 
 
 class BUTDDetection_Eng(_BottomUpMixin, CaptionEngine):
