@@ -6,6 +6,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -62,6 +63,7 @@ struct capdec_handle {
     const float* feats = nullptr;
     const float* mask = nullptr;
     int64_t launches = 0;
+    bool no_stream_attention = false;  // CAPDEC_NO_STREAM_ATTENTION=1: use the non-persistent attention kernel
     bool prof = false;  // bracket every launch with CUDA events (capdec_profile)
     struct ProfRec {
         int cat;
@@ -438,11 +440,40 @@ int launch_butd_att_t(capdec_handle* h, const StepCtx& c, const T* enc, const T*
     return CAPDEC_OK;
 }
 
+template <int KR, typename T>
+int launch_butd_att_stream_t(capdec_handle* h, const StepCtx& c, const T* enc, const T* feats, cudaStream_t st) {
+    using C = AttStreamCfg<KR, T>;
+    static bool attr_set = false;
+    auto kern = butd_attention_stream_kernel<KR, T>;
+    const size_t smem = static_cast<size_t>(C::STAGES) * C::STAGE_BYTES + 2 * C::STAGES * 8 +
+                        (static_cast<size_t>(KR) * h->R + 2 * 8 * C::NP) * sizeof(float) + 128;
+    if (!attr_set) {
+        CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    if (smem > 200 * 1024) return fail(h, CAPDEC_ERR_INVALID, "attention ring does not fit shared memory");
+    const int per_sm = sizeof(T) == 2 ? 2 : 1;
+    const int grid = h->B < h->num_sms * per_sm ? h->B : h->num_sms * per_sm;
+    prof_begin(h, CAPDEC_CAT_ATTENTION, 0.0, st);
+    kern<<<grid, C::THREADS, smem, st>>>(enc, feats, h->dec_ctx, h->w_aff, h->b_aff, h->B, h->R, h->A, h->D, c.K, h->XB.p, h->XB.ld,
+                                         h->XB.lo);
+    prof_end(h, st);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    return CAPDEC_OK;
+}
+
 // fp16 mode reads the fp16 copies (projected features written by the projection GEMM, raw features converted for
 // it); the fp32-grade mode reads the caller's fp32 features and the fp32 projection.
 template <int KR>
 int launch_butd_att(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
-    if (h->split) return launch_butd_att_t<KR, float>(h, c, h->enc_ctx, h->feats, h->D, st);
+    // streaming (persistent, bulk-copy fed) kernel when one region row of A / D columns fits the ring layout
+    const bool stream_ok = h->A <= 1024 && h->D <= 2048 && !h->no_stream_attention;
+    if (h->split) {
+        if (stream_ok) return launch_butd_att_stream_t<KR, float>(h, c, h->enc_ctx, h->feats, st);
+        return launch_butd_att_t<KR, float>(h, c, h->enc_ctx, h->feats, h->D, st);
+    }
+    if (stream_ok && h->feats16.ld == h->D) return launch_butd_att_stream_t<KR, __half>(h, c, h->enc16.p, h->feats16.p, st);
     return launch_butd_att_t<KR, __half>(h, c, h->enc16.p, h->feats16.p, h->feats16.ld, st);
 }
 
@@ -724,6 +755,10 @@ static int create_impl(capdec_handle* h) {
     CK(h, cudaGetDeviceProperties(&prop, c.device));
     if (prop.major != 10) return fail(h, CAPDEC_ERR_CUDA, "libcapdec needs an sm_100a (B200) device; there is no fallback path");
     h->num_sms = prop.multiProcessorCount;
+    {
+        const char* e = getenv("CAPDEC_NO_STREAM_ATTENTION");
+        h->no_stream_attention = e && e[0] == '1';
+    }
     h->Mmax = h->Bmax * h->Kmax;
     h->n_tiles_v = ((V + BN - 1) / BN) * EPI_SPLIT;  // partial slots per row: (N tile, column share)
     const int M = h->Mmax;

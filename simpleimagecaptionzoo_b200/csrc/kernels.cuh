@@ -150,6 +150,10 @@ template <> struct Raw8<float> {
         a = __ldg(reinterpret_cast<const float4*>(p));
         b = __ldg(reinterpret_cast<const float4*>(p) + 1);
     }
+    __device__ __forceinline__ void lds(const float* p) {
+        a = *reinterpret_cast<const float4*>(p);
+        b = *(reinterpret_cast<const float4*>(p) + 1);
+    }
     __device__ __forceinline__ void zero() { a = make_float4(0.f, 0.f, 0.f, 0.f), b = a; }
     __device__ __forceinline__ void get(float (&x)[8]) const {
         x[0] = a.x, x[1] = a.y, x[2] = a.z, x[3] = a.w, x[4] = b.x, x[5] = b.y, x[6] = b.z, x[7] = b.w;
@@ -158,6 +162,7 @@ template <> struct Raw8<float> {
 template <> struct Raw8<__half> {
     uint4 u;
     __device__ __forceinline__ void load(const __half* p) { u = __ldg(reinterpret_cast<const uint4*>(p)); }
+    __device__ __forceinline__ void lds(const __half* p) { u = *reinterpret_cast<const uint4*>(p); }
     __device__ __forceinline__ void zero() { u = make_uint4(0u, 0u, 0u, 0u); }
     __device__ __forceinline__ void get(float (&x)[8]) const {
         const __half2* h = reinterpret_cast<const __half2*>(&u);
@@ -349,6 +354,205 @@ __global__ void __launch_bounds__(256) butd_attention_kernel(const T* __restrict
         for (int k = 0; k < KR; ++k) {
             if (k < K) store_h16x8(ctx16 + (static_cast<size_t>(img) * K + k) * ld16 + d0, lo16, acc[k]);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ streaming form
+// Persistent, copy-engine-fed variant of the kernel above (the one the decode loop uses when A <= 1024, D <= 2048 and
+// rows are dense): CTAs loop over images; one producer thread streams each image's projected features (phase 1) and
+// raw features (phase 3) into a shared-memory ring with cp.async.bulk (completion on mbarriers), running ahead of
+// the 256 consumer threads across chunk AND image boundaries, so HBM reads never wait for the arithmetic.
+template <int KR, typename T> struct AttStreamCfg {
+    static constexpr int GR = KR <= 3 ? 6 : (KR <= 5 ? 4 : 2);
+    static constexpr int NV = KR * GR;
+    static constexpr int NP = NV <= 8 ? 8 : (NV <= 16 ? 16 : 32);
+    static constexpr int RC3 = 6;                                            // regions per phase-3 chunk
+    static constexpr int STAGE_BYTES = 12 * 1024 * static_cast<int>(sizeof(T));  // 12 regions x 1024 cols / 6 x 2048
+    static constexpr int STAGES = sizeof(T) == 2 ? 4 : 3;
+    static constexpr int THREADS = 288;                                      // warp 0 = producer, warps 1-8 = consumers
+};
+
+template <int KR, typename T>
+__global__ void __launch_bounds__(288, (sizeof(T) == 2 ? 2 : 1))
+butd_attention_stream_kernel(const T* __restrict__ enc_ctx, const T* __restrict__ feats, const float* __restrict__ dec_ctx,
+                             const float* __restrict__ w_aff, float b_aff, int B, int R, int A, int D, int K,
+                             __half* __restrict__ ctx16, int ld16, int lo16) {
+    using C = AttStreamCfg<KR, T>;
+    constexpr int GR = C::GR, NV = C::NV, NP = C::NP, RC3 = C::RC3, STAGES = C::STAGES;
+    extern __shared__ uint8_t att_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(att_smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+    float* s_e = reinterpret_cast<float*>(bars + 2 * STAGES);  // [KR][R]
+    float* s_red = s_e + KR * R;                               // [2][8][NP]
+    const uint32_t full_bar = smem_u32(bars), empty_bar = smem_u32(bars + STAGES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_groups = (R + 2 * GR - 1) / (2 * GR);
+    const int n_chunks3 = (R + RC3 - 1) / RC3;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar + 8 * s, 1);
+            mbar_init(empty_bar + 8 * s, 8);  // one arrive per consumer warp
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ===================== producer: one thread issues every bulk copy, in consumer order =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int img = blockIdx.x; img < B; img += gridDim.x) {
+                const T* enc = enc_ctx + static_cast<size_t>(img) * R * A;
+                const T* f = feats + static_cast<size_t>(img) * R * D;
+                for (int c = 0; c < n_groups + n_chunks3; ++c) {
+                    const void* src;
+                    uint32_t bytes;
+                    if (c < n_groups) {
+                        const int r0 = c * 2 * GR, nr = min(2 * GR, R - r0);
+                        src = enc + static_cast<size_t>(r0) * A;
+                        bytes = static_cast<uint32_t>(nr) * A * sizeof(T);
+                    } else {
+                        const int r0 = (c - n_groups) * RC3, nr = min(RC3, R - r0);
+                        src = f + static_cast<size_t>(r0) * D;
+                        bytes = static_cast<uint32_t>(nr) * D * sizeof(T);
+                    }
+                    mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                    mbar_arrive_expect_tx(full_bar + 8 * stage, bytes);
+                    bulk_load_1d(smem_u32(smem + stage * C::STAGE_BYTES), src, bytes, full_bar + 8 * stage);
+                    if (++stage == STAGES) stage = 0, phase ^= 1;
+                }
+            }
+        }
+        return;
+    }
+
+    // ===================== consumers (256 threads) =====================
+    const int tid = threadIdx.x - 32, cw = warp - 1;
+    const int parity = tid >> 7, tcol = tid & 127;
+    const int a0 = tcol * 8;
+    const bool a_ok = a0 < A;
+    const int d0 = tid * 8;
+    const bool d_ok = d0 < D;
+    float w[8];
+    {
+        Raw8<float> t;
+        if (a_ok) t.load(w_aff + a0); else t.zero();
+        t.get(w);
+    }
+    float d[KR][8];
+    auto load_dec = [&](int img) {
+#pragma unroll
+        for (int k = 0; k < KR; ++k) {
+            Raw8<float> t;
+            if (a_ok && k < K && img < B) t.load(dec_ctx + (static_cast<size_t>(img) * K + k) * A + a0); else t.zero();
+            t.get(d[k]);
+        }
+    };
+    load_dec(blockIdx.x);
+    int stage = 0;
+    uint32_t phase = 0;
+    int red_flip = 0;
+    for (int img = blockIdx.x; img < B; img += gridDim.x) {
+        // ---------------- phase 1: scores, one ring stage per group of 2*GR regions
+        for (int g = 0; g < n_groups; ++g) {
+            float p[NP];
+#pragma unroll
+            for (int i = 0; i < NP; ++i) p[i] = 0.f;
+            mbar_wait(full_bar + 8 * stage, phase);
+            const T* chunk = reinterpret_cast<const T*>(smem + stage * C::STAGE_BYTES);
+            if (a_ok) {
+#pragma unroll
+                for (int i = 0; i < GR; ++i) {
+                    const int rl = 2 * i + parity;
+                    if (g * 2 * GR + rl < R) {
+                        float x[8];
+                        Raw8<T> raw;
+                        raw.lds(chunk + static_cast<size_t>(rl) * A + a0);
+                        raw.get(x);
+#pragma unroll
+                        for (int k = 0; k < KR; ++k) {
+                            float acc = 0.f;
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) acc = fmaf(w[q], fmaxf(x[q] + d[k][q], 0.f), acc);
+                            p[k * GR + i] = acc;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar + 8 * stage);
+            if (++stage == STAGES) stage = 0, phase ^= 1;
+            int oidx;
+            const float tot = warp_transpose_reduce<NP>(p, lane, oidx);
+            float* red = s_red + red_flip * 8 * NP;
+            red_flip ^= 1;
+            if ((lane & (32 / NP - 1)) == 0) red[cw * NP + oidx] = tot;
+            named_bar_sync(1, 256);
+            if (tid < 2 * NV) {
+                const int par = tid / NV, v = tid - par * NV;
+                const float sum = red[(par * 4 + 0) * NP + v] + red[(par * 4 + 1) * NP + v] + red[(par * 4 + 2) * NP + v] +
+                                  red[(par * 4 + 3) * NP + v];
+                const int k = v / GR, i = v - k * GR;
+                const int r = g * 2 * GR + par + 2 * i;
+                if (r < R && k < K) s_e[k * R + r] = sum + b_aff;
+            }
+        }
+        load_dec(img + gridDim.x);  // next image's dec_att rows: latency hidden behind phases 2-3
+        named_bar_sync(1, 256);
+        // ---------------- phase 2: softmax over regions, one warp per row
+        for (int k = cw; k < K; k += 8) {
+            float m = -INFINITY;
+            for (int r = lane; r < R; r += 32) m = fmaxf(m, s_e[k * R + r]);
+            m = warp_max(m);
+            float s = 0.f;
+            for (int r = lane; r < R; r += 32) {
+                const float ex = expf(s_e[k * R + r] - m);
+                s_e[k * R + r] = ex;
+                s += ex;
+            }
+            s = warp_sum(s);
+            for (int r = lane; r < R; r += 32) s_e[k * R + r] = s_e[k * R + r] / s;
+        }
+        named_bar_sync(1, 256);
+        // ---------------- phase 3: weighted feature sum, one ring stage per RC3 regions
+        float acc[KR][8];
+#pragma unroll
+        for (int k = 0; k < KR; ++k)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[k][q] = 0.f;
+        for (int c = 0; c < n_chunks3; ++c) {
+            mbar_wait(full_bar + 8 * stage, phase);
+            const T* chunk = reinterpret_cast<const T*>(smem + stage * C::STAGE_BYTES);
+            if (d_ok) {
+#pragma unroll
+                for (int i = 0; i < RC3; ++i) {
+                    const int r = c * RC3 + i;
+                    if (r < R) {
+                        float x[8];
+                        Raw8<T> raw;
+                        raw.lds(chunk + static_cast<size_t>(i) * D + d0);
+                        raw.get(x);
+#pragma unroll
+                        for (int k = 0; k < KR; ++k) {
+                            const float al = s_e[k * R + r];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) acc[k][q] = fmaf(al, x[q], acc[k][q]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar + 8 * stage);
+            if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+        if (d_ok) {
+#pragma unroll
+            for (int k = 0; k < KR; ++k)
+                if (k < K) store_h16x8(ctx16 + (static_cast<size_t>(img) * K + k) * ld16 + d0, lo16, acc[k]);
+        }
+        named_bar_sync(1, 256);  // s_e is rewritten by the next image's phase 1
     }
 }
 
