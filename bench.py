@@ -33,10 +33,12 @@ UNIT = "captions/s"
 
 WORKLOADS = {
     # name: arch, model_type, regions, beam, images per GPU, description
-    "butd_det": dict(arch="BUTD", model_type="BUTDDetection", R=36, beam=3, batch=1024,
+    # 1578 images x beam 3 = 4734 rows = 37 row tiles of 128: the gate GEMMs (16 column tiles) then fill exactly 4 waves of
+    # the 148 SMs and the dec_att GEMM exactly one
+    "butd_det": dict(arch="BUTD", model_type="BUTDDetection", R=36, beam=3, batch=1578,
                      desc="BUTDDetection beam=3 eval, synthetic 36x2048 region feats, vocab 9487, random init "
                           "(BASELINE configs[0] model at a GPU-sized batch)"),
-    "butd_spatial": dict(arch="BUTD", model_type="BUTDSpatial", R=196, beam=5, batch=1024,
+    "butd_spatial": dict(arch="BUTD", model_type="BUTDSpatial", R=196, beam=5, batch=947,
                          desc="BUTDSpatial beam=5 over a 14x14x2048 feature grid (configs[2], decoder only)"),
     "nic": dict(arch="NIC", model_type="NIC", R=0, beam=3, batch=256,
                 desc="NIC LSTM decoder beam=3 on synthetic image embeddings (configs[1] without the ResNet-101 encoder)"),

@@ -452,7 +452,7 @@ int launch_butd_att_stream_t(capdec_handle* h, const StepCtx& c, const T* enc, c
         attr_set = true;
     }
     if (smem > 200 * 1024) return fail(h, CAPDEC_ERR_INVALID, "attention ring does not fit shared memory");
-    const int per_sm = sizeof(T) == 2 ? 2 : 1;
+    const int per_sm = C::CTAS_PER_SM;
     const int grid = h->B < h->num_sms * per_sm ? h->B : h->num_sms * per_sm;
     prof_begin(h, CAPDEC_CAT_ATTENTION, 0.0, st);
     kern<<<grid, C::THREADS, smem, st>>>(enc, feats, h->dec_ctx, h->w_aff, h->b_aff, h->B, h->R, h->A, h->D, c.K, h->XB.p, h->XB.ld,
@@ -1001,7 +1001,10 @@ int capdec_beam_search(capdec_handle* h, int32_t beam, int32_t max_seq, int32_t*
     s.seqs_in = h->seqs[0], s.seqs_out = h->seqs[1];
     const bool nic = h->cfg.arch == CAPDEC_ARCH_NIC;
     // NIC: step 1 reads the primed cell state of the image, so parent[row] starts as the image index into c0
-    beam_init_kernel<<<B, 128, 0, st>>>(s, adv_ops(h, true), nic ? 1 : 0);
+    if (K <= 1) beam_init_kernel<1><<<B, 128, 0, st>>>(s, adv_ops(h, true), nic ? 1 : 0);
+    else if (K <= 3) beam_init_kernel<3><<<B, 128, 0, st>>>(s, adv_ops(h, true), nic ? 1 : 0);
+    else if (K <= 5) beam_init_kernel<5><<<B, 128, 0, st>>>(s, adv_ops(h, true), nic ? 1 : 0);
+    else beam_init_kernel<8><<<B, 128, 0, st>>>(s, adv_ops(h, true), nic ? 1 : 0);
     CK(h, cudaGetLastError());
     h->launches++;
     StepCtx c{};
@@ -1015,8 +1018,11 @@ int capdec_beam_search(capdec_handle* h, int32_t beam, int32_t max_seq, int32_t*
         s.seqs_in = h->seqs[(t + 1) & 1];
         s.seqs_out = h->seqs[t & 1];
         prof_begin(h, CAPDEC_CAT_BOOKKEEPING, 0.0, st);
-        if (c.ktop == 4) beam_step_kernel<4><<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t, ops);
-        else beam_step_kernel<8><<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t, ops);
+        if (K <= 1) beam_step_kernel<4, 1><<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t, ops);
+        else if (K <= 3) beam_step_kernel<4, 3><<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t, ops);
+        else if (K <= 4) beam_step_kernel<4, 5><<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t, ops);
+        else if (K <= 5) beam_step_kernel<8, 5><<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t, ops);
+        else beam_step_kernel<8, 8><<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t, ops);
         prof_end(h, st);
         CK(h, cudaGetLastError());
         h->launches++;
@@ -1046,7 +1052,10 @@ int capdec_sample(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t 
     s.tokens = tokens, s.logprobs = logprobs;
     s.multinomial = mode == CAPDEC_SAMPLE_MULTINOMIAL;
     const bool nic = h->cfg.arch == CAPDEC_ARCH_NIC;
-    sample_init_kernel<<<B, 128, 0, st>>>(s, adv_ops(h, true), nic ? 1 : 0);
+    if (n <= 1) sample_init_kernel<1><<<B, 128, 0, st>>>(s, adv_ops(h, true), nic ? 1 : 0);
+    else if (n <= 3) sample_init_kernel<3><<<B, 128, 0, st>>>(s, adv_ops(h, true), nic ? 1 : 0);
+    else if (n <= 5) sample_init_kernel<5><<<B, 128, 0, st>>>(s, adv_ops(h, true), nic ? 1 : 0);
+    else sample_init_kernel<8><<<B, 128, 0, st>>>(s, adv_ops(h, true), nic ? 1 : 0);
     CK(h, cudaGetLastError());
     h->launches++;
     StepCtx c{};
@@ -1060,7 +1069,10 @@ int capdec_sample(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t 
         c.first_from_c0 = nic && t == 1;
         CKS(h, run_step(h, c, st));
         prof_begin(h, CAPDEC_CAT_BOOKKEEPING, 0.0, st);
-        sample_step_kernel<<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t - 1, ops);
+        if (n <= 1) sample_step_kernel<1><<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t - 1, ops);
+        else if (n <= 3) sample_step_kernel<3><<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t - 1, ops);
+        else if (n <= 5) sample_step_kernel<5><<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t - 1, ops);
+        else sample_step_kernel<8><<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t - 1, ops);
         prof_end(h, st);
         CK(h, cudaGetLastError());
         h->launches++;

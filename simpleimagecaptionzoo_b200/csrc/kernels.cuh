@@ -370,10 +370,11 @@ template <int KR, typename T> struct AttStreamCfg {
     static constexpr int STAGE_BYTES = 12 * 1024 * static_cast<int>(sizeof(T));  // 12 regions x 1024 cols / 6 x 2048
     static constexpr int STAGES = sizeof(T) == 2 ? 4 : 3;
     static constexpr int THREADS = 288;                                      // warp 0 = producer, warps 1-8 = consumers
+    static constexpr int CTAS_PER_SM = (sizeof(T) == 2 && KR <= 3) ? 2 : 1;  // register budget: no spills
 };
 
 template <int KR, typename T>
-__global__ void __launch_bounds__(288, (sizeof(T) == 2 ? 2 : 1))
+__global__ void __launch_bounds__(288, AttStreamCfg<KR, T>::CTAS_PER_SM)
 butd_attention_stream_kernel(const T* __restrict__ enc_ctx, const T* __restrict__ feats, const float* __restrict__ dec_ctx,
                              const float* __restrict__ w_aff, float b_aff, int B, int R, int A, int D, int K,
                              __half* __restrict__ ctx16, int ld16, int lo16) {
@@ -726,38 +727,72 @@ struct AdvOps {
     AdvOp op[6];
 };
 
-// row = destination row, prow = source (parent) row, img = image index, tok = word fed to the next step
-__device__ __forceinline__ void advance_row(const AdvOps& ops, int row, int prow, int img, int tok, int tid, int nthreads) {
+// Rebuild the operand rows of all K slots of one image.  s_prow[slot] = absolute source (parent) row, s_tok[slot] =
+// word fed to the next step (both in shared memory).  For every 16-byte vector the loads of all K slots are issued
+// before the first store, so K (x2 with the lo halves) independent loads are in flight per thread.
+template <int KR>
+__device__ __forceinline__ void advance_image(const AdvOps& ops, int img, int K, const int* s_prow, const int* s_tok, int tid,
+                                              int nthreads) {
     for (int q = 0; q < ops.n; ++q) {
         const AdvOp& o = ops.op[q];
-        __half* dst = o.dst + static_cast<size_t>(row) * o.dst_ld;
         if (o.kind == ADV_COPY16 || o.kind == ADV_BCAST16) {
-            const int srow = o.kind == ADV_COPY16 ? prow : img;
-            const __half* src = static_cast<const __half*>(o.src) + static_cast<size_t>(srow) * o.src_ld;
-            const int n8 = o.n >> 3;
-            for (int i = tid; i < n8; i += nthreads) {
-                reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
-                if (o.dst_lo > 0) reinterpret_cast<uint4*>(dst + o.dst_lo)[i] = reinterpret_cast<const uint4*>(src + o.src_lo)[i];
+            const __half* src = static_cast<const __half*>(o.src);
+            const bool lo = o.dst_lo > 0;
+            for (int v = tid; v < (o.n >> 3); v += nthreads) {
+                uint4 hi_v[KR], lo_v[KR];
+#pragma unroll
+                for (int s = 0; s < KR; ++s) {
+                    if (s < K) {
+                        const size_t srow = o.kind == ADV_COPY16 ? s_prow[s] : img;
+                        hi_v[s] = reinterpret_cast<const uint4*>(src + srow * o.src_ld)[v];
+                        if (lo) lo_v[s] = reinterpret_cast<const uint4*>(src + srow * o.src_ld + o.src_lo)[v];
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < KR; ++s) {
+                    if (s < K) {
+                        __half* dst = o.dst + static_cast<size_t>(img * K + s) * o.dst_ld;
+                        reinterpret_cast<uint4*>(dst)[v] = hi_v[s];
+                        if (lo) reinterpret_cast<uint4*>(dst + o.dst_lo)[v] = lo_v[s];
+                    }
+                }
             }
-        } else if (o.kind == ADV_EMBED) {
-            const float* src = static_cast<const float*>(o.src) + static_cast<size_t>(tok) * o.src_ld;
-            for (int i = tid; i < o.n; i += nthreads) {
-                float x = __ldg(src + i);
-                if (o.flag) x = fmaxf(x, 0.f);
-                __half hi, lo;
-                split_f16(x, hi, lo);
-                dst[i] = hi;
-                if (o.dst_lo > 0) dst[o.dst_lo + i] = lo;
-            }
-        } else {  // ADV_MEAN_PLUS
-            const float* c = o.src ? static_cast<const float*>(o.src) + static_cast<size_t>(prow) * o.src_ld : nullptr;
-            const float* mn = o.aux + static_cast<size_t>(img) * o.n;
-            for (int i = tid; i < o.n; i += nthreads) {
-                const float x = mn[i] + (c ? c[i] : 0.f);
-                __half hi, lo;
-                split_f16(x, hi, lo);
-                dst[i] = hi;
-                if (o.dst_lo > 0) dst[o.dst_lo + i] = lo;
+        } else {
+            const bool embed = o.kind == ADV_EMBED;
+            for (int v = tid; v < (o.n >> 2); v += nthreads) {
+                float4 x[KR];
+#pragma unroll
+                for (int s = 0; s < KR; ++s) {
+                    if (s < K) {
+                        if (embed) {
+                            x[s] = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(o.src) +
+                                                                         static_cast<size_t>(s_tok[s]) * o.src_ld) + v);
+                        } else {  // ADV_MEAN_PLUS: mean[img] + ctx[parent row]
+                            x[s] = __ldg(reinterpret_cast<const float4*>(o.aux + static_cast<size_t>(img) * o.n) + v);
+                            if (o.src) {
+                                const float4 c = reinterpret_cast<const float4*>(static_cast<const float*>(o.src) +
+                                                                                 static_cast<size_t>(s_prow[s]) * o.src_ld)[v];
+                                x[s].x += c.x, x[s].y += c.y, x[s].z += c.z, x[s].w += c.w;
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < KR; ++s) {
+                    if (s < K) {
+                        float4 y = x[s];
+                        if (embed && o.flag) y.x = fmaxf(y.x, 0.f), y.y = fmaxf(y.y, 0.f), y.z = fmaxf(y.z, 0.f), y.w = fmaxf(y.w, 0.f);
+                        __align__(8) __half hi[4];
+                        __align__(8) __half lw[4];
+                        split_f16(y.x, hi[0], lw[0]);
+                        split_f16(y.y, hi[1], lw[1]);
+                        split_f16(y.z, hi[2], lw[2]);
+                        split_f16(y.w, hi[3], lw[3]);
+                        __half* dst = o.dst + static_cast<size_t>(img * K + s) * o.dst_ld + 4 * v;
+                        *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(hi);
+                        if (o.dst_lo > 0) *reinterpret_cast<uint2*>(dst + o.dst_lo) = *reinterpret_cast<const uint2*>(lw);
+                    }
+                }
             }
         }
     }
@@ -779,6 +814,7 @@ struct BeamState {
 
 // t = 0: initial state (all K slots <sta>, cum 0; BUTD_Model.py:247-250); no partials are read.
 // parent_is_img: the first LSTM step reads a per-IMAGE cell state (NIC's primed c0), so parent[row] = image.
+template <int KR>
 __global__ void beam_init_kernel(BeamState s, AdvOps ops, int parent_is_img) {
     const int img = blockIdx.x;
     const int L = s.T + 1;
@@ -800,8 +836,10 @@ __global__ void beam_init_kernel(BeamState s, AdvOps ops, int parent_is_img) {
         s.best_score[img] = -INFINITY;
         s.best_len[img] = 0;
     }
-    for (int slot = 0; slot < s.K; ++slot)
-        advance_row(ops, img * s.K + slot, img * s.K + slot, img, TOK_STA, threadIdx.x, blockDim.x);
+    __shared__ int i_prow[MAX_ROWS], i_tok[MAX_ROWS];
+    if (threadIdx.x < MAX_ROWS) i_prow[threadIdx.x] = img * s.K + threadIdx.x, i_tok[threadIdx.x] = TOK_STA;
+    __syncthreads();
+    advance_image<KR>(ops, img, s.K, i_prow, i_tok, threadIdx.x, blockDim.x);
 }
 
 // One CTA (128 threads) per image.  Merges the per-(row, N-tile) partials of the logit GEMM into log-softmax
@@ -809,7 +847,7 @@ __global__ void beam_init_kernel(BeamState s, AdvOps ops, int parent_is_img) {
 // (BUTD_Model.py:271-302 == NIC_Model.py:175-202 == AoA_Model.py:456-488):
 //   step 1 looks at row 0 only; selected <end> candidates complete (running best, strict '>' = first max) and
 //   shrink the beam; survivors keep their sorted order; states follow their parent.
-template <int KTOP>
+template <int KTOP, int KR>
 __global__ void __launch_bounds__(128) beam_step_kernel(const float* __restrict__ part, int n_tiles, BeamState s, int t,
                                                         AdvOps ops) {
     constexpr int PS = topk_part_stride(KTOP);
@@ -899,7 +937,7 @@ __global__ void __launch_bounds__(128) beam_step_kernel(const float* __restrict_
             } else {
                 for (int i = 0; i < t; ++i) sout[n_new * L + i] = sin[br * L + i];
                 sout[n_new * L + t] = word;
-                s_parent[n_new] = br;
+                s_parent[n_new] = img * K + br;  // absolute parent row
                 s_tok[n_new] = word;
                 s.cum[img * K + n_new] = bv;
                 ++n_new;
@@ -908,18 +946,17 @@ __global__ void __launch_bounds__(128) beam_step_kernel(const float* __restrict_
         s.best_score[img] = best;
         s.n_live[img] = n_new;
         for (int q = n_new; q < K; ++q) {
-            s_parent[q] = 0;
+            s_parent[q] = img * K;
             s_tok[q] = TOK_PAD;
             s.cum[img * K + q] = -INFINITY;
         }
     }
     __syncthreads();
     if (threadIdx.x < K) {
-        s.parent[img * K + threadIdx.x] = img * K + s_parent[threadIdx.x];
+        s.parent[img * K + threadIdx.x] = s_parent[threadIdx.x];
         s.tok[img * K + threadIdx.x] = s_tok[threadIdx.x];
     }
-    for (int slot = 0; slot < K; ++slot)
-        advance_row(ops, img * K + slot, img * K + s_parent[slot], img, s_tok[slot], threadIdx.x, blockDim.x);
+    advance_image<KR>(ops, img, K, s_parent, s_tok, threadIdx.x, blockDim.x);
 }
 
 // Result selection (BUTD_Model.py:306-315): the best COMPLETED hypothesis if any, else live slot 0 (slots stay
@@ -948,6 +985,7 @@ struct SampleState {
     int multinomial;
 };
 
+template <int KR>
 __global__ void sample_init_kernel(SampleState s, AdvOps ops, int parent_is_img) {
     const int img = blockIdx.x;
     if (threadIdx.x < s.n) {
@@ -958,17 +996,22 @@ __global__ void sample_init_kernel(SampleState s, AdvOps ops, int parent_is_img)
     }
     if (img == 0)
         for (int i = threadIdx.x; i <= s.T; i += blockDim.x) s.live_count[i] = 0;
-    for (int j = 0; j < s.n; ++j) advance_row(ops, img * s.n + j, img * s.n + j, img, TOK_STA, threadIdx.x, blockDim.x);
+    __shared__ int i_prow[MAX_ROWS], i_tok[MAX_ROWS];
+    if (threadIdx.x < MAX_ROWS) i_prow[threadIdx.x] = img * s.n + threadIdx.x, i_tok[threadIdx.x] = TOK_STA;
+    __syncthreads();
+    advance_image<KR>(ops, img, s.n, i_prow, i_tok, threadIdx.x, blockDim.x);
 }
 
 // One CTA per image, one warp per row.  sample (BUTD_Model.py:183-188): word = argmax; sample_rl (:221-233):
 // word ~ multinomial via Gumbel-max, logprob gathered, <end> and everything after it stored as 0, 0 fed back.
+template <int KR>
 __global__ void __launch_bounds__(128) sample_step_kernel(const float* __restrict__ part, int n_tiles, SampleState s, int t,
                                                           AdvOps ops) {
-    __shared__ int s_tok[MAX_ROWS];
+    __shared__ int s_tok[MAX_ROWS], s_prow[MAX_ROWS];
     const int img = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int PS = SAMPLE_PART_STRIDE;
+    if (threadIdx.x < MAX_ROWS) s_prow[threadIdx.x] = img * s.n + threadIdx.x;
     const bool stopped = s.multinomial && t > 0 && s.live_count[t - 1] == 0;  // reference broke out of the loop
     for (int r = warp; r < s.n; r += 4) {
         const int row = img * s.n + r;
@@ -1016,7 +1059,7 @@ __global__ void __launch_bounds__(128) sample_step_kernel(const float* __restric
         }
     }
     __syncthreads();
-    for (int j = 0; j < s.n; ++j) advance_row(ops, img * s.n + j, img * s.n + j, img, s_tok[j], threadIdx.x, blockDim.x);
+    advance_image<KR>(ops, img, s.n, s_prow, s_tok, threadIdx.x, blockDim.x);
 }
 
 }  // namespace capdec
