@@ -187,7 +187,7 @@ int launch_gemm_t(capdec_handle* h, const CUtensorMap& ma, const CUtensorMap& mb
         CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    const int tiles = p.num_m_blocks * p.num_n_blocks;
+    const int tiles = p.runs > 0 ? p.num_m_blocks * p.runs : p.num_m_blocks * p.num_n_blocks;
     const int grid = tiles < h->num_sms ? tiles : h->num_sms;
     const int cat = EPI == EPI_LSTM ? CAPDEC_CAT_GEMM_LSTM : EPI == EPI_STORE ? CAPDEC_CAT_GEMM_STORE
                   : EPI == EPI_GLU ? CAPDEC_CAT_GEMM_GLU : CAPDEC_CAT_GEMM_LOGITS;
@@ -200,6 +200,15 @@ int launch_gemm_t(capdec_handle* h, const CUtensorMap& ma, const CUtensorMap& mb
 }
 
 // D[M,N] = A[M,Kdim] * B[N,Kdim]^T with the chosen epilogue.
+// number of vocabulary-tile runs per row block of the logit GEMM: fill the SMs with (row block, run) items
+int logit_runs(const capdec_handle* h, int M, int N) {
+    const int num_m = (M + BLOCK_M - 1) / BLOCK_M, num_n = (N + BN - 1) / BN;
+    int runs = h->num_sms / num_m;
+    if (runs < 1) runs = 1;
+    if (runs > num_n) runs = num_n;
+    return runs;
+}
+
 int launch_gemm(capdec_handle* h, int epi, int ktop, const CUtensorMap& ma, int a_lo, const CUtensorMap& mb, int b_lo, int M,
                 int N, int Kdim, const EpiParams& e, cudaStream_t st) {
     if (Kdim % BLOCK_K) return fail(h, CAPDEC_ERR_INVALID, "GEMM K must be a multiple of 64");
@@ -213,6 +222,7 @@ int launch_gemm(capdec_handle* h, int epi, int ktop, const CUtensorMap& ma, int 
     p.b_lo_off = b_lo;
     p.num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
     p.num_n_blocks = (N + BN - 1) / BN;
+    p.runs = (epi == EPI_TOPK || epi == EPI_SAMPLE) ? logit_runs(h, M, N) : 0;
     p.epi = e;
     switch (epi) {
         case EPI_STORE: return launch_gemm_t<EPI_STORE, 1>(h, ma, mb, p, st);
@@ -414,7 +424,7 @@ int run_logits(capdec_handle* h, const Act16& a, const StepCtx& c, cudaStream_t 
     EpiParams e{};
     e.bias = h->b_pred;
     e.part = h->part;
-    e.n_tiles = h->n_tiles_v;
+    e.n_tiles = logit_runs(h, c.M, h->V) * EPI_SPLIT;
     e.seed = c.seed;
     e.step = c.t - 1;
     e.use_noise = c.use_noise;
@@ -1007,6 +1017,7 @@ int capdec_beam_search(capdec_handle* h, int32_t beam, int32_t max_seq, int32_t*
     else beam_init_kernel<8><<<B, 128, 0, st>>>(s, adv_ops(h, true), nic ? 1 : 0);
     CK(h, cudaGetLastError());
     h->launches++;
+    const int n_slots = logit_runs(h, M, h->V) * EPI_SPLIT;  // partial records per row written by the logit GEMM
     StepCtx c{};
     c.M = M, c.K = K, c.logits_epi = EPI_TOPK, c.ktop = ktop_for(K);
     const AdvOps ops = adv_ops(h, false);
@@ -1018,11 +1029,11 @@ int capdec_beam_search(capdec_handle* h, int32_t beam, int32_t max_seq, int32_t*
         s.seqs_in = h->seqs[(t + 1) & 1];
         s.seqs_out = h->seqs[t & 1];
         prof_begin(h, CAPDEC_CAT_BOOKKEEPING, 0.0, st);
-        if (K <= 1) beam_step_kernel<4, 1><<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t, ops);
-        else if (K <= 3) beam_step_kernel<4, 3><<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t, ops);
-        else if (K <= 4) beam_step_kernel<4, 5><<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t, ops);
-        else if (K <= 5) beam_step_kernel<8, 5><<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t, ops);
-        else beam_step_kernel<8, 8><<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t, ops);
+        if (K <= 1) beam_step_kernel<4, 1><<<B, 128, 0, st>>>(h->part, n_slots, s, t, ops);
+        else if (K <= 3) beam_step_kernel<4, 3><<<B, 128, 0, st>>>(h->part, n_slots, s, t, ops);
+        else if (K <= 4) beam_step_kernel<4, 5><<<B, 128, 0, st>>>(h->part, n_slots, s, t, ops);
+        else if (K <= 5) beam_step_kernel<8, 5><<<B, 128, 0, st>>>(h->part, n_slots, s, t, ops);
+        else beam_step_kernel<8, 8><<<B, 128, 0, st>>>(h->part, n_slots, s, t, ops);
         prof_end(h, st);
         CK(h, cudaGetLastError());
         h->launches++;
@@ -1058,6 +1069,7 @@ int capdec_sample(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t 
     else sample_init_kernel<8><<<B, 128, 0, st>>>(s, adv_ops(h, true), nic ? 1 : 0);
     CK(h, cudaGetLastError());
     h->launches++;
+    const int n_slots = logit_runs(h, M, h->V) * EPI_SPLIT;
     StepCtx c{};
     c.M = M, c.K = n, c.logits_epi = EPI_SAMPLE, c.ktop = 1;
     c.seed = static_cast<uint32_t>(seed & 0xFFFFFFFFu);
@@ -1069,10 +1081,10 @@ int capdec_sample(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t 
         c.first_from_c0 = nic && t == 1;
         CKS(h, run_step(h, c, st));
         prof_begin(h, CAPDEC_CAT_BOOKKEEPING, 0.0, st);
-        if (n <= 1) sample_step_kernel<1><<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t - 1, ops);
-        else if (n <= 3) sample_step_kernel<3><<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t - 1, ops);
-        else if (n <= 5) sample_step_kernel<5><<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t - 1, ops);
-        else sample_step_kernel<8><<<B, 128, 0, st>>>(h->part, h->n_tiles_v, s, t - 1, ops);
+        if (n <= 1) sample_step_kernel<1><<<B, 128, 0, st>>>(h->part, n_slots, s, t - 1, ops);
+        else if (n <= 3) sample_step_kernel<3><<<B, 128, 0, st>>>(h->part, n_slots, s, t - 1, ops);
+        else if (n <= 5) sample_step_kernel<5><<<B, 128, 0, st>>>(h->part, n_slots, s, t - 1, ops);
+        else sample_step_kernel<8><<<B, 128, 0, st>>>(h->part, n_slots, s, t - 1, ops);
         prof_end(h, st);
         CK(h, cudaGetLastError());
         h->launches++;
@@ -1187,7 +1199,7 @@ int capdec_test_gemm_time(int32_t m, int32_t n, int32_t k, int32_t epi, int32_t 
             e.c_in = c0, e.c_out = c1, e.ldc = n / 4;
             e.out16 = H16.p, e.ld16 = H16.ld, e.lo16 = H16.lo;
         } else if (epi == EPI_TOPK) {
-            const int nt = ((n + BN - 1) / BN) * EPI_SPLIT;
+            const int nt = logit_runs(h, m, n) * EPI_SPLIT;
             if ((status = dalloc(h, &part, static_cast<size_t>(m) * nt * topk_part_stride(4))) != CAPDEC_OK) break;
             e.part = part;
             e.n_tiles = nt;

@@ -63,6 +63,7 @@ struct GemmParams {
     int passes;             // 1 (fp16) or 3 (split)
     int a_lo_off, b_lo_off; // column offset of the lo halves (elements)
     int num_m_blocks, num_n_blocks;
+    int runs;               // > 0: (row block, vocabulary-tile run) work items, see TileIter
     EpiParams epi;
 };
 
@@ -292,43 +293,50 @@ __device__ __forceinline__ float logits_chunk_stats(float (&v)[32], int n0, int 
     return cmax;
 }
 
-// Per (row, partial slot): running max, sum of exp(x - max), and the KTOP largest logits with their vocabulary
-// indices (ties keep the lower index first).  The full logits row is never written to HBM.
-template <int BLOCK_N, int KTOP>
-__device__ __forceinline__ void epi_topk(uint32_t taddr, int row, int n_base, int c0, int c1, int slot, const GemmParams& p) {
-    const EpiParams& e = p.epi;
-    float m = -INFINITY, s = 0.f;
+// Running per-row state of the fused log-softmax / top-k epilogue.  It is carried in registers across all the
+// vocabulary tiles one CTA processes for a row block (a "run"), so the top-k warm-up is paid once per run and a
+// row produces only runs * EPI_SPLIT partial records: (max, sum of exp(x - max), KTOP largest logits with their
+// vocabulary indices, ties keep the lower index first).  The full logits row is never written to HBM.
+template <int KTOP>
+struct TopkState {
+    float m, s;
     float tv[KTOP];
     int ti[KTOP];
+    __device__ __forceinline__ void init() {
+        m = -INFINITY, s = 0.f;
 #pragma unroll
-    for (int q = 0; q < KTOP; ++q) tv[q] = -INFINITY, ti[q] = 0x7FFFFFFF;
+        for (int q = 0; q < KTOP; ++q) tv[q] = -INFINITY, ti[q] = 0x7FFFFFFF;
+    }
+    __device__ __forceinline__ void tile(uint32_t taddr, int n_base, int c0, int c1, const GemmParams& p) {
 #pragma unroll 1
-    for (int c = c0; c < c1; ++c) {
-        const int n0 = n_base + c * 32;
-        if (n0 >= p.N) break;
-        float v[32];
-        tmem_ld_32x32(taddr + c * 32, v);
-        const float cmax = logits_chunk_stats(v, n0, p.N, e.bias, m, s);
-        if (cmax > tv[KTOP - 1]) {
+        for (int c = c0; c < c1; ++c) {
+            const int n0 = n_base + c * 32;
+            if (n0 >= p.N) break;
+            float v[32];
+            tmem_ld_32x32(taddr + c * 32, v);
+            const float cmax = logits_chunk_stats(v, n0, p.N, p.epi.bias, m, s);
+            if (cmax > tv[KTOP - 1]) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                if (v[i] > tv[KTOP - 1]) {
-                    tv[KTOP - 1] = v[i];
-                    ti[KTOP - 1] = n0 + i;
+                for (int i = 0; i < 32; ++i) {
+                    if (v[i] > tv[KTOP - 1]) {
+                        tv[KTOP - 1] = v[i];
+                        ti[KTOP - 1] = n0 + i;
 #pragma unroll
-                    for (int q = KTOP - 1; q > 0; --q) {
-                        if (tv[q] > tv[q - 1]) {
-                            const float fv = tv[q]; tv[q] = tv[q - 1]; tv[q - 1] = fv;
-                            const int iv = ti[q]; ti[q] = ti[q - 1]; ti[q - 1] = iv;
+                        for (int q = KTOP - 1; q > 0; --q) {
+                            if (tv[q] > tv[q - 1]) {
+                                const float fv = tv[q]; tv[q] = tv[q - 1]; tv[q - 1] = fv;
+                                const int iv = ti[q]; ti[q] = ti[q - 1]; ti[q - 1] = iv;
+                            }
                         }
                     }
                 }
             }
         }
     }
-    if (row < p.M) {
+    __device__ __forceinline__ void flush(int row, int slot, const GemmParams& p) const {
+        if (row >= p.M) return;
         constexpr int PS = topk_part_stride(KTOP);
-        float* o = e.part + (static_cast<size_t>(row) * e.n_tiles + slot) * PS;
+        float* o = p.epi.part + (static_cast<size_t>(row) * p.epi.n_tiles + slot) * PS;
         o[0] = m;
         o[1] = s;
 #pragma unroll
@@ -337,47 +345,90 @@ __device__ __forceinline__ void epi_topk(uint32_t taddr, int row, int n_base, in
             o[2 + KTOP + q] = __int_as_float(ti[q]);
         }
     }
-}
+};
 
 // Greedy / multinomial draw: argmax over the vocabulary of (logit + Gumbel noise); with use_noise == 0 this is
 // the plain argmax of ``sample``.  Also carries (max, sum-exp) for the log-prob of the drawn word.
-template <int BLOCK_N>
-__device__ __forceinline__ void epi_sample(uint32_t taddr, int row, int n_base, int c0, int c1, int slot, const GemmParams& p) {
-    const EpiParams& e = p.epi;
-    float m = -INFINITY, s = 0.f;
-    float best = -INFINITY, best_raw = 0.f;
-    int best_i = 0x7FFFFFFF;
-    const uint32_t rs = gumbel_row_step_hash(e.seed, static_cast<uint32_t>(row), static_cast<uint32_t>(e.step));
+struct DrawState {
+    float m, s, best, best_raw;
+    int best_i;
+    uint32_t rs;
+    __device__ __forceinline__ void init(int row, const GemmParams& p) {
+        m = -INFINITY, s = 0.f, best = -INFINITY, best_raw = 0.f, best_i = 0x7FFFFFFF;
+        rs = gumbel_row_step_hash(p.epi.seed, static_cast<uint32_t>(row), static_cast<uint32_t>(p.epi.step));
+    }
+    __device__ __forceinline__ void tile(uint32_t taddr, int n_base, int c0, int c1, const GemmParams& p) {
 #pragma unroll 1
-    for (int c = c0; c < c1; ++c) {
-        const int n0 = n_base + c * 32;
-        if (n0 >= p.N) break;
-        float v[32];
-        tmem_ld_32x32(taddr + c * 32, v);
-        const float cmax = logits_chunk_stats(v, n0, p.N, e.bias, m, s);
-        if (e.use_noise) {
+        for (int c = c0; c < c1; ++c) {
+            const int n0 = n_base + c * 32;
+            if (n0 >= p.N) break;
+            float v[32];
+            tmem_ld_32x32(taddr + c * 32, v);
+            const float cmax = logits_chunk_stats(v, n0, p.N, p.epi.bias, m, s);
+            if (p.epi.use_noise) {
 #pragma unroll 4
-            for (int i = 0; i < 32; ++i) {
-                if (n0 + i < p.N) {
-                    const float pv = v[i] + gumbel_from_hash(rs, static_cast<uint32_t>(n0 + i));
-                    if (pv > best) best = pv, best_i = n0 + i, best_raw = v[i];
+                for (int i = 0; i < 32; ++i) {
+                    if (n0 + i < p.N) {
+                        const float pv = v[i] + gumbel_from_hash(rs, static_cast<uint32_t>(n0 + i));
+                        if (pv > best) best = pv, best_i = n0 + i, best_raw = v[i];
+                    }
                 }
-            }
-        } else if (cmax > best) {
+            } else if (cmax > best) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (v[i] > best) best = v[i], best_i = n0 + i, best_raw = v[i];
+                for (int i = 0; i < 32; ++i)
+                    if (v[i] > best) best = v[i], best_i = n0 + i, best_raw = v[i];
+            }
         }
     }
-    if (row < p.M) {
-        float* o = e.part + (static_cast<size_t>(row) * e.n_tiles + slot) * SAMPLE_PART_STRIDE;
+    __device__ __forceinline__ void flush(int row, int slot, const GemmParams& p) const {
+        if (row >= p.M) return;
+        float* o = p.epi.part + (static_cast<size_t>(row) * p.epi.n_tiles + slot) * SAMPLE_PART_STRIDE;
         o[0] = m;
         o[1] = s;
         o[2] = best;
         o[3] = __int_as_float(best_i);
         o[4] = best_raw;
     }
-}
+};
+
+// Work decomposition.  runs == 0: output tiles in M-fastest order, round-robin over the CTAs (CTAs resident at the
+// same time share weight tiles in L2).  runs > 0 (logit GEMM): a work item is (row block, run) = a contiguous range of
+// vocabulary tiles of one row block, so the epilogue's per-row state persists across the item's tiles.
+struct TileIter {
+    int item, items, step, runs, num_m, num_n;
+    int m_blk, n_blk, n_end, run;
+    __device__ __forceinline__ TileIter(const GemmParams& p)
+        : item(blockIdx.x), step(gridDim.x), runs(p.runs), num_m(p.num_m_blocks), num_n(p.num_n_blocks) {
+        items = runs > 0 ? num_m * runs : num_m * num_n;
+        n_blk = 0, n_end = 0, m_blk = 0, run = 0;
+    }
+    // advance to the next tile of this CTA; returns false when done.  first_of_item / last_of_item delimit a run.
+    __device__ __forceinline__ bool next(bool& first_of_item, bool& last_of_item) {
+        if (runs > 0) {
+            if (n_blk + 1 < n_end) {
+                ++n_blk;
+                first_of_item = false;
+            } else {
+                if (n_end != 0) item += step;
+                if (item >= items) return false;
+                m_blk = item / runs;
+                run = item - m_blk * runs;
+                n_blk = (run * num_n) / runs;
+                n_end = ((run + 1) * num_n) / runs;
+                first_of_item = true;
+            }
+            last_of_item = n_blk + 1 == n_end;
+            return true;
+        }
+        if (n_end != 0) item += step;
+        n_end = 1;
+        if (item >= items) return false;
+        m_blk = item % num_m;
+        n_blk = item / num_m;
+        first_of_item = last_of_item = true;
+        return true;
+    }
+};
 
 // ------------------------------------------------------------------------------------------------ the kernel
 template <int BLOCK_N, int EPI, int KTOP>
@@ -397,7 +448,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = p.num_m_blocks * p.num_n_blocks;
     const int total_kb = p.k_blocks * p.passes;
 
     if (warp == 0 && lane == 0) {
@@ -427,9 +477,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile % p.num_m_blocks;
-                const int n_blk = tile / p.num_m_blocks;
+            TileIter it(p);
+            bool f, l;
+            while (it.next(f, l)) {
+                const int m_blk = it.m_blk, n_blk = it.n_blk;
                 for (int kk = 0; kk < total_kb; ++kk) {
                     const int pass = kk / p.k_blocks;
                     const int kb = kk - pass * p.k_blocks;
@@ -453,7 +504,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            TileIter it(p);
+            bool f, l;
+            while (it.next(f, l)) {
                 mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -483,9 +536,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         const int c0 = split * (CHUNKS / EPI_SPLIT), c1 = c0 + CHUNKS / EPI_SPLIT;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_blk = tile % p.num_m_blocks;
-            const int n_blk = tile / p.num_m_blocks;
+        TopkState<KTOP> tk;
+        DrawState sp;
+        TileIter it(p);
+        bool first, last;
+        while (it.next(first, last)) {
+            const int m_blk = it.m_blk, n_blk = it.n_blk;
             mbar_wait(tfull_bar + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -494,8 +550,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             if constexpr (EPI == EPI_STORE) epi_store<BLOCK_N>(taddr, row, n_base, c0, c1, p);
             else if constexpr (EPI == EPI_LSTM) epi_lstm<BLOCK_N>(taddr, row, n_base, c0, c1, p);
             else if constexpr (EPI == EPI_GLU) epi_glu<BLOCK_N>(taddr, row, n_base, c0, c1, p);
-            else if constexpr (EPI == EPI_TOPK) epi_topk<BLOCK_N, KTOP>(taddr, row, n_base, c0, c1, n_blk * EPI_SPLIT + split, p);
-            else epi_sample<BLOCK_N>(taddr, row, n_base, c0, c1, n_blk * EPI_SPLIT + split, p);
+            else {
+                // partial record slot: (run, column share) with runs, (vocabulary tile, column share) without
+                const int slot = (p.runs > 0 ? it.run : n_blk) * EPI_SPLIT + split;
+                if constexpr (EPI == EPI_TOPK) {
+                    if (first) tk.init();
+                    tk.tile(taddr, n_base, c0, c1, p);
+                    if (last) tk.flush(row, slot, p);
+                } else {
+                    if (first) sp.init(row, p);
+                    sp.tile(taddr, n_base, c0, c1, p);
+                    if (last) sp.flush(row, slot, p);
+                }
+            }
             __syncwarp();
             tc_fence_before();
             mbar_arrive(tempty_bar + 8 * acc);
