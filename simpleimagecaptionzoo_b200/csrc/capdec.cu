@@ -64,6 +64,7 @@ struct capdec_handle {
     const float* mask = nullptr;
     int64_t launches = 0;
     bool no_stream_attention = false;  // CAPDEC_NO_STREAM_ATTENTION=1: use the non-persistent attention kernel
+    int att_variant = 0;               // CAPDEC_ATT_VARIANT=1: FFMA streaming kernel instead of the MMA-fragment kernel
     bool prof = false;  // bracket every launch with CUDA events (capdec_profile)
     struct ProfRec {
         int cat;
@@ -473,6 +474,28 @@ int launch_butd_att_stream_t(capdec_handle* h, const StepCtx& c, const T* enc, c
     return CAPDEC_OK;
 }
 
+template <int KR>
+int launch_butd_att_mma(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
+    using C = AttMmaCfg<KR>;
+    static bool attr_set = false;
+    auto kern = butd_attention_mma_kernel<KR>;
+    const size_t smem = att_mma_smem_bytes(KR, C::STAGES, h->R, h->A, h->D);
+    if (!attr_set) {
+        CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_set = true;
+    }
+    if (smem > 220 * 1024) return fail(h, CAPDEC_ERR_INVALID, "attention ring does not fit shared memory");
+    const int cap = h->num_sms * C::CTAS_PER_SM;
+    const int grid = h->B < cap ? h->B : cap;
+    prof_begin(h, CAPDEC_CAT_ATTENTION, 0.0, st);
+    kern<<<grid, C::THREADS, smem, st>>>(h->enc16.p, h->feats16.p, h->dec_ctx, h->w_aff, h->b_aff, h->B, h->R, h->A, h->D, c.K,
+                                         h->XB.p, h->XB.ld);
+    prof_end(h, st);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    return CAPDEC_OK;
+}
+
 // fp16 mode reads the fp16 copies (projected features written by the projection GEMM, raw features converted for
 // it); the fp32-grade mode reads the caller's fp32 features and the fp32 projection.
 template <int KR>
@@ -483,6 +506,8 @@ int launch_butd_att(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
         if (stream_ok) return launch_butd_att_stream_t<KR, float>(h, c, h->enc_ctx, h->feats, st);
         return launch_butd_att_t<KR, float>(h, c, h->enc_ctx, h->feats, h->D, st);
     }
+    if (stream_ok && h->feats16.ld == h->D && h->A % 16 == 0 && h->D % 32 == 0 && h->att_variant == 0)
+        return launch_butd_att_mma<KR>(h, c, st);
     if (stream_ok && h->feats16.ld == h->D) return launch_butd_att_stream_t<KR, __half>(h, c, h->enc16.p, h->feats16.p, st);
     return launch_butd_att_t<KR, __half>(h, c, h->enc16.p, h->feats16.p, h->feats16.ld, st);
 }
@@ -768,6 +793,8 @@ static int create_impl(capdec_handle* h) {
     {
         const char* e = getenv("CAPDEC_NO_STREAM_ATTENTION");
         h->no_stream_attention = e && e[0] == '1';
+        const char* v = getenv("CAPDEC_ATT_VARIANT");
+        h->att_variant = v ? atoi(v) : 0;
     }
     h->Mmax = h->Bmax * h->Kmax;
     h->n_tiles_v = ((V + BN - 1) / BN) * EPI_SPLIT;  // partial slots per row: (N tile, column share)

@@ -557,6 +557,255 @@ butd_attention_stream_kernel(const T* __restrict__ enc_ctx, const T* __restrict_
     }
 }
 
+// ------------------------------------------------------------------------------------------------ fp16 fragment form
+// The fp16-mode attention kernel of the decode loop.  Same persistent bulk-copy ring as above, but the arithmetic
+// is done on MMA fragments so that the kernel is bound by HBM, not by instruction issue (the FFMA form executes
+// ~40 k warp instructions per image, this one ~10 k):
+//   phase 1  e[k,r] = sum_a w[a]*relu(enc[r,a] + dec[k,a]): ldmatrix loads a 16-region x 16-column tile as an
+//            m16n8k16 A fragment, the add + ReLU run as packed half2 ops on the fragment, and the dot product with
+//            w is one MMA whose B fragment holds w in column 0 -- the reduction over a happens inside the MMA.
+//   phase 3  ctx[k,d] = sum_r alpha[k,r]*feats[r,d]: feats^T tiles (ldmatrix.trans) are the A operand of m16n8k8,
+//            alpha (beam = n) the B operand.
+// Rows are copied into shared memory with a 16-byte pad so that ldmatrix is bank-conflict free.
+// Requires A % 16 == 0, A <= 1024, D % 32 == 0, D <= 2048, K <= 8.
+struct AttMmaShape {
+    int row1, row3;        // padded smem row bytes of a projected / raw feature row
+    int stage_bytes;       // max(16*row1, 8*row3)
+    int zrow_bytes;
+    int rp;                // R rounded up to 16
+};
+__host__ __device__ inline AttMmaShape att_mma_shape(int R, int A, int D) {
+    AttMmaShape s;
+    s.row1 = A * 2 + 16;
+    s.row3 = D * 2 + 16;
+    s.stage_bytes = 16 * s.row1 > 8 * s.row3 ? 16 * s.row1 : 8 * s.row3;
+    s.zrow_bytes = s.row1 > s.row3 ? s.row1 : s.row3;
+    s.rp = (R + 15) / 16 * 16;
+    return s;
+}
+template <int KR> struct AttMmaCfg {
+    static constexpr int CTAS_PER_SM = KR <= 3 ? 2 : 1;
+    static constexpr int STAGES = KR <= 3 ? 2 : 4;
+    static constexpr int THREADS = 288;
+};
+__host__ __device__ inline size_t att_mma_smem_bytes(int KR, int stages, int R, int A, int D) {
+    const AttMmaShape s = att_mma_shape(R, A, D);
+    return static_cast<size_t>(stages) * s.stage_bytes + s.zrow_bytes + 2 * stages * 8 + static_cast<size_t>(KR) * (A + 8) * 2 +
+           static_cast<size_t>(KR) * s.rp * 4 + 2 * 8 * KR * 16 * 4 + 8 * (s.rp + 8) * 2 + static_cast<size_t>(A) * 2 + 128;
+}
+
+__device__ __forceinline__ uint32_t relu_add_h2(uint32_t x, uint32_t d) {
+    const __half2 r = __hmax2(__hadd2(*reinterpret_cast<const __half2*>(&x), *reinterpret_cast<const __half2*>(&d)),
+                              __float2half2_rn(0.f));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    const __half2 r = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+template <int KR>
+__global__ void __launch_bounds__(288, AttMmaCfg<KR>::CTAS_PER_SM)
+butd_attention_mma_kernel(const __half* __restrict__ enc16, const __half* __restrict__ feats16, const float* __restrict__ dec_ctx,
+                          const float* __restrict__ w_aff, float b_aff, int B, int R, int A, int D, int K,
+                          __half* __restrict__ ctx16, int ld16) {
+    constexpr int STAGES = AttMmaCfg<KR>::STAGES;
+    const AttMmaShape sh = att_mma_shape(R, A, D);
+    extern __shared__ uint8_t att_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(att_smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+    uint8_t* zrow = smem + STAGES * sh.stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(zrow + sh.zrow_bytes);
+    __half* s_dec16 = reinterpret_cast<__half*>(bars + 2 * STAGES);          // [KR][A+8]
+    float* s_e = reinterpret_cast<float*>(s_dec16 + KR * (A + 8));           // [KR][rp]
+    float* s_part = s_e + KR * sh.rp;                                        // [2][8][KR][16]
+    __half* s_alpha = reinterpret_cast<__half*>(s_part + 2 * 8 * KR * 16);   // [8][rp+8]
+    __half* s_w16 = s_alpha + 8 * (sh.rp + 8);                               // [A]
+    const uint32_t full_bar = smem_u32(bars), empty_bar = smem_u32(bars + STAGES);
+    const uint32_t ring = smem_u32(smem), zrow_a = smem_u32(zrow);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_chunks1 = (R + 15) / 16, n_chunks3 = (R + 7) / 8;
+
+    for (int i = threadIdx.x; i < sh.zrow_bytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(zrow)[i] = 0u;
+    for (int i = threadIdx.x; i < 8 * (sh.rp + 8) / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(s_alpha)[i] = 0u;
+    for (int i = threadIdx.x; i < A; i += blockDim.x) s_w16[i] = __float2half_rn(w_aff[i]);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar + 8 * s, 1);
+            mbar_init(empty_bar + 8 * s, 8);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ===================== producer: row-wise bulk copies into padded smem rows =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int img = blockIdx.x; img < B; img += gridDim.x) {
+                const __half* enc = enc16 + static_cast<size_t>(img) * R * A;
+                const __half* f = feats16 + static_cast<size_t>(img) * R * D;
+                for (int c = 0; c < n_chunks1 + n_chunks3; ++c) {
+                    const bool p1 = c < n_chunks1;
+                    const int r0 = p1 ? c * 16 : (c - n_chunks1) * 8;
+                    const int nr = min(p1 ? 16 : 8, R - r0);
+                    const uint32_t row_bytes = static_cast<uint32_t>(p1 ? A : D) * 2u;
+                    const int row_pitch = p1 ? sh.row1 : sh.row3;
+                    const __half* src = p1 ? enc + static_cast<size_t>(r0) * A : f + static_cast<size_t>(r0) * D;
+                    mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                    mbar_arrive_expect_tx(full_bar + 8 * stage, row_bytes * nr);
+                    const uint32_t dst = ring + stage * sh.stage_bytes;
+                    for (int i = 0; i < nr; ++i)
+                        bulk_load_1d(dst + i * row_pitch, src + static_cast<size_t>(i) * (p1 ? A : D), row_bytes, full_bar + 8 * stage);
+                    if (++stage == STAGES) stage = 0, phase ^= 1;
+                }
+            }
+        }
+        return;
+    }
+
+    // ===================== consumers (256 threads, 8 warps) =====================
+    const int tid = threadIdx.x - 32, cw = warp - 1;
+    const int g = lane >> 2, t = lane & 3;
+    const int AT = A >> 4, DT = D >> 4;
+    const uint32_t wmask = g == 0 ? 0xFFFFFFFFu : 0u;  // B fragment of the w-dot: w in output column 0 only
+    float4 dn[KR];  // this thread's 4 columns of the next image's dec_att rows
+    auto load_dec = [&](int img) {
+#pragma unroll
+        for (int k = 0; k < KR; ++k) {
+            dn[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tid * 4 < A && k < K && img < B)
+                dn[k] = __ldg(reinterpret_cast<const float4*>(dec_ctx + (static_cast<size_t>(img) * K + k) * A) + tid);
+        }
+    };
+    load_dec(blockIdx.x);
+    int stage = 0;
+    uint32_t phase = 0;
+    int flip = 0;
+    for (int img = blockIdx.x; img < B; img += gridDim.x) {
+        if (tid * 4 < A) {
+#pragma unroll
+            for (int k = 0; k < KR; ++k) {
+                uint2 v;
+                v.x = pack_h2(dn[k].x, dn[k].y);
+                v.y = pack_h2(dn[k].z, dn[k].w);
+                *reinterpret_cast<uint2*>(s_dec16 + k * (A + 8) + tid * 4) = v;
+            }
+        }
+        named_bar_sync(1, 256);
+        // ---------------- phase 1: scores
+        for (int c = 0; c < n_chunks1; ++c) {
+            float acc[KR][4];
+#pragma unroll
+            for (int k = 0; k < KR; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f;
+            mbar_wait(full_bar + 8 * stage, phase);
+            const int rl = (lane & 7) + ((lane >> 3) & 1) * 8;
+            const uint32_t rowaddr = (c * 16 + rl < R) ? ring + stage * sh.stage_bytes + rl * sh.row1 : zrow_a;
+            const int colsel = (lane >> 4) * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int at = cw + 8 * j;
+                if (at < AT) {
+                    const int a0 = at * 16;
+                    uint32_t x[4];
+                    ldmatrix_x4(x, rowaddr + (a0 + colsel) * 2);
+                    const uint32_t wb0 = *reinterpret_cast<const uint32_t*>(s_w16 + a0 + 2 * t) & wmask;
+                    const uint32_t wb1 = *reinterpret_cast<const uint32_t*>(s_w16 + a0 + 8 + 2 * t) & wmask;
+#pragma unroll
+                    for (int k = 0; k < KR; ++k) {
+                        if (k < K) {
+                            const uint32_t dlo = *reinterpret_cast<const uint32_t*>(s_dec16 + k * (A + 8) + a0 + 2 * t);
+                            const uint32_t dhi = *reinterpret_cast<const uint32_t*>(s_dec16 + k * (A + 8) + a0 + 8 + 2 * t);
+                            mma_m16n8k16_f16(acc[k], relu_add_h2(x[0], dlo), relu_add_h2(x[1], dlo), relu_add_h2(x[2], dhi),
+                                             relu_add_h2(x[3], dhi), wb0, wb1);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar + 8 * stage);
+            if (++stage == STAGES) stage = 0, phase ^= 1;
+            float* part = s_part + flip * 8 * KR * 16;
+            flip ^= 1;
+            if (t == 0) {
+#pragma unroll
+                for (int k = 0; k < KR; ++k) {
+                    part[(cw * KR + k) * 16 + g] = acc[k][0];
+                    part[(cw * KR + k) * 16 + g + 8] = acc[k][2];
+                }
+            }
+            named_bar_sync(1, 256);
+            if (tid < KR * 16) {
+                const int k = tid >> 4, i = tid & 15;
+                float sum = 0.f;
+#pragma unroll
+                for (int w8 = 0; w8 < 8; ++w8) sum += part[(w8 * KR + k) * 16 + i];
+                const int r = c * 16 + i;
+                if (r < R && k < K) s_e[k * sh.rp + r] = sum + b_aff;
+            }
+        }
+        load_dec(img + gridDim.x);
+        named_bar_sync(1, 256);
+        // ---------------- phase 2: softmax over regions -> fp16 alpha rows (B operand of phase 3)
+        for (int k = cw; k < K; k += 8) {
+            float m = -INFINITY;
+            for (int r = lane; r < R; r += 32) m = fmaxf(m, s_e[k * sh.rp + r]);
+            m = warp_max(m);
+            float s = 0.f;
+            for (int r = lane; r < R; r += 32) {
+                const float ex = expf(s_e[k * sh.rp + r] - m);
+                s_e[k * sh.rp + r] = ex;
+                s += ex;
+            }
+            s = warp_sum(s);
+            for (int r = lane; r < R; r += 32) s_alpha[k * (sh.rp + 8) + r] = __float2half_rn(s_e[k * sh.rp + r] / s);
+        }
+        named_bar_sync(1, 256);
+        // ---------------- phase 3: ctx = alpha * feats
+        float acc3[16][4];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc3[j][0] = acc3[j][1] = acc3[j][2] = acc3[j][3] = 0.f;
+        for (int c = 0; c < n_chunks3; ++c) {
+            mbar_wait(full_bar + 8 * stage, phase);
+            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(s_alpha + g * (sh.rp + 8) + c * 8 + 2 * t);
+            const int rl = lane & 7;
+            const uint32_t rowaddr = (c * 8 + rl < R) ? ring + stage * sh.stage_bytes + rl * sh.row3 : zrow_a;
+            const int msel = lane >> 3;
+#pragma unroll
+            for (int jp = 0; jp < 8; ++jp) {
+                const int dt0 = cw * 16 + 2 * jp;
+                if (dt0 < DT) {
+                    uint32_t m4[4];
+                    ldmatrix_x4_trans(m4, rowaddr + ((dt0 + (msel >> 1)) * 16 + (msel & 1) * 8) * 2);
+                    mma_m16n8k8_f16(acc3[2 * jp], m4[0], m4[1], b0);
+                    mma_m16n8k8_f16(acc3[2 * jp + 1], m4[2], m4[3], b0);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar + 8 * stage);
+            if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int dt = cw * 16 + j;
+            if (dt < DT) {
+                const int d = dt * 16 + g;
+                if (2 * t < K) {
+                    __half* o = ctx16 + (static_cast<size_t>(img) * K + 2 * t) * ld16 + d;
+                    o[0] = __float2half_rn(acc3[j][0]);
+                    o[8] = __float2half_rn(acc3[j][2]);
+                }
+                if (2 * t + 1 < K) {
+                    __half* o = ctx16 + (static_cast<size_t>(img) * K + 2 * t + 1) * ld16 + d;
+                    o[0] = __float2half_rn(acc3[j][1]);
+                    o[8] = __float2half_rn(acc3[j][3]);
+                }
+            }
+        }
+        named_bar_sync(1, 256);  // s_dec16 / s_e / s_alpha are rewritten by the next image
+    }
+}
+
 // ================================================================================================ AoA pieces
 // LayerNorm of the reference (AoA_Model.py:14-25): gain*(x-mean)/(std_unbiased + eps) + bias.  One warp per row;
 // writes the fp16 operand (query for linear_Q and for the AoA gate GEMM).
