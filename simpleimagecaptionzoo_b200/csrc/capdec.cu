@@ -152,10 +152,11 @@ int dalloc(capdec_handle* h, T** out, size_t n, bool zero = true) {
     return CAPDEC_OK;
 }
 
-int alloc_act(capdec_handle* h, Act16* a, int rows, int cols) {
+// pad > 0 (fp16 mode only): extra halves per row, so that rows bulk-copied to shared memory are bank-conflict free
+int alloc_act(capdec_handle* h, Act16* a, int rows, int cols, int pad = 0) {
     a->rows = rows;
     a->cols = cols;
-    a->ld = cols * (h->split ? 2 : 1);
+    a->ld = cols * (h->split ? 2 : 1) + (h->split ? 0 : pad);
     a->lo = h->split ? cols : 0;
     return dalloc(h, &a->p, static_cast<size_t>(rows) * a->ld);
 }
@@ -433,7 +434,7 @@ int run_logits(capdec_handle* h, const Act16& a, const StepCtx& c, cudaStream_t 
 }
 
 template <int KR, typename T>
-int launch_butd_att_t(capdec_handle* h, const StepCtx& c, const T* enc, const T* feats, int feats_ld, cudaStream_t st) {
+int launch_butd_att_t(capdec_handle* h, const StepCtx& c, const T* enc, int enc_ld, const T* feats, int feats_ld, cudaStream_t st) {
     static bool attr_set = false;
     auto kern = butd_attention_kernel<KR, T>;
     const size_t smem = (static_cast<size_t>(KR) * h->R + 2 * 8 * AttCfg<KR>::NP) * sizeof(float);
@@ -443,7 +444,7 @@ int launch_butd_att_t(capdec_handle* h, const StepCtx& c, const T* enc, const T*
     }
     if (smem > 160 * 1024) return fail(h, CAPDEC_ERR_INVALID, "attention tile does not fit shared memory");
     prof_begin(h, CAPDEC_CAT_ATTENTION, 0.0, st);
-    kern<<<h->B, 256, smem, st>>>(enc, feats, feats_ld, h->dec_ctx, h->w_aff, h->b_aff, h->R, h->A, h->D, c.K, h->XB.p, h->XB.ld,
+    kern<<<h->B, 256, smem, st>>>(enc, enc_ld, feats, feats_ld, h->dec_ctx, h->w_aff, h->b_aff, h->R, h->A, h->D, c.K, h->XB.p, h->XB.ld,
                                   h->XB.lo, nullptr);
     prof_end(h, st);
     CK(h, cudaGetLastError());
@@ -474,26 +475,34 @@ int launch_butd_att_stream_t(capdec_handle* h, const StepCtx& c, const T* enc, c
     return CAPDEC_OK;
 }
 
-template <int KR>
-int launch_butd_att_mma(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
-    using C = AttMmaCfg<KR>;
+template <int KR, int CTAS>
+int launch_butd_att_mma_t(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
+    using C = AttMmaCfg<KR, CTAS>;
     static bool attr_set = false;
-    auto kern = butd_attention_mma_kernel<KR>;
-    const size_t smem = att_mma_smem_bytes(KR, C::STAGES, h->R, h->A, h->D);
+    auto kern = butd_attention_mma_kernel<KR, CTAS>;
+    const size_t smem = att_mma_smem_bytes(KR, C::STAGES, h->R, h->A, h->enc16.ld, h->feats16.ld);
     if (!attr_set) {
-        CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    if (smem > 220 * 1024) return fail(h, CAPDEC_ERR_INVALID, "attention ring does not fit shared memory");
+    if (smem > 227 * 1024) return fail(h, CAPDEC_ERR_INVALID, "attention ring does not fit shared memory");
     const int cap = h->num_sms * C::CTAS_PER_SM;
     const int grid = h->B < cap ? h->B : cap;
     prof_begin(h, CAPDEC_CAT_ATTENTION, 0.0, st);
-    kern<<<grid, C::THREADS, smem, st>>>(h->enc16.p, h->feats16.p, h->dec_ctx, h->w_aff, h->b_aff, h->B, h->R, h->A, h->D, c.K,
-                                         h->XB.p, h->XB.ld);
+    kern<<<grid, C::THREADS, smem, st>>>(h->enc16.p, h->enc16.ld, h->feats16.p, h->feats16.ld, static_cast<size_t>(h->B) * h->R,
+                                         h->dec_ctx, h->w_aff, h->b_aff, h->B, h->R, h->A, h->D, c.K, h->XB.p, h->XB.ld);
     prof_end(h, st);
     CK(h, cudaGetLastError());
     h->launches++;
     return CAPDEC_OK;
+}
+template <int KR>
+int launch_butd_att_mma(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
+    // two CTAs per SM (3-stage rings) when the per-CTA state is small enough, else one CTA with a deep ring
+    if (KR <= 3 && h->att_variant != 2 &&
+        2 * (att_mma_smem_bytes(KR, AttMmaCfg<KR, 2>::STAGES, h->R, h->A, h->enc16.ld, h->feats16.ld) + 1024) <= 228 * 1024)
+        return launch_butd_att_mma_t<KR, 2>(h, c, st);
+    return launch_butd_att_mma_t<KR, 1>(h, c, st);
 }
 
 // fp16 mode reads the fp16 copies (projected features written by the projection GEMM, raw features converted for
@@ -504,12 +513,10 @@ int launch_butd_att(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
     const bool stream_ok = h->A <= 1024 && h->D <= 2048 && !h->no_stream_attention;
     if (h->split) {
         if (stream_ok) return launch_butd_att_stream_t<KR, float>(h, c, h->enc_ctx, h->feats, st);
-        return launch_butd_att_t<KR, float>(h, c, h->enc_ctx, h->feats, h->D, st);
+        return launch_butd_att_t<KR, float>(h, c, h->enc_ctx, h->A, h->feats, h->D, st);
     }
-    if (stream_ok && h->feats16.ld == h->D && h->A % 16 == 0 && h->D % 32 == 0 && h->att_variant == 0)
-        return launch_butd_att_mma<KR>(h, c, st);
-    if (stream_ok && h->feats16.ld == h->D) return launch_butd_att_stream_t<KR, __half>(h, c, h->enc16.p, h->feats16.p, st);
-    return launch_butd_att_t<KR, __half>(h, c, h->enc16.p, h->feats16.p, h->feats16.ld, st);
+    if (stream_ok && h->A % 16 == 0 && h->D % 32 == 0 && h->att_variant != 1) return launch_butd_att_mma<KR>(h, c, st);
+    return launch_butd_att_t<KR, __half>(h, c, h->enc16.p, h->enc16.ld, h->feats16.p, h->feats16.ld, st);
 }
 
 template <int KR>
@@ -832,10 +839,10 @@ static int create_impl(capdec_handle* h) {
         CKS(h, dalloc(h, &h->b_aux1, A));
         CKS(h, dalloc(h, &h->b_aux2, A));
         CKS(h, dalloc(h, &h->w_aff, A));
-        CKS(h, alloc_act(h, &h->feats16, static_cast<int>(BR), D));
+        CKS(h, alloc_act(h, &h->feats16, static_cast<int>(BR), D, 8));
         CKS(h, alloc_act(h, &h->mean16, h->Bmax, D));
         if (h->split) CKS(h, dalloc(h, &h->enc_ctx, BR * A));
-        else CKS(h, alloc_act(h, &h->enc16, static_cast<int>(BR), A));
+        else CKS(h, alloc_act(h, &h->enc16, static_cast<int>(BR), A, 8));
         CKS(h, dalloc(h, &h->G0, static_cast<size_t>(h->Bmax) * 4 * H));
         CKS(h, alloc_act(h, &h->XA, M, H + E + H));
         CKS(h, alloc_act(h, &h->XB, M, D + H + H));

@@ -224,7 +224,7 @@ template <int KR> struct AttCfg {
 // per group; partial dot products are reduced with a transposing butterfly + one smem hop across the 4 warps of a
 // parity.  A, D multiples of 8.
 template <int KR, typename T>
-__global__ void __launch_bounds__(256) butd_attention_kernel(const T* __restrict__ enc_ctx, const T* __restrict__ feats,
+__global__ void __launch_bounds__(256) butd_attention_kernel(const T* __restrict__ enc_ctx, int enc_ld, const T* __restrict__ feats,
                                                              int feats_ld, const float* __restrict__ dec_ctx,
                                                              const float* __restrict__ w_aff, float b_aff, int R, int A, int D,
                                                              int K, __half* __restrict__ ctx16, int ld16, int lo16,
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256) butd_attention_kernel(const T* __restrict
     const int tcol = tid & 127;
 
     // ---------------- phase 1: attention scores
-    const T* enc = enc_ctx + static_cast<size_t>(img) * R * A;
+    const T* enc = enc_ctx + static_cast<size_t>(img) * R * enc_ld;
     const float* dec = dec_ctx + static_cast<size_t>(img) * K * A;
     const int n_groups = (R + 2 * GR - 1) / (2 * GR);
     for (int g = 0; g < n_groups; ++g) {
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(256) butd_attention_kernel(const T* __restrict
 #pragma unroll
             for (int i = 0; i < GR; ++i) {
                 const int r = g * 2 * GR + parity + 2 * i;
-                if (r < R) raw[i].load(enc + static_cast<size_t>(r) * A + a0);
+                if (r < R) raw[i].load(enc + static_cast<size_t>(r) * enc_ld + a0);
                 else raw[i].zero();
             }
             float w[8];
@@ -566,31 +566,30 @@ butd_attention_stream_kernel(const T* __restrict__ enc_ctx, const T* __restrict_
 //            w is one MMA whose B fragment holds w in column 0 -- the reduction over a happens inside the MMA.
 //   phase 3  ctx[k,d] = sum_r alpha[k,r]*feats[r,d]: feats^T tiles (ldmatrix.trans) are the A operand of m16n8k8,
 //            alpha (beam = n) the B operand.
-// Rows are copied into shared memory with a 16-byte pad so that ldmatrix is bank-conflict free.
+// The fp16 copies of the projected / raw features are stored in HBM with a 16-byte row pad (ld = cols + 8), so one
+// contiguous bulk copy per chunk lands rows in shared memory at a pitch that makes ldmatrix bank-conflict free.
 // Requires A % 16 == 0, A <= 1024, D % 32 == 0, D <= 2048, K <= 8.
 struct AttMmaShape {
-    int row1, row3;        // padded smem row bytes of a projected / raw feature row
+    int row1, row3;        // row pitch in bytes of a projected / raw feature row (global == smem: rows are padded by 16 B)
     int stage_bytes;       // max(16*row1, 8*row3)
-    int zrow_bytes;
     int rp;                // R rounded up to 16
 };
-__host__ __device__ inline AttMmaShape att_mma_shape(int R, int A, int D) {
+__host__ __device__ inline AttMmaShape att_mma_shape(int R, int ld_enc, int ld_feats) {
     AttMmaShape s;
-    s.row1 = A * 2 + 16;
-    s.row3 = D * 2 + 16;
+    s.row1 = ld_enc * 2;
+    s.row3 = ld_feats * 2;
     s.stage_bytes = 16 * s.row1 > 8 * s.row3 ? 16 * s.row1 : 8 * s.row3;
-    s.zrow_bytes = s.row1 > s.row3 ? s.row1 : s.row3;
     s.rp = (R + 15) / 16 * 16;
     return s;
 }
-template <int KR> struct AttMmaCfg {
-    static constexpr int CTAS_PER_SM = KR <= 3 ? 2 : 1;
-    static constexpr int STAGES = KR <= 3 ? 2 : 4;
+template <int KR, int CTAS> struct AttMmaCfg {
+    static constexpr int CTAS_PER_SM = CTAS;
+    static constexpr int STAGES = CTAS == 2 ? 3 : (KR <= 5 ? 6 : 5);
     static constexpr int THREADS = 288;
 };
-__host__ __device__ inline size_t att_mma_smem_bytes(int KR, int stages, int R, int A, int D) {
-    const AttMmaShape s = att_mma_shape(R, A, D);
-    return static_cast<size_t>(stages) * s.stage_bytes + s.zrow_bytes + 2 * stages * 8 + static_cast<size_t>(KR) * (A + 8) * 2 +
+__host__ __device__ inline size_t att_mma_smem_bytes(int KR, int stages, int R, int A, int ld_enc, int ld_feats) {
+    const AttMmaShape s = att_mma_shape(R, ld_enc, ld_feats);
+    return static_cast<size_t>(stages) * s.stage_bytes + 2 * stages * 8 + static_cast<size_t>(KR) * (A + 8) * 2 +
            static_cast<size_t>(KR) * s.rp * 4 + 2 * 8 * KR * 16 * 4 + 8 * (s.rp + 8) * 2 + static_cast<size_t>(A) * 2 + 128;
 }
 
@@ -604,28 +603,29 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     return *reinterpret_cast<const uint32_t*>(&r);
 }
 
-template <int KR>
-__global__ void __launch_bounds__(288, AttMmaCfg<KR>::CTAS_PER_SM)
-butd_attention_mma_kernel(const __half* __restrict__ enc16, const __half* __restrict__ feats16, const float* __restrict__ dec_ctx,
-                          const float* __restrict__ w_aff, float b_aff, int B, int R, int A, int D, int K,
-                          __half* __restrict__ ctx16, int ld16) {
-    constexpr int STAGES = AttMmaCfg<KR>::STAGES;
-    const AttMmaShape sh = att_mma_shape(R, A, D);
+template <int KR, int CTAS>
+__global__ void __launch_bounds__(288, CTAS)
+butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __half* __restrict__ feats16, int ld_feats,
+                          size_t total_rows, const float* __restrict__ dec_ctx, const float* __restrict__ w_aff, float b_aff, int B,
+                          int R, int A, int D, int K, __half* __restrict__ ctx16, int ld16) {
+    constexpr int STAGES = AttMmaCfg<KR, CTAS>::STAGES;
+    const AttMmaShape sh = att_mma_shape(R, ld_enc, ld_feats);
     extern __shared__ uint8_t att_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(att_smem_raw) + 127) & ~static_cast<uintptr_t>(127));
-    uint8_t* zrow = smem + STAGES * sh.stage_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(zrow + sh.zrow_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * sh.stage_bytes);
     __half* s_dec16 = reinterpret_cast<__half*>(bars + 2 * STAGES);          // [KR][A+8]
     float* s_e = reinterpret_cast<float*>(s_dec16 + KR * (A + 8));           // [KR][rp]
     float* s_part = s_e + KR * sh.rp;                                        // [2][8][KR][16]
     __half* s_alpha = reinterpret_cast<__half*>(s_part + 2 * 8 * KR * 16);   // [8][rp+8]
     __half* s_w16 = s_alpha + 8 * (sh.rp + 8);                               // [A]
     const uint32_t full_bar = smem_u32(bars), empty_bar = smem_u32(bars + STAGES);
-    const uint32_t ring = smem_u32(smem), zrow_a = smem_u32(zrow);
+    const uint32_t ring = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_chunks1 = (R + 15) / 16, n_chunks3 = (R + 7) / 8;
 
-    for (int i = threadIdx.x; i < sh.zrow_bytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(zrow)[i] = 0u;
+    // tail rows of a chunk (beyond the image's R regions) hold whatever followed in HBM / an earlier chunk: finite
+    // fp16 data that is multiplied by alpha = 0 or ignored -- but never uninitialised bits
+    for (int i = threadIdx.x; i < STAGES * sh.stage_bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     for (int i = threadIdx.x; i < 8 * (sh.rp + 8) / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(s_alpha)[i] = 0u;
     for (int i = threadIdx.x; i < A; i += blockDim.x) s_w16[i] = __float2half_rn(w_aff[i]);
     if (threadIdx.x == 0) {
@@ -635,28 +635,25 @@ butd_attention_mma_kernel(const __half* __restrict__ enc16, const __half* __rest
         }
         fence_barrier_init();
     }
+    fence_proxy_async_smem();  // the zero fill above (generic proxy) is ordered before the bulk copies (async proxy)
     __syncthreads();
 
     if (warp == 0) {
-        // ===================== producer: row-wise bulk copies into padded smem rows =====================
+        // ===================== producer: ONE contiguous bulk copy per chunk (16 / 8 padded rows) =====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
             for (int img = blockIdx.x; img < B; img += gridDim.x) {
-                const __half* enc = enc16 + static_cast<size_t>(img) * R * A;
-                const __half* f = feats16 + static_cast<size_t>(img) * R * D;
                 for (int c = 0; c < n_chunks1 + n_chunks3; ++c) {
                     const bool p1 = c < n_chunks1;
-                    const int r0 = p1 ? c * 16 : (c - n_chunks1) * 8;
-                    const int nr = min(p1 ? 16 : 8, R - r0);
-                    const uint32_t row_bytes = static_cast<uint32_t>(p1 ? A : D) * 2u;
-                    const int row_pitch = p1 ? sh.row1 : sh.row3;
-                    const __half* src = p1 ? enc + static_cast<size_t>(r0) * A : f + static_cast<size_t>(r0) * D;
+                    const size_t row0 = static_cast<size_t>(img) * R + (p1 ? c * 16 : (c - n_chunks1) * 8);
+                    size_t nr = p1 ? 16 : 8;
+                    if (row0 + nr > total_rows) nr = total_rows - row0;  // never read past the last prepared row
+                    const uint32_t bytes = static_cast<uint32_t>(nr) * (p1 ? sh.row1 : sh.row3);
+                    const __half* src = p1 ? enc16 + row0 * ld_enc : feats16 + row0 * ld_feats;
                     mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-                    mbar_arrive_expect_tx(full_bar + 8 * stage, row_bytes * nr);
-                    const uint32_t dst = ring + stage * sh.stage_bytes;
-                    for (int i = 0; i < nr; ++i)
-                        bulk_load_1d(dst + i * row_pitch, src + static_cast<size_t>(i) * (p1 ? A : D), row_bytes, full_bar + 8 * stage);
+                    mbar_arrive_expect_tx(full_bar + 8 * stage, bytes);
+                    bulk_load_1d(ring + stage * sh.stage_bytes, src, bytes, full_bar + 8 * stage);
                     if (++stage == STAGES) stage = 0, phase ^= 1;
                 }
             }
@@ -700,7 +697,7 @@ butd_attention_mma_kernel(const __half* __restrict__ enc16, const __half* __rest
             for (int k = 0; k < KR; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f;
             mbar_wait(full_bar + 8 * stage, phase);
             const int rl = (lane & 7) + ((lane >> 3) & 1) * 8;
-            const uint32_t rowaddr = (c * 16 + rl < R) ? ring + stage * sh.stage_bytes + rl * sh.row1 : zrow_a;
+            const uint32_t rowaddr = ring + stage * sh.stage_bytes + rl * sh.row1;
             const int colsel = (lane >> 4) * 8;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -769,7 +766,7 @@ butd_attention_mma_kernel(const __half* __restrict__ enc16, const __half* __rest
             mbar_wait(full_bar + 8 * stage, phase);
             const uint32_t b0 = *reinterpret_cast<const uint32_t*>(s_alpha + g * (sh.rp + 8) + c * 8 + 2 * t);
             const int rl = lane & 7;
-            const uint32_t rowaddr = (c * 8 + rl < R) ? ring + stage * sh.stage_bytes + rl * sh.row3 : zrow_a;
+            const uint32_t rowaddr = ring + stage * sh.stage_bytes + rl * sh.row3;
             const int msel = lane >> 3;
 #pragma unroll
             for (int jp = 0; jp < 8; ++jp) {
