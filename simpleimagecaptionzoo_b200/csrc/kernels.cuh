@@ -603,6 +603,19 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     return *reinterpret_cast<const uint32_t*>(&r);
 }
 
+__device__ __forceinline__ uint32_t lds_b32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// plain spin on an mbarrier phase (try_wait suspends in hardware); traps instead of hanging after ~2^26 failed tries
+__device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
+    int tries = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++tries > (1 << 26)) __trap();
+    }
+}
+
 template <int KR, int CTAS>
 __global__ void __launch_bounds__(288, CTAS)
 butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __half* __restrict__ feats16, int ld_feats,
@@ -610,8 +623,8 @@ butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __
                           int R, int A, int D, int K, __half* __restrict__ ctx16, int ld16) {
     constexpr int STAGES = AttMmaCfg<KR, CTAS>::STAGES;
     const AttMmaShape sh = att_mma_shape(R, ld_enc, ld_feats);
-    extern __shared__ uint8_t att_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(att_smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+    extern __shared__ __align__(128) uint8_t att_smem[];
+    uint8_t* smem = att_smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * sh.stage_bytes);
     __half* s_dec16 = reinterpret_cast<__half*>(bars + 2 * STAGES);          // [KR][A+8]
     float* s_e = reinterpret_cast<float*>(s_dec16 + KR * (A + 8));           // [KR][rp]
@@ -651,7 +664,7 @@ butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __
                     if (row0 + nr > total_rows) nr = total_rows - row0;  // never read past the last prepared row
                     const uint32_t bytes = static_cast<uint32_t>(nr) * (p1 ? sh.row1 : sh.row3);
                     const __half* src = p1 ? enc16 + row0 * ld_enc : feats16 + row0 * ld_feats;
-                    mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                    mbar_wait_lean(empty_bar + 8 * stage, phase ^ 1);
                     mbar_arrive_expect_tx(full_bar + 8 * stage, bytes);
                     bulk_load_1d(ring + stage * sh.stage_bytes, src, bytes, full_bar + 8 * stage);
                     if (++stage == STAGES) stage = 0, phase ^= 1;
@@ -664,14 +677,24 @@ butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __
     // ===================== consumers (256 threads, 8 warps) =====================
     const int tid = threadIdx.x - 32, cw = warp - 1;
     const int g = lane >> 2, t = lane & 3;
-    const int AT = A >> 4, DT = D >> 4;
     const uint32_t wmask = g == 0 ? 0xFFFFFFFFu : 0u;  // B fragment of the w-dot: w in output column 0 only
+    // loop-invariant per-thread shared addresses (bytes).  Warp cw owns column tiles cw, cw+8, ... (phase 1) and the
+    // 16 d-tiles [16cw, 16cw+16) (phase 3); tile j of a warp is a compile-time offset from these bases.
+    const int nj1 = max(0, min(8, ((A >> 4) - cw + 7) >> 3));           // valid phase-1 tiles of this warp
+    const int nj3 = max(0, min(16, (D >> 4) - cw * 16));                // valid phase-3 tiles of this warp
+    const uint32_t w_addr = smem_u32(s_w16) + (cw * 16 + 2 * t) * 2;    // + 256*j (+16 for the upper 8 columns)
+    const uint32_t dec_addr = smem_u32(s_dec16) + (cw * 16 + 2 * t) * 2;  // + k*(A+8)*2 + 256*j (+16)
+    const uint32_t dec_pitch = (A + 8) * 2;
+    const uint32_t ld1_off = ((lane & 7) + ((lane >> 3) & 1) * 8) * sh.row1 + (cw * 16 + (lane >> 4) * 8) * 2;  // + 256*j
+    const uint32_t ld3_off = (lane & 7) * sh.row3 + ((cw * 16 + (lane >> 4)) * 16 + ((lane >> 3) & 1) * 8) * 2;  // + 64*jp
+    const uint32_t alpha_addr = smem_u32(s_alpha) + (g * (sh.rp + 8) + 2 * t) * 2;                              // + 16*c
     float4 dn[KR];  // this thread's 4 columns of the next image's dec_att rows
+    const bool dec_ok = tid * 4 < A;
     auto load_dec = [&](int img) {
 #pragma unroll
         for (int k = 0; k < KR; ++k) {
             dn[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (tid * 4 < A && k < K && img < B)
+            if (dec_ok && k < K && img < B)
                 dn[k] = __ldg(reinterpret_cast<const float4*>(dec_ctx + (static_cast<size_t>(img) * K + k) * A) + tid);
         }
     };
@@ -680,7 +703,7 @@ butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __
     uint32_t phase = 0;
     int flip = 0;
     for (int img = blockIdx.x; img < B; img += gridDim.x) {
-        if (tid * 4 < A) {
+        if (dec_ok) {
 #pragma unroll
             for (int k = 0; k < KR; ++k) {
                 uint2 v;
@@ -695,27 +718,21 @@ butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __
             float acc[KR][4];
 #pragma unroll
             for (int k = 0; k < KR; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f;
-            mbar_wait(full_bar + 8 * stage, phase);
-            const int rl = (lane & 7) + ((lane >> 3) & 1) * 8;
-            const uint32_t rowaddr = ring + stage * sh.stage_bytes + rl * sh.row1;
-            const int colsel = (lane >> 4) * 8;
+            mbar_wait_lean(full_bar + 8 * stage, phase);
+            const uint32_t base1 = ring + stage * sh.stage_bytes + ld1_off;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int at = cw + 8 * j;
-                if (at < AT) {
-                    const int a0 = at * 16;
+                if (j < nj1) {
                     uint32_t x[4];
-                    ldmatrix_x4(x, rowaddr + (a0 + colsel) * 2);
-                    const uint32_t wb0 = *reinterpret_cast<const uint32_t*>(s_w16 + a0 + 2 * t) & wmask;
-                    const uint32_t wb1 = *reinterpret_cast<const uint32_t*>(s_w16 + a0 + 8 + 2 * t) & wmask;
+                    ldmatrix_x4(x, base1 + 256 * j);
+                    const uint32_t wb0 = lds_b32(w_addr + 256 * j) & wmask;
+                    const uint32_t wb1 = lds_b32(w_addr + 256 * j + 16) & wmask;
 #pragma unroll
                     for (int k = 0; k < KR; ++k) {
-                        if (k < K) {
-                            const uint32_t dlo = *reinterpret_cast<const uint32_t*>(s_dec16 + k * (A + 8) + a0 + 2 * t);
-                            const uint32_t dhi = *reinterpret_cast<const uint32_t*>(s_dec16 + k * (A + 8) + a0 + 8 + 2 * t);
-                            mma_m16n8k16_f16(acc[k], relu_add_h2(x[0], dlo), relu_add_h2(x[1], dlo), relu_add_h2(x[2], dhi),
-                                             relu_add_h2(x[3], dhi), wb0, wb1);
-                        }
+                        const uint32_t dlo = lds_b32(dec_addr + k * dec_pitch + 256 * j);
+                        const uint32_t dhi = lds_b32(dec_addr + k * dec_pitch + 256 * j + 16);
+                        mma_m16n8k16_f16(acc[k], relu_add_h2(x[0], dlo), relu_add_h2(x[1], dlo), relu_add_h2(x[2], dhi),
+                                         relu_add_h2(x[3], dhi), wb0, wb1);
                     }
                 }
             }
@@ -750,12 +767,13 @@ butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __
             m = warp_max(m);
             float s = 0.f;
             for (int r = lane; r < R; r += 32) {
-                const float ex = expf(s_e[k * sh.rp + r] - m);
+                const float ex = __expf(s_e[k * sh.rp + r] - m);
                 s_e[k * sh.rp + r] = ex;
                 s += ex;
             }
             s = warp_sum(s);
-            for (int r = lane; r < R; r += 32) s_alpha[k * (sh.rp + 8) + r] = __float2half_rn(s_e[k * sh.rp + r] / s);
+            const float inv = 1.0f / s;
+            for (int r = lane; r < R; r += 32) s_alpha[k * (sh.rp + 8) + r] = __float2half_rn(s_e[k * sh.rp + r] * inv);
         }
         named_bar_sync(1, 256);
         // ---------------- phase 3: ctx = alpha * feats
@@ -763,17 +781,14 @@ butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc3[j][0] = acc3[j][1] = acc3[j][2] = acc3[j][3] = 0.f;
         for (int c = 0; c < n_chunks3; ++c) {
-            mbar_wait(full_bar + 8 * stage, phase);
-            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(s_alpha + g * (sh.rp + 8) + c * 8 + 2 * t);
-            const int rl = lane & 7;
-            const uint32_t rowaddr = ring + stage * sh.stage_bytes + rl * sh.row3;
-            const int msel = lane >> 3;
+            mbar_wait_lean(full_bar + 8 * stage, phase);
+            const uint32_t b0 = lds_b32(alpha_addr + 16 * c);
+            const uint32_t base3 = ring + stage * sh.stage_bytes + ld3_off;
 #pragma unroll
             for (int jp = 0; jp < 8; ++jp) {
-                const int dt0 = cw * 16 + 2 * jp;
-                if (dt0 < DT) {
+                if (2 * jp < nj3) {
                     uint32_t m4[4];
-                    ldmatrix_x4_trans(m4, rowaddr + ((dt0 + (msel >> 1)) * 16 + (msel & 1) * 8) * 2);
+                    ldmatrix_x4_trans(m4, base3 + 64 * jp);
                     mma_m16n8k8_f16(acc3[2 * jp], m4[0], m4[1], b0);
                     mma_m16n8k8_f16(acc3[2 * jp + 1], m4[2], m4[3], b0);
                 }
@@ -782,20 +797,22 @@ butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __
             if (lane == 0) mbar_arrive(empty_bar + 8 * stage);
             if (++stage == STAGES) stage = 0, phase ^= 1;
         }
+        {
+            // c0/c2: beam 2t, columns g / g+8 of the tile; c1/c3: beam 2t+1
+            __half* o0 = ctx16 + (static_cast<size_t>(img) * K + 2 * t) * ld16 + cw * 256 + g;
+            __half* o1 = o0 + ld16;
+            const bool b0ok = 2 * t < K, b1ok = 2 * t + 1 < K;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int dt = cw * 16 + j;
-            if (dt < DT) {
-                const int d = dt * 16 + g;
-                if (2 * t < K) {
-                    __half* o = ctx16 + (static_cast<size_t>(img) * K + 2 * t) * ld16 + d;
-                    o[0] = __float2half_rn(acc3[j][0]);
-                    o[8] = __float2half_rn(acc3[j][2]);
-                }
-                if (2 * t + 1 < K) {
-                    __half* o = ctx16 + (static_cast<size_t>(img) * K + 2 * t + 1) * ld16 + d;
-                    o[0] = __float2half_rn(acc3[j][1]);
-                    o[8] = __float2half_rn(acc3[j][3]);
+            for (int j = 0; j < 16; ++j) {
+                if (j < nj3) {
+                    if (b0ok) {
+                        o0[16 * j] = __float2half_rn(acc3[j][0]);
+                        o0[16 * j + 8] = __float2half_rn(acc3[j][2]);
+                    }
+                    if (b1ok) {
+                        o1[16 * j] = __float2half_rn(acc3[j][1]);
+                        o1[16 * j + 8] = __float2half_rn(acc3[j][3]);
+                    }
                 }
             }
         }
