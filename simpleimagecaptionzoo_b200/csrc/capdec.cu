@@ -80,11 +80,11 @@ struct capdec_handle {
     int n_tiles_v = 0;
 
     // packed weights
-    Act16 W_pred, W_l1, W_l2, W_aux1, W_aux2, W_aux3;
+    Act16 W_pred, W_l1, W_l2, W_aux1, W_aux2, W_aux3, W_emb, emb16;
+    float* emb_gates = nullptr;  // [V, 4H] gate pre-activations contributed by each vocabulary word (embedding x W_ih slice)
     float *b_pred = nullptr, *b_l1 = nullptr, *b_l2 = nullptr, *b_aux1 = nullptr, *b_aux2 = nullptr, *b_aux3 = nullptr;
     float* w_aff = nullptr;
     float b_aff = 0.f;
-    const float* embed = nullptr;
     const float *ln_gain = nullptr, *ln_bias = nullptr;
     double* scale_tmp = nullptr;
 
@@ -288,6 +288,22 @@ int pack_bias(capdec_handle* h, const Raw* a, const Raw* b, float* dst, int N, i
     return CAPDEC_OK;
 }
 
+// emb_gates[v, :] = act(embed[v, :]) * W_emb^T : the fed-back word's contribution to the LSTM gates becomes a row
+// gather in the gate GEMM's epilogue instead of E columns of its K loop (embed + Linear folded once at load;
+// BUTD_Model.py:264-265, NIC_Model.py:172-173, AoA_Model.py:439-441).
+int build_embedding_gates(capdec_handle* h, const Raw* emb, int relu, cudaStream_t st) {
+    const int V = h->V, E = h->E, H = h->H;
+    cvt_f16_kernel<<<grid_for(static_cast<size_t>(V) * E / 4), 256, 0, st>>>(emb->d, V, E, h->emb16.p, h->emb16.ld, h->emb16.lo, 0, relu);
+    CK(h, cudaGetLastError());
+    CUtensorMap ma, mb;
+    CKS(h, map_a(h, &ma, h->emb16));
+    CKS(h, map_b(h, &mb, h->W_emb));
+    EpiParams e{};
+    e.out32 = h->emb_gates;
+    e.ld32 = 4 * H;
+    return launch_gemm(h, EPI_STORE, 1, ma, h->emb16.lo, mb, h->W_emb.lo, V, 4 * H, E, e, st);
+}
+
 int finalize_predict(capdec_handle* h, cudaStream_t st) {
     const Raw *g, *v, *b;
     CKS(h, need(h, "predict.weight_g", {h->V, 1}, &g));
@@ -320,14 +336,15 @@ int finalize_butd(capdec_handle* h, cudaStream_t st) {
     fold_vector_kernel<<<(A + 255) / 256, 256, 0, st>>>(v->d, h->scale_tmp, h->w_aff, A);
     CK(h, cudaGetLastError());
     CK(h, cudaMemcpyAsync(&h->b_aff, b->d, sizeof(float), cudaMemcpyDeviceToHost, st));
-    // top-down attention LSTM: input cat[h2, mean, emb] (BUTD_Model.py:265) -> operand [h2 | emb | h1]
+    // top-down attention LSTM: input cat[h2, mean, emb] (BUTD_Model.py:265) -> operand [h2 | h1]; the mean slice is
+    // hoisted per image (W_aux3), the emb slice per vocabulary word (W_emb -> emb_gates)
     CKS(h, need(h, "TD_atten.weight_ih", {4 * H, H + D + E}, &wih));
     CKS(h, need(h, "TD_atten.weight_hh", {4 * H, H}, &whh));
     CKS(h, need(h, "TD_atten.bias_ih", {4 * H}, &bih));
     CKS(h, need(h, "TD_atten.bias_hh", {4 * H}, &bhh));
     CKS(h, pack_segment(h, wih, 0, H, nullptr, h->W_l1, 0, 1, H, st));
-    CKS(h, pack_segment(h, wih, H + D, E, nullptr, h->W_l1, H, 1, H, st));
-    CKS(h, pack_segment(h, whh, 0, H, nullptr, h->W_l1, H + E, 1, H, st));
+    CKS(h, pack_segment(h, whh, 0, H, nullptr, h->W_l1, H, 1, H, st));
+    CKS(h, pack_segment(h, wih, H + D, E, nullptr, h->W_emb, 0, 1, H, st));
     CKS(h, pack_segment(h, wih, H, D, nullptr, h->W_aux3, 0, 1, H, st));  // W_aux3 = mean-feature slice [4H, D]
     CKS(h, pack_bias(h, bih, bhh, h->b_l1, 4 * H, 1, H, st));
     // language LSTM: input cat[ctx, h1] (BUTD_Model.py:268) -> operand [ctx | h1 | h2]
@@ -340,8 +357,7 @@ int finalize_butd(capdec_handle* h, cudaStream_t st) {
     CKS(h, pack_bias(h, bih, bhh, h->b_l2, 4 * H, 1, H, st));
     const Raw* emb;
     CKS(h, need(h, "embed.0.weight", {h->V, E}, &emb));
-    h->embed = emb->d;
-    return CAPDEC_OK;
+    return build_embedding_gates(h, emb, 1, st);  // embed = Embedding + ReLU (BUTD_Model.py:77-81)
 }
 
 int finalize_nic(capdec_handle* h, cudaStream_t st) {
@@ -351,24 +367,24 @@ int finalize_nic(capdec_handle* h, cudaStream_t st) {
     CKS(h, need(h, "lstm.weight_hh", {4 * H, H}, &whh));
     CKS(h, need(h, "lstm.bias_ih", {4 * H}, &bih));
     CKS(h, need(h, "lstm.bias_hh", {4 * H}, &bhh));
-    CKS(h, pack_segment(h, wih, 0, E, nullptr, h->W_l1, 0, 1, H, st));
-    CKS(h, pack_segment(h, whh, 0, H, nullptr, h->W_l1, E, 1, H, st));
+    CKS(h, pack_segment(h, wih, 0, E, nullptr, h->W_emb, 0, 1, H, st));  // also the operand of the priming step
+    CKS(h, pack_segment(h, whh, 0, H, nullptr, h->W_l1, 0, 1, H, st));
     CKS(h, pack_bias(h, bih, bhh, h->b_l1, 4 * H, 1, H, st));
     CKS(h, need(h, "embed.weight", {h->V, E}, &emb));
-    h->embed = emb->d;
-    return CAPDEC_OK;
+    return build_embedding_gates(h, emb, 0, st);  // plain nn.Embedding (NIC_Model.py:47)
 }
 
 int finalize_aoa(capdec_handle* h, cudaStream_t st) {
     const int H = h->H, E = h->E;
     const Raw *wih, *whh, *bih, *bhh, *w, *b, *emb, *gn, *bs;
-    // lstm input cat[emb, mean+ctx] (AoA_Model.py:441) -> operand [emb | mean+ctx | h]
+    // lstm input cat[emb, mean+ctx] (AoA_Model.py:441) -> operand [mean+ctx | h]; emb slice -> emb_gates
     CKS(h, need(h, "lstm.weight_ih", {4 * H, E + H}, &wih));
     CKS(h, need(h, "lstm.weight_hh", {4 * H, H}, &whh));
     CKS(h, need(h, "lstm.bias_ih", {4 * H}, &bih));
     CKS(h, need(h, "lstm.bias_hh", {4 * H}, &bhh));
-    CKS(h, pack_segment(h, wih, 0, E + H, nullptr, h->W_l1, 0, 1, H, st));
-    CKS(h, pack_segment(h, whh, 0, H, nullptr, h->W_l1, E + H, 1, H, st));
+    CKS(h, pack_segment(h, wih, E, H, nullptr, h->W_l1, 0, 1, H, st));
+    CKS(h, pack_segment(h, whh, 0, H, nullptr, h->W_l1, H, 1, H, st));
+    CKS(h, pack_segment(h, wih, 0, E, nullptr, h->W_emb, 0, 1, H, st));
     CKS(h, pack_bias(h, bih, bhh, h->b_l1, 4 * H, 1, H, st));
     CKS(h, need(h, "aoa_block.linear_Q.weight", {H, H}, &w));
     CKS(h, need(h, "aoa_block.linear_Q.bias", {H}, &b));
@@ -398,12 +414,11 @@ int finalize_aoa(capdec_handle* h, cudaStream_t st) {
     CKS(h, pack_segment(h, w, 0, 2 * H, nullptr, h->W_aux3, 0, 2, H, st));
     CKS(h, pack_bias(h, b, nullptr, h->b_aux3, 2 * H, 2, H, st));
     CKS(h, need(h, "embed.0.weight", {h->V, E}, &emb));
-    h->embed = emb->d;
     CKS(h, need(h, "h_norm.gain", {H}, &gn));
     CKS(h, need(h, "h_norm.bias", {H}, &bs));
     h->ln_gain = gn->d;
     h->ln_bias = bs->d;
-    return CAPDEC_OK;
+    return build_embedding_gates(h, emb, 1, st);  // embed = Embedding + ReLU (AoA_Model.py:206-210)
 }
 
 // ------------------------------------------------------------------------------------------------ per-arch steps
@@ -537,9 +552,9 @@ int launch_aoa_att(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
     return CAPDEC_OK;
 }
 
-// BUTD: XA = [h2 | emb | h1] (top-down LSTM operand), XB = [ctx | h1 | h2] (language LSTM operand), Hb2 = new h2.
+// BUTD: XA = [h2 | h1] (top-down LSTM operand), XB = [ctx | h1 | h2] (language LSTM operand), Hb2 = new h2.
 int step_butd(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
-    const int H = h->H, E = h->E, A = h->A, D = h->D;
+    const int H = h->H, A = h->A, D = h->D;
     CUtensorMap ma, mb;
     {  // top-down attention LSTM (BUTD_Model.py:265)
         CKS(h, map_a(h, &ma, h->XA));
@@ -548,6 +563,9 @@ int step_butd(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
         e.rowadd = h->G0;
         e.rowadd_ld = 4 * H;
         e.rows_per_group = c.K;
+        e.gather = h->emb_gates;
+        e.gather_idx = h->tok;
+        e.gather_ld = 4 * H;
         e.c_in = h->c1[c.cur];
         e.c_out = h->c1[c.cur ^ 1];
         e.ldc = H;
@@ -555,7 +573,7 @@ int step_butd(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
         e.out16 = h->XB.p + D;
         e.ld16 = h->XB.ld;
         e.lo16 = h->XB.lo;
-        CKS(h, launch_gemm(h, EPI_LSTM, 1, ma, h->XA.lo, mb, h->W_l1.lo, c.M, 4 * H, H + E + H, e, st));
+        CKS(h, launch_gemm(h, EPI_LSTM, 1, ma, h->XA.lo, mb, h->W_l1.lo, c.M, 4 * H, H + H, e, st));
     }
     {  // dec_att(h1) (BUTD_Model.py:58)
         CKS(h, map_a(h, &ma, h->XB, D));
@@ -599,39 +617,28 @@ AdvOp op_copy(const Act16& src, int src_col, const Act16& dst, int dst_col, int 
     o.n = n;
     return o;
 }
-AdvOp op_embed(const float* table, int E, const Act16& dst, int dst_col, int relu) {
-    AdvOp o{};
-    o.kind = ADV_EMBED;
-    o.src = table;
-    o.src_ld = E;
-    o.dst = dst.p + dst_col;
-    o.dst_ld = dst.ld;
-    o.dst_lo = dst.lo;
-    o.n = E;
-    o.flag = relu;
-    return o;
-}
-
 AdvOps adv_butd(capdec_handle* h, bool init) {
-    const int H = h->H, E = h->E, D = h->D;
+    const int H = h->H, D = h->D;
     AdvOps a{};
-    a.op[a.n++] = op_embed(h->embed, E, h->XA, H, 1);
     if (!init) {
         a.op[a.n++] = op_copy(h->Hb2, 0, h->XA, 0, H);      // h2 -> top-down operand
         a.op[a.n++] = op_copy(h->Hb2, 0, h->XB, D + H, H);  // h2 -> language operand (recurrent part)
-        a.op[a.n++] = op_copy(h->XB, D, h->XA, H + E, H);   // h1 -> top-down operand (recurrent part)
+        a.op[a.n++] = op_copy(h->XB, D, h->XA, H, H);       // h1 -> top-down operand (recurrent part)
     }
     return a;
 }
 
-// NIC: XA = [emb | h], Hb = new h.
+// NIC: XA = [h], Hb = new h.
 int step_nic(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
-    const int H = h->H, E = h->E;
+    const int H = h->H;
     CUtensorMap ma, mb;
     CKS(h, map_a(h, &ma, h->XA));
     CKS(h, map_b(h, &mb, h->W_l1));
     EpiParams e{};
     e.bias = h->b_l1;
+    e.gather = h->emb_gates;
+    e.gather_idx = h->tok;
+    e.gather_ld = 4 * H;
     e.c_in = c.first_from_c0 ? h->c0 : h->c1[c.cur];
     e.c_out = h->c1[c.cur ^ 1];
     e.ldc = H;
@@ -639,33 +646,35 @@ int step_nic(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
     e.out16 = h->Hb.p;
     e.ld16 = h->Hb.ld;
     e.lo16 = h->Hb.lo;
-    CKS(h, launch_gemm(h, EPI_LSTM, 1, ma, h->XA.lo, mb, h->W_l1.lo, c.M, 4 * H, E + H, e, st));
+    CKS(h, launch_gemm(h, EPI_LSTM, 1, ma, h->XA.lo, mb, h->W_l1.lo, c.M, 4 * H, H, e, st));
     return run_logits(h, h->Hb, c, st);
 }
 
 AdvOps adv_nic(capdec_handle* h, bool init) {
-    const int H = h->H, E = h->E;
+    const int H = h->H;
     AdvOps a{};
-    a.op[a.n++] = op_embed(h->embed, E, h->XA, 0, 0);
     if (init) {
-        AdvOp o = op_copy(h->H0, 0, h->XA, E, H);  // primed hidden state of the image (NIC_Model.py:164,170)
+        AdvOp o = op_copy(h->H0, 0, h->XA, 0, H);  // primed hidden state of the image (NIC_Model.py:164,170)
         o.kind = ADV_BCAST16;
         a.op[a.n++] = o;
     } else {
-        a.op[a.n++] = op_copy(h->Hb, 0, h->XA, E, H);
+        a.op[a.n++] = op_copy(h->Hb, 0, h->XA, 0, H);
     }
     return a;
 }
 
-// AoA: XA = [emb | mean+ctx | h] (LSTM operand), XB = [att | query] (AoA gate operand), Hb = new h, Hb2 = ctx fp16.
+// AoA: XA = [mean+ctx | h] (LSTM operand), XB = [att | query] (AoA gate operand), Hb = new h, Hb2 = ctx fp16.
 int step_aoa(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
-    const int H = h->H, E = h->E;
+    const int H = h->H;
     CUtensorMap ma, mb;
     {
         CKS(h, map_a(h, &ma, h->XA));
         CKS(h, map_b(h, &mb, h->W_l1));
         EpiParams e{};
         e.bias = h->b_l1;
+        e.gather = h->emb_gates;
+        e.gather_idx = h->tok;
+        e.gather_ld = 4 * H;
         e.c_in = h->c1[c.cur];
         e.c_out = h->c1[c.cur ^ 1];
         e.ldc = H;
@@ -675,7 +684,7 @@ int step_aoa(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
         e.lo16 = h->Hb.lo;
         e.h32 = h->h32;
         e.ldh32 = H;
-        CKS(h, launch_gemm(h, EPI_LSTM, 1, ma, h->XA.lo, mb, h->W_l1.lo, c.M, 4 * H, E + H + H, e, st));
+        CKS(h, launch_gemm(h, EPI_LSTM, 1, ma, h->XA.lo, mb, h->W_l1.lo, c.M, 4 * H, H + H, e, st));
     }
     prof_begin(h, CAPDEC_CAT_OTHER, 0.0, st);
     aoa_layernorm_kernel<<<(c.M + 7) / 8, 256, 0, st>>>(h->h32, c.M, H, h->ln_gain, h->ln_bias, 1e-6f, h->XB.p + H, h->XB.ld,
@@ -712,20 +721,19 @@ int step_aoa(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
 }
 
 AdvOps adv_aoa(capdec_handle* h, bool init) {
-    const int H = h->H, E = h->E;
+    const int H = h->H;
     AdvOps a{};
-    a.op[a.n++] = op_embed(h->embed, E, h->XA, 0, 1);
     AdvOp m{};
     m.kind = ADV_MEAN_PLUS;
     m.src = init ? nullptr : h->ctx32;
     m.src_ld = H;
     m.aux = h->mean32;
-    m.dst = h->XA.p + E;
+    m.dst = h->XA.p;
     m.dst_ld = h->XA.ld;
     m.dst_lo = h->XA.lo;
     m.n = H;
     a.op[a.n++] = m;
-    if (!init) a.op[a.n++] = op_copy(h->Hb, 0, h->XA, E + H, H);
+    if (!init) a.op[a.n++] = op_copy(h->Hb, 0, h->XA, H, H);
     return a;
 }
 
@@ -809,6 +817,9 @@ static int create_impl(capdec_handle* h) {
 
     CKS(h, dalloc(h, &h->scale_tmp, static_cast<size_t>(V > 4 * H ? V : 4 * H)));
     CKS(h, alloc_act(h, &h->W_pred, V, H));
+    CKS(h, alloc_act(h, &h->W_emb, 4 * H, E));
+    CKS(h, alloc_act(h, &h->emb16, V, E));
+    CKS(h, dalloc(h, &h->emb_gates, static_cast<size_t>(V) * 4 * H));
     CKS(h, dalloc(h, &h->b_pred, V));
     CKS(h, dalloc(h, &h->b_l1, 4 * H));
     const size_t part_stride = topk_part_stride(8) > SAMPLE_PART_STRIDE ? topk_part_stride(8) : SAMPLE_PART_STRIDE;
@@ -830,7 +841,7 @@ static int create_impl(capdec_handle* h) {
     if (c.arch == CAPDEC_ARCH_BUTD) {
         const int A = h->A, D = h->D;
         const size_t BR = static_cast<size_t>(h->Bmax) * h->Rmax;
-        CKS(h, alloc_act(h, &h->W_l1, 4 * H, H + E + H));
+        CKS(h, alloc_act(h, &h->W_l1, 4 * H, H + H));
         CKS(h, alloc_act(h, &h->W_l2, 4 * H, D + H + H));
         CKS(h, alloc_act(h, &h->W_aux1, A, D));
         CKS(h, alloc_act(h, &h->W_aux2, A, H));
@@ -844,22 +855,22 @@ static int create_impl(capdec_handle* h) {
         if (h->split) CKS(h, dalloc(h, &h->enc_ctx, BR * A));
         else CKS(h, alloc_act(h, &h->enc16, static_cast<int>(BR), A, 8));
         CKS(h, dalloc(h, &h->G0, static_cast<size_t>(h->Bmax) * 4 * H));
-        CKS(h, alloc_act(h, &h->XA, M, H + E + H));
+        CKS(h, alloc_act(h, &h->XA, M, H + H));
         CKS(h, alloc_act(h, &h->XB, M, D + H + H));
         CKS(h, alloc_act(h, &h->Hb2, M, H));
         CKS(h, dalloc(h, &h->dec_ctx, static_cast<size_t>(M) * A));
         CKS(h, dalloc(h, &h->c2[0], static_cast<size_t>(M) * H));
         CKS(h, dalloc(h, &h->c2[1], static_cast<size_t>(M) * H));
     } else if (c.arch == CAPDEC_ARCH_NIC) {
-        CKS(h, alloc_act(h, &h->W_l1, 4 * H, E + H));
-        CKS(h, alloc_act(h, &h->XA, M, E + H));
+        CKS(h, alloc_act(h, &h->W_l1, 4 * H, H));
+        CKS(h, alloc_act(h, &h->XA, M, H));
         CKS(h, alloc_act(h, &h->Hb, M, H));
-        CKS(h, alloc_act(h, &h->Xp, h->Bmax, E + H));
+        CKS(h, alloc_act(h, &h->Xp, h->Bmax, E));
         CKS(h, alloc_act(h, &h->H0, h->Bmax, H));
         CKS(h, dalloc(h, &h->c0, static_cast<size_t>(h->Bmax) * H));
     } else {
         const size_t BR = static_cast<size_t>(h->Bmax) * h->Rmax;
-        CKS(h, alloc_act(h, &h->W_l1, 4 * H, E + H + H));
+        CKS(h, alloc_act(h, &h->W_l1, 4 * H, H + H));
         CKS(h, alloc_act(h, &h->W_aux1, H, H));
         CKS(h, alloc_act(h, &h->W_aux2, 2 * H, H));
         CKS(h, alloc_act(h, &h->W_aux3, 2 * H, 2 * H));
@@ -869,7 +880,7 @@ static int create_impl(capdec_handle* h) {
         CKS(h, alloc_act(h, &h->feats16, static_cast<int>(BR), H));
         CKS(h, dalloc(h, &h->kv32, BR * 2 * H));
         CKS(h, dalloc(h, &h->mean32, static_cast<size_t>(h->Bmax) * H));
-        CKS(h, alloc_act(h, &h->XA, M, E + H + H));
+        CKS(h, alloc_act(h, &h->XA, M, H + H));
         CKS(h, alloc_act(h, &h->XB, M, 2 * H));
         CKS(h, alloc_act(h, &h->Hb, M, H));
         CKS(h, alloc_act(h, &h->Hb2, M, H));
@@ -959,7 +970,7 @@ int capdec_prepare(capdec_handle* h, const float* feats, const float* mask, int3
         CK(h, cudaGetLastError());
         h->launches++;
         CKS(h, map_a(h, &ma, h->Xp));
-        CKS(h, map_b(h, &mb, h->W_l1));
+        CKS(h, map_b(h, &mb, h->W_emb));
         EpiParams e{};
         e.bias = h->b_l1;
         e.c_out = h->c0;
@@ -967,7 +978,7 @@ int capdec_prepare(capdec_handle* h, const float* feats, const float* mask, int3
         e.out16 = h->H0.p;
         e.ld16 = h->H0.ld;
         e.lo16 = h->H0.lo;
-        CKS(h, launch_gemm(h, EPI_LSTM, 1, ma, h->Xp.lo, mb, h->W_l1.lo, batch, 4 * H, E + H, e, st));
+        CKS(h, launch_gemm(h, EPI_LSTM, 1, ma, h->Xp.lo, mb, h->W_emb.lo, batch, 4 * H, E, e, st));
         h->R = 0;
     } else {
         if (regions <= 0 || regions > h->Rmax) return fail(h, CAPDEC_ERR_INVALID, "prepare: regions out of range");

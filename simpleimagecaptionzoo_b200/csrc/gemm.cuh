@@ -43,6 +43,9 @@ struct EpiParams {
     const float* rowadd;    // additive per-row-group term [M/rows_per_group, N] or null (hoisted, step-invariant part)
     int rowadd_ld;
     int rows_per_group;
+    const float* gather;    // additive per-row term gathered by index: gather[gather_idx[row], N] (embedding-table
+    const int* gather_idx;  //   contribution of the fed-back word: precomputed embed(word) * W_ih[:, emb]^T), or null
+    int gather_ld;
     const float* c_in;      // [.., H] previous cell state (null = zeros)
     float* c_out;           // [M, H]
     int ldc;
@@ -183,6 +186,7 @@ __device__ __forceinline__ void epi_lstm(uint32_t taddr, int row, int n_base, in
         if (e.rowadd) add = e.rowadd + static_cast<size_t>(row / e.rows_per_group) * e.rowadd_ld;  // ... or per image
     }
     const float* cin = e.c_in ? e.c_in + static_cast<size_t>(prow) * e.ldc : nullptr;
+    const float* gat = (e.gather && row_ok) ? e.gather + static_cast<size_t>(__ldg(e.gather_idx + row)) * e.gather_ld : nullptr;
 #pragma unroll 1
     for (int c = c0; c < c1; ++c) {
         const int n0 = n_base + c * 32;
@@ -193,6 +197,13 @@ __device__ __forceinline__ void epi_lstm(uint32_t taddr, int row, int n_base, in
         if (row_ok) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) ad[i] = __ldg(reinterpret_cast<const float4*>(add + n0) + i);
+            if (gat) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 q = __ldg(reinterpret_cast<const float4*>(gat + n0) + i);
+                    ad[i].x += q.x, ad[i].y += q.y, ad[i].z += q.z, ad[i].w += q.w;
+                }
+            }
             if (cin) {
                 cp0 = *reinterpret_cast<const float4*>(cin + j0);
                 cp1 = *reinterpret_cast<const float4*>(cin + j0 + 4);

@@ -87,14 +87,15 @@ __global__ void fold_vector_kernel(const float* __restrict__ v, const double* __
 // ================================================================================================ prepare
 // fp32 [rows, cols] -> fp16 hi|lo operand
 __global__ void cvt_f16_kernel(const float* __restrict__ src, size_t rows, int cols, __half* __restrict__ dst, int dst_ld,
-                               int dst_lo, int dst_col) {
+                               int dst_lo, int dst_col, int relu = 0) {
     const size_t total4 = rows * static_cast<size_t>(cols) / 4;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total4;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const size_t e = i * 4;
         const size_t r = e / cols;
         const int c = static_cast<int>(e - r * cols);
-        const float4 x = __ldg(reinterpret_cast<const float4*>(src + e));
+        float4 x = __ldg(reinterpret_cast<const float4*>(src + e));
+        if (relu) x.x = fmaxf(x.x, 0.f), x.y = fmaxf(x.y, 0.f), x.z = fmaxf(x.z, 0.f), x.w = fmaxf(x.w, 0.f);
         __align__(8) __half hi[4];
         __align__(8) __half lo[4];
         split_f16(x.x, hi[0], lo[0]);
