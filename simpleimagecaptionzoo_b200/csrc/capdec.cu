@@ -63,6 +63,7 @@ struct capdec_handle {
     const float* feats = nullptr;
     const float* mask = nullptr;
     int64_t launches = 0;
+    bool pair_gemm = true;             // CAPDEC_GEMM_1CTA=1 selects the single-CTA GEMM kernel instead of the CTA-pair one
     bool no_stream_attention = false;  // CAPDEC_NO_STREAM_ATTENTION=1: use the non-persistent attention kernel
     int att_variant = 0;               // CAPDEC_ATT_VARIANT=1: FFMA streaming kernel instead of the MMA-fragment kernel
     bool prof = false;  // bracket every launch with CUDA events (capdec_profile)
@@ -178,7 +179,10 @@ int make_map(capdec_handle* h, CUtensorMap* m, const __half* base, int rows, int
 int map_a(capdec_handle* h, CUtensorMap* m, const Act16& a, int col_off = 0) {
     return make_map(h, m, a.p, a.rows, a.ld, col_off, BLOCK_M);
 }
-int map_b(capdec_handle* h, CUtensorMap* m, const Act16& a) { return make_map(h, m, a.p, a.rows, a.ld, 0, BN); }
+// weight operand: the single-CTA kernel loads 256-row boxes, the CTA-pair kernel 128-row halves
+int map_b(capdec_handle* h, CUtensorMap* m, const Act16& a) {
+    return make_map(h, m, a.p, a.rows, a.ld, 0, h->pair_gemm ? BN / 2 : BN);
+}
 
 template <int EPI, int KTOP>
 int launch_gemm_t(capdec_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
@@ -202,10 +206,32 @@ int launch_gemm_t(capdec_handle* h, const CUtensorMap& ma, const CUtensorMap& mb
 }
 
 // D[M,N] = A[M,Kdim] * B[N,Kdim]^T with the chosen epilogue.
+template <int EPI, int KTOP>
+int launch_gemm2_t(capdec_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
+    static bool attr_set = false;
+    auto kern = gemm2_kernel<EPI, KTOP>;
+    if (!attr_set) {
+        CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg2::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int items = p.runs > 0 ? p.num_m_blocks * p.runs : p.num_m_blocks * p.num_n_blocks;
+    const int pairs = items < h->num_sms / 2 ? items : h->num_sms / 2;
+    const int cat = EPI == EPI_LSTM ? CAPDEC_CAT_GEMM_LSTM : EPI == EPI_STORE ? CAPDEC_CAT_GEMM_STORE
+                  : EPI == EPI_GLU ? CAPDEC_CAT_GEMM_GLU : CAPDEC_CAT_GEMM_LOGITS;
+    prof_begin(h, cat, 2.0 * p.M * p.N * (static_cast<double>(p.k_blocks) * BLOCK_K), st);
+    kern<<<2 * pairs, GEMM_THREADS, GemmCfg2::SMEM_BYTES, st>>>(ma, mb, p);
+    prof_end(h, st);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    return CAPDEC_OK;
+}
+
 // number of vocabulary-tile runs per row block of the logit GEMM: fill the SMs with (row block, run) items
 int logit_runs(const capdec_handle* h, int M, int N) {
-    const int num_m = (M + BLOCK_M - 1) / BLOCK_M, num_n = (N + BN - 1) / BN;
-    int runs = h->num_sms / num_m;
+    const int rows = h->pair_gemm ? 2 * BLOCK_M : BLOCK_M;  // row-block height of a work item
+    const int workers = h->pair_gemm ? h->num_sms / 2 : h->num_sms;
+    const int num_m = (M + rows - 1) / rows, num_n = (N + BN - 1) / BN;
+    int runs = workers / num_m;
     if (runs < 1) runs = 1;
     if (runs > num_n) runs = num_n;
     return runs;
@@ -226,6 +252,19 @@ int launch_gemm(capdec_handle* h, int epi, int ktop, const CUtensorMap& ma, int 
     p.num_n_blocks = (N + BN - 1) / BN;
     p.runs = (epi == EPI_TOPK || epi == EPI_SAMPLE) ? logit_runs(h, M, N) : 0;
     p.epi = e;
+    if (h->pair_gemm) {  // CTA-pair kernel: 256-row blocks; `mb` must be a 128-row-box map (map_b)
+        p.num_m_blocks = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+        switch (epi) {
+            case EPI_STORE: return launch_gemm2_t<EPI_STORE, 1>(h, ma, mb, p, st);
+            case EPI_LSTM: return launch_gemm2_t<EPI_LSTM, 1>(h, ma, mb, p, st);
+            case EPI_GLU: return launch_gemm2_t<EPI_GLU, 1>(h, ma, mb, p, st);
+            case EPI_SAMPLE: return launch_gemm2_t<EPI_SAMPLE, 1>(h, ma, mb, p, st);
+            case EPI_TOPK:
+                if (ktop <= 4) return launch_gemm2_t<EPI_TOPK, 4>(h, ma, mb, p, st);
+                return launch_gemm2_t<EPI_TOPK, 8>(h, ma, mb, p, st);
+        }
+        return fail(h, CAPDEC_ERR_INVALID, "unknown epilogue");
+    }
     switch (epi) {
         case EPI_STORE: return launch_gemm_t<EPI_STORE, 1>(h, ma, mb, p, st);
         case EPI_LSTM: return launch_gemm_t<EPI_LSTM, 1>(h, ma, mb, p, st);
@@ -808,6 +847,8 @@ static int create_impl(capdec_handle* h) {
     {
         const char* e = getenv("CAPDEC_NO_STREAM_ATTENTION");
         h->no_stream_attention = e && e[0] == '1';
+        const char* g1 = getenv("CAPDEC_GEMM_1CTA");
+        h->pair_gemm = !(g1 && g1[0] == '1');
         const char* v = getenv("CAPDEC_ATT_VARIANT");
         h->att_variant = v ? atoi(v) : 0;
     }
@@ -1178,6 +1219,10 @@ int capdec_test_gemm(const float* a, const float* b, const float* bias, float* d
     h->cfg.device = dev;
     h->num_sms = prop.multiProcessorCount;
     h->split = math_mode == CAPDEC_MATH_F16X3;
+    {
+        const char* g1 = getenv("CAPDEC_GEMM_1CTA");
+        h->pair_gemm = !(g1 && g1[0] == '1');
+    }
     int status = CAPDEC_OK;
     Act16 A16, B16;
     do {
@@ -1218,6 +1263,10 @@ int capdec_test_gemm_time(int32_t m, int32_t n, int32_t k, int32_t epi, int32_t 
     h->cfg.device = dev;
     h->num_sms = prop.multiProcessorCount;
     h->split = math_mode == CAPDEC_MATH_F16X3;
+    {
+        const char* g1 = getenv("CAPDEC_GEMM_1CTA");
+        h->pair_gemm = !(g1 && g1[0] == '1');
+    }
     int status = CAPDEC_OK;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     do {

@@ -408,8 +408,8 @@ struct DrawState {
 struct TileIter {
     int item, items, step, runs, num_m, num_n;
     int m_blk, n_blk, n_end, run;
-    __device__ __forceinline__ TileIter(const GemmParams& p)
-        : item(blockIdx.x), step(gridDim.x), runs(p.runs), num_m(p.num_m_blocks), num_n(p.num_n_blocks) {
+    __device__ __forceinline__ TileIter(const GemmParams& p, int first = blockIdx.x, int stride = gridDim.x)
+        : item(first), step(stride), runs(p.runs), num_m(p.num_m_blocks), num_n(p.num_n_blocks) {
         items = runs > 0 ? num_m * runs : num_m * num_n;
         n_blk = 0, n_end = 0, m_blk = 0, run = 0;
     }
@@ -586,6 +586,175 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ CTA-pair kernel
+// Same GEMM with tcgen05.mma.cta_group::2: a cluster of two CTAs (one SM pair) computes a 256 x 256 output tile.
+// Each CTA stages its own 128 rows of A and only HALF of the B tile (128 of the 256 weight rows); the pair MMA
+// reads both halves, so per-SM shared-memory fill and L2->SM traffic drop from 48 KB to 32 KB per k-block and the
+// operand reads per MMA from 12 KB to 8 KB -- the single-CTA kernel saturates the SM's shared-memory bandwidth
+// at ~70 % tensor-pipe activity.  p.num_m_blocks counts 256-row PAIR blocks here.
+//   full[s]   (leader only) : armed by the leader with the bytes of BOTH CTAs; both CTAs' TMA loads signal it
+//   empty[s]  (each CTA)    : multicast tcgen05.commit from the leader's MMA thread
+//   tfull[a]  (each CTA)    : multicast tcgen05.commit -> both epilogues
+//   tempty[a] (leader only) : one arrive per epilogue warp of both CTAs (remote arrive from the peer)
+struct GemmCfg2 {
+    static constexpr int BLOCK_N = 256;
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+    static constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = 6;
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+};
+
+template <int EPI, int KTOP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+    using Cfg = GemmCfg2;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int BLOCK_N = Cfg::BLOCK_N;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    const uint32_t full_bar = smem_u32(bars);
+    const uint32_t empty_bar = smem_u32(bars + STAGES);
+    const uint32_t tfull_bar = smem_u32(bars + 2 * STAGES);
+    const uint32_t tempty_bar = smem_u32(bars + 2 * STAGES + 2);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    const uint32_t smem_base = smem_u32(smem);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int total_kb = p.k_blocks * p.passes;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar + 8 * s, 1);
+            mbar_init(empty_bar + 8 * s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar + 8 * s, 1);
+            mbar_init(tempty_bar + 8 * s, 2 * EPI_WARPS);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc_cg2(smem_u32(tmem_slot), Cfg::TMEM_COLS);
+        tmem_relinquish_cg2();
+    }
+    tc_fence_before();
+    cluster_sync_all();  // barrier inits and TMEM allocation of BOTH CTAs are visible before any remote signal
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (each CTA loads its A rows and its half of B) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            TileIter it(p, pair, npairs);
+            bool f, l;
+            while (it.next(f, l)) {
+                const int m_blk = 2 * it.m_blk + static_cast<int>(rank), n_blk = it.n_blk;
+                for (int kk = 0; kk < total_kb; ++kk) {
+                    const int pass = kk / p.k_blocks;
+                    const int kb = kk - pass * p.k_blocks;
+                    const int ka = kb * BLOCK_K + (pass == 2 ? p.a_lo_off : 0);
+                    const int kbb = kb * BLOCK_K + (pass == 1 ? p.b_lo_off : 0);
+                    mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t sb = sa + Cfg::A_BYTES;
+                    const uint32_t lead_full = mapa_shared(full_bar + 8 * stage, 0);
+                    if (leader) mbar_arrive_expect_tx(full_bar + 8 * stage, 2 * Cfg::STAGE_BYTES);
+                    tma_load_2d_cg2(sa, &tma_a, lead_full, ka, m_blk * BLOCK_M);
+                    tma_load_2d_cg2(sb, &tma_b, lead_full, kbb, n_blk * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2));
+                    if (++stage == STAGES) stage = 0, phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer: one thread of the LEADER CTA drives both tensor cores =====================
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = make_idesc_f16(2 * BLOCK_M, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            TileIter it(p, pair, npairs);
+            bool f, l;
+            while (it.next(f, l)) {
+                mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kk = 0; kk < total_kb; ++kk) {
+                    mbar_wait(full_bar + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint64_t da = make_smem_desc_sw128(sa);
+                    const uint64_t db = make_smem_desc_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                        umma_f16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kk | k) != 0 ? 1u : 0u);
+                    umma_commit_cg2(empty_bar + 8 * stage, 3);  // frees the slot in BOTH CTAs
+                    if (++stage == STAGES) stage = 0, phase ^= 1;
+                }
+                umma_commit_cg2(tfull_bar + 8 * acc, 3);
+                if (++acc == 2) acc = 0, acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ===================== epilogue warps of both CTAs: each CTA owns its 128 accumulator rows =====================
+        const int quarter = warp & 3;
+        const int split = (warp - 2) >> 2;
+        constexpr int CHUNKS = BLOCK_N / 32;
+        const int c0 = split * (CHUNKS / EPI_SPLIT), c1 = c0 + CHUNKS / EPI_SPLIT;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        TopkState<KTOP> tk;
+        DrawState sp;
+        TileIter it(p, pair, npairs);
+        bool first, last;
+        while (it.next(first, last)) {
+            const int m_blk = 2 * it.m_blk + static_cast<int>(rank), n_blk = it.n_blk;
+            mbar_wait(tfull_bar + 8 * acc, acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quarter * 32) << 16);
+            const int row = m_blk * BLOCK_M + quarter * 32 + lane;
+            const int n_base = n_blk * BLOCK_N;
+            if constexpr (EPI == EPI_STORE) epi_store<BLOCK_N>(taddr, row, n_base, c0, c1, p);
+            else if constexpr (EPI == EPI_LSTM) epi_lstm<BLOCK_N>(taddr, row, n_base, c0, c1, p);
+            else if constexpr (EPI == EPI_GLU) epi_glu<BLOCK_N>(taddr, row, n_base, c0, c1, p);
+            else {
+                const int slot = (p.runs > 0 ? it.run : n_blk) * EPI_SPLIT + split;
+                if constexpr (EPI == EPI_TOPK) {
+                    if (first) tk.init();
+                    tk.tile(taddr, n_base, c0, c1, p);
+                    if (last) tk.flush(row, slot, p);
+                } else {
+                    if (first) sp.init(row, p);
+                    sp.tile(taddr, n_base, c0, c1, p);
+                    if (last) sp.flush(row, slot, p);
+                }
+            }
+            __syncwarp();
+            tc_fence_before();
+            if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar + 8 * acc, 0));
+            if (++acc == 2) acc = 0, acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();  // nobody frees TMEM / exits while the peer may still signal it
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
