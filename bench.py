@@ -33,17 +33,17 @@ UNIT = "captions/s"
 
 WORKLOADS = {
     # name: arch, model_type, regions, beam, images per GPU, description
-    # 1578 images x beam 3 = 4734 rows = 37 row tiles of 128: the gate GEMMs (16 column tiles) then fill exactly 4 waves of
-    # the 148 SMs and the dec_att GEMM exactly one
-    "butd_det": dict(arch="BUTD", model_type="BUTDDetection", R=36, beam=3, batch=1578,
+    # 1536 images x beam 3 = 4608 rows = 18 row blocks of 256 (one CTA pair each): the gate GEMMs (16 column tiles) are
+    # 288 pair tiles = 3.9 waves of the 74 SM pairs
+    "butd_det": dict(arch="BUTD", model_type="BUTDDetection", R=36, beam=3, batch=1536,
                      desc="BUTDDetection beam=3 eval, synthetic 36x2048 region feats, vocab 9487, random init "
                           "(BASELINE configs[0] model at a GPU-sized batch)"),
-    "butd_spatial": dict(arch="BUTD", model_type="BUTDSpatial", R=196, beam=5, batch=947,
+    "butd_spatial": dict(arch="BUTD", model_type="BUTDSpatial", R=196, beam=5, batch=921,
                          desc="BUTDSpatial beam=5 over a 14x14x2048 feature grid (configs[2], decoder only)"),
-    "nic": dict(arch="NIC", model_type="NIC", R=0, beam=3, batch=256,
+    "nic": dict(arch="NIC", model_type="NIC", R=0, beam=3, batch=1536,
                 desc="NIC LSTM decoder beam=3 on synthetic image embeddings (configs[1] without the ResNet-101 encoder)"),
-    "aoa": dict(arch="AOA", model_type="AoADetection", R=36, beam=3, batch=256,
-                desc="AoADetection 8-head AoA decoder beam=3, 256 images per GPU (configs[3] shard, refined feats synthetic)"),
+    "aoa": dict(arch="AOA", model_type="AoADetection", R=36, beam=3, batch=1536,
+                desc="AoADetection 8-head AoA decoder beam=3 (configs[3] per-GPU shard, refined feats synthetic)"),
 }
 
 
@@ -290,7 +290,7 @@ def run_gpu_arm(args, w):
     dom = max(gemm_ms, key=gemm_ms.get)
     dms, dfl, dcnt = prof[dom]
     achieved = dfl / (dms * 1e-3) / 1e12
-    roofline = {"kernel": f"capdec::gemm_kernel<256,{dom}>", "bound": "tensor", "achieved": achieved,
+    roofline = {"kernel": f"capdec::gemm2_kernel<{dom}> (tcgen05 cta_group::2, 256x256 tiles)", "bound": "tensor", "achieved": achieved,
                 "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
                 "traffic": None, "peak_source": peaks["source"] + ", sustained bf16 cuBLAS",
                 "flops_per_launch": dfl / dcnt, "us_per_launch": 1e3 * dms / dcnt,
