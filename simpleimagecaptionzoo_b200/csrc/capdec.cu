@@ -90,7 +90,7 @@ struct capdec_handle {
     double* scale_tmp = nullptr;
 
     // activations / workspace
-    Act16 feats16, enc16, mean16, XA, XB, Hb, Hb2, Xp, H0;
+    Act16 feats16, enc16, mean16, XA, XB, Hb, Hb2, Xp, H0, k16, v16, q16;
     float *enc_ctx = nullptr, *G0 = nullptr, *dec_ctx = nullptr, *kv32 = nullptr, *mean32 = nullptr, *q32 = nullptr,
           *ctx32 = nullptr, *h32 = nullptr, *c0 = nullptr;
     float* c1[2] = {nullptr, nullptr};
@@ -573,8 +573,38 @@ int launch_butd_att(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
     return launch_butd_att_t<KR, __half>(h, c, h->enc16.p, h->enc16.ld, h->feats16.p, h->feats16.ld, st);
 }
 
+bool aoa_mma_ok(const capdec_handle* h) {
+    const int d = h->NH > 0 ? h->H / h->NH : 0;
+    return !h->split && h->NH <= 8 && d % 16 == 0 && d <= 256 && h->att_variant != 1;
+}
+
+template <int KR>
+int launch_aoa_att_mma(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
+    static bool attr_set = false;
+    auto kern = aoa_attention_mma_kernel<KR>;
+    const size_t fixed = aoa_mma_fixed_smem(KR, h->R, h->H, h->NH);
+    const size_t stage_bytes = static_cast<size_t>(16) * h->k16.ld * 2;
+    int stages = static_cast<int>((226 * 1024 - fixed) / stage_bytes);
+    if (stages > 8) stages = 8;
+    if (stages < 2) return fail(h, CAPDEC_ERR_INVALID, "AoA attention ring does not fit shared memory");
+    const size_t smem = fixed + stages * stage_bytes;
+    if (!attr_set) {
+        CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const int grid = h->B < h->num_sms ? h->B : h->num_sms;
+    prof_begin(h, CAPDEC_CAT_ATTENTION, 0.0, st);
+    kern<<<grid, 288, smem, st>>>(h->k16.p, h->v16.p, h->k16.ld, static_cast<size_t>(h->B) * h->R, h->q16.p, h->q16.ld, h->mask, h->B,
+                                  h->R, h->H, h->NH, c.K, stages, h->XB.p, h->XB.ld);
+    prof_end(h, st);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    return CAPDEC_OK;
+}
+
 template <int KR>
 int launch_aoa_att(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
+    if (aoa_mma_ok(h)) return launch_aoa_att_mma<KR>(h, c, st);
     static bool attr_set = false;
     auto kern = aoa_attention_kernel<KR>;
     const size_t smem = (static_cast<size_t>(KR) * h->H + static_cast<size_t>(KR) * h->NH * h->R) * sizeof(float);
@@ -736,8 +766,13 @@ int step_aoa(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
         CKS(h, map_b(h, &mb, h->W_aux1));
         EpiParams e{};
         e.bias = h->b_aux1;
-        e.out32 = h->q32;
-        e.ld32 = H;
+        if (aoa_mma_ok(h)) {
+            e.out16 = h->q16.p;
+            e.ld16 = h->q16.ld;
+        } else {
+            e.out32 = h->q32;
+            e.ld32 = H;
+        }
         CKS(h, launch_gemm(h, EPI_STORE, 1, ma, h->XB.lo, mb, h->W_aux1.lo, c.M, H, H, e, st));
     }
     if (c.K <= 1) CKS(h, launch_aoa_att<1>(h, c, st));
@@ -919,7 +954,13 @@ static int create_impl(capdec_handle* h) {
         CKS(h, dalloc(h, &h->b_aux2, 2 * H));
         CKS(h, dalloc(h, &h->b_aux3, 2 * H));
         CKS(h, alloc_act(h, &h->feats16, static_cast<int>(BR), H));
-        CKS(h, dalloc(h, &h->kv32, BR * 2 * H));
+        if (aoa_mma_ok(h)) {
+            CKS(h, alloc_act(h, &h->k16, static_cast<int>(BR), H, 8));
+            CKS(h, alloc_act(h, &h->v16, static_cast<int>(BR), H, 8));
+            CKS(h, alloc_act(h, &h->q16, M, H));
+        } else {
+            CKS(h, dalloc(h, &h->kv32, BR * 2 * H));
+        }
         CKS(h, dalloc(h, &h->mean32, static_cast<size_t>(h->Bmax) * H));
         CKS(h, alloc_act(h, &h->XA, M, H + H));
         CKS(h, alloc_act(h, &h->XB, M, 2 * H));
@@ -1062,12 +1103,25 @@ int capdec_prepare(capdec_handle* h, const float* feats, const float* mask, int3
             CK(h, cudaGetLastError());
             h->launches += 2;
             CKS(h, map_a(h, &ma, h->feats16));
-            CKS(h, map_b(h, &mb, h->W_aux2));
-            EpiParams e{};
-            e.bias = h->b_aux2;
-            e.out32 = h->kv32;
-            e.ld32 = 2 * H;
-            CKS(h, launch_gemm(h, EPI_STORE, 1, ma, h->feats16.lo, mb, h->W_aux2.lo, static_cast<int>(BR), 2 * H, H, e, st));
+            if (aoa_mma_ok(h)) {  // fp16 K and V as separate row-padded matrices for the fragment kernel
+                for (int part = 0; part < 2; ++part) {
+                    CKS(h, make_map(h, &mb, h->W_aux2.p + static_cast<size_t>(part) * H * h->W_aux2.ld, H, h->W_aux2.ld, 0,
+                                    h->pair_gemm ? BN / 2 : BN));
+                    EpiParams e{};
+                    e.bias = h->b_aux2 + part * H;
+                    Act16& dst = part == 0 ? h->k16 : h->v16;
+                    e.out16 = dst.p;
+                    e.ld16 = dst.ld;
+                    CKS(h, launch_gemm(h, EPI_STORE, 1, ma, h->feats16.lo, mb, h->W_aux2.lo, static_cast<int>(BR), H, H, e, st));
+                }
+            } else {
+                CKS(h, map_b(h, &mb, h->W_aux2));
+                EpiParams e{};
+                e.bias = h->b_aux2;
+                e.out32 = h->kv32;
+                e.ld32 = 2 * H;
+                CKS(h, launch_gemm(h, EPI_STORE, 1, ma, h->feats16.lo, mb, h->W_aux2.lo, static_cast<int>(BR), 2 * H, H, e, st));
+            }
         }
         h->R = regions;
     }

@@ -971,6 +971,185 @@ __global__ void __launch_bounds__(256) aoa_attention_kernel(const float* __restr
     }
 }
 
+// ------------------------------------------------------------------------------------------------ AoA, fp16 fragment form
+// Multi-head attention of the AoA decoder on MMA fragments behind the same persistent bulk-copy ring as the BUTD
+// kernel (fp16 mode).  K and V projections are stored as separate fp16 matrices with padded rows (ld = H + 8).
+// One warp owns one head (heads <= 8, head dim a multiple of 16):
+//   phase 1  S[r, beam] = K[r, head, :] . Q[beam, head, :]   m16n8k16: A = K tile (ldmatrix), B = Q^T (beam = n)
+//   phase 2  softmax over regions per (beam, head), mask -> -1e9 before it (AoA_Model.py:62-65)
+//   phase 3  X[d, beam] = sum_r V[r, head, d] * P[beam, head, r]   A = V^T tile (ldmatrix.trans), B = P
+__host__ __device__ inline size_t aoa_mma_fixed_smem(int KR, int R, int H, int nh) {
+    const int rp = (R + 15) / 16 * 16;
+    return 2 * 8 * 8 /*bars*/ + static_cast<size_t>(8) * (H + 8) * 2 /*q16*/ + static_cast<size_t>(KR) * nh * rp * 4 /*scores*/ +
+           static_cast<size_t>(8) * nh * (rp + 8) * 2 /*p16*/ + static_cast<size_t>(rp) * 4 /*mask*/ + 128;
+}
+
+template <int KR>
+__global__ void __launch_bounds__(288, 1)
+aoa_attention_mma_kernel(const __half* __restrict__ k16, const __half* __restrict__ v16, int ld_kv, size_t total_rows,
+                         const __half* __restrict__ q16, int ld_q, const float* __restrict__ mask, int B, int R, int H, int nh,
+                         int K, int stages, __half* __restrict__ x16, int ld16) {
+    const int row_bytes = ld_kv * 2;
+    const int stage_bytes = 16 * row_bytes;
+    const int rp = (R + 15) / 16 * 16;
+    const int d = H / nh;
+    extern __shared__ __align__(128) uint8_t att_smem[];
+    uint8_t* smem = att_smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+    __half* s_q = reinterpret_cast<__half*>(bars + 16);                 // [8][H+8], rows >= K stay zero
+    float* s_s = reinterpret_cast<float*>(s_q + 8 * (H + 8));           // [KR][nh][rp]
+    __half* s_p = reinterpret_cast<__half*>(s_s + KR * nh * rp);        // [8][nh][rp+8], rows >= K stay zero
+    float* s_mask = reinterpret_cast<float*>(s_p + 8 * nh * (rp + 8));  // [rp]
+    const uint32_t full_bar = smem_u32(bars), empty_bar = smem_u32(bars + 8);
+    const uint32_t ring = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_chunks = (R + 15) / 16;
+
+    for (int i = threadIdx.x; i < stages * stage_bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < 8 * (H + 8) / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(s_q)[i] = 0u;
+    for (int i = threadIdx.x; i < 8 * nh * (rp + 8) / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(s_p)[i] = 0u;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(full_bar + 8 * s, 1);
+            mbar_init(empty_bar + 8 * s, 8);
+        }
+        fence_barrier_init();
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+
+    if (warp == 0) {
+        if (lane == 0) {  // producer: K chunks then V chunks of every image, one contiguous copy each
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int img = blockIdx.x; img < B; img += gridDim.x) {
+                for (int c = 0; c < 2 * n_chunks; ++c) {
+                    const bool kpart = c < n_chunks;
+                    const size_t row0 = static_cast<size_t>(img) * R + (kpart ? c : c - n_chunks) * 16;
+                    size_t nr = 16;
+                    if (row0 + nr > total_rows) nr = total_rows - row0;
+                    const uint32_t bytes = static_cast<uint32_t>(nr) * row_bytes;
+                    mbar_wait_lean(empty_bar + 8 * stage, phase ^ 1);
+                    mbar_arrive_expect_tx(full_bar + 8 * stage, bytes);
+                    bulk_load_1d(ring + stage * stage_bytes, (kpart ? k16 : v16) + row0 * ld_kv, bytes, full_bar + 8 * stage);
+                    if (++stage == stages) stage = 0, phase ^= 1;
+                }
+            }
+        }
+        return;
+    }
+
+    const int tid = threadIdx.x - 32, cw = warp - 1;
+    const int g = lane >> 2, t = lane & 3;
+    const bool has_head = cw < nh;
+    const int hd = cw;                              // this warp's head
+    const int nds = d >> 4;                         // 16-wide steps across the head dim (<= 16)
+    const float inv_sqrt_d = rsqrtf(static_cast<float>(d));
+    const uint32_t q_addr = smem_u32(s_q) + (g * (H + 8) + hd * d + 2 * t) * 2;            // + 32*ds (+16)
+    const uint32_t ld1_off = ((lane & 7) + ((lane >> 3) & 1) * 8) * row_bytes + (hd * d + (lane >> 4) * 8) * 2;  // + 32*ds
+    const uint32_t ld3_off = ((lane & 7) + ((lane >> 4) & 1) * 8) * row_bytes + (hd * d + ((lane >> 3) & 1) * 8) * 2;  // + 32*dt
+    const uint32_t p_addr = smem_u32(s_p) + ((g * nh + hd) * (rp + 8) + 2 * t) * 2;         // + 32*c (+16)
+    const int nq8 = K * H / 8;                      // uint4 vectors of this image's query rows
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int img = blockIdx.x; img < B; img += gridDim.x) {
+        for (int i = tid; i < nq8; i += 256) {
+            const int k = i / (H / 8), c8 = i - k * (H / 8);
+            *reinterpret_cast<uint4*>(s_q + k * (H + 8) + c8 * 8) =
+                __ldg(reinterpret_cast<const uint4*>(q16 + (static_cast<size_t>(img) * K + k) * ld_q) + c8);
+        }
+        for (int r = tid; r < rp; r += 256) s_mask[r] = (mask && r < R) ? mask[static_cast<size_t>(img) * R + r] : 1.f;
+        named_bar_sync(1, 256);
+        // ---------------- phase 1: scores
+        for (int c = 0; c < n_chunks; ++c) {
+            mbar_wait_lean(full_bar + 8 * stage, phase);
+            if (has_head) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                const uint32_t base1 = ring + stage * stage_bytes + ld1_off;
+#pragma unroll 4
+                for (int ds = 0; ds < nds; ++ds) {
+                    uint32_t x[4];
+                    ldmatrix_x4(x, base1 + 32 * ds);
+                    mma_m16n8k16_f16(acc, x[0], x[1], x[2], x[3], lds_b32(q_addr + 32 * ds), lds_b32(q_addr + 32 * ds + 16));
+                }
+                // c0/c1: region g, beams 2t/2t+1; c2/c3: region g+8
+                const int r0 = c * 16 + g, r1 = r0 + 8;
+                const float m0 = s_mask[r0], m1 = s_mask[r1];
+                if (2 * t < K) {
+                    s_s[((2 * t) * nh + hd) * rp + r0] = m0 == 0.f ? -1e9f : acc[0] * inv_sqrt_d;
+                    s_s[((2 * t) * nh + hd) * rp + r1] = m1 == 0.f ? -1e9f : acc[2] * inv_sqrt_d;
+                }
+                if (2 * t + 1 < K) {
+                    s_s[((2 * t + 1) * nh + hd) * rp + r0] = m0 == 0.f ? -1e9f : acc[1] * inv_sqrt_d;
+                    s_s[((2 * t + 1) * nh + hd) * rp + r1] = m1 == 0.f ? -1e9f : acc[3] * inv_sqrt_d;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar + 8 * stage);
+            if (++stage == stages) stage = 0, phase ^= 1;
+        }
+        named_bar_sync(1, 256);
+        // ---------------- phase 2: softmax over regions per (beam, head)
+        for (int kh = cw; kh < K * nh; kh += 8) {
+            float* sr = s_s + kh * rp;
+            float m = -INFINITY;
+            for (int r = lane; r < R; r += 32) m = fmaxf(m, sr[r]);
+            m = warp_max(m);
+            float sum = 0.f;
+            for (int r = lane; r < R; r += 32) {
+                const float ex = __expf(sr[r] - m);
+                sr[r] = ex;
+                sum += ex;
+            }
+            sum = warp_sum(sum);
+            const float inv = 1.0f / sum;
+            for (int r = lane; r < R; r += 32) s_p[kh * (rp + 8) + r] = __float2half_rn(sr[r] * inv);
+        }
+        named_bar_sync(1, 256);
+        // ---------------- phase 3: weighted value sum
+        float acc3[16][4];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc3[j][0] = acc3[j][1] = acc3[j][2] = acc3[j][3] = 0.f;
+        for (int c = 0; c < n_chunks; ++c) {
+            mbar_wait_lean(full_bar + 8 * stage, phase);
+            if (has_head) {
+                const uint32_t b0 = lds_b32(p_addr + 32 * c), b1 = lds_b32(p_addr + 32 * c + 16);
+                const uint32_t base3 = ring + stage * stage_bytes + ld3_off;
+#pragma unroll
+                for (int dt = 0; dt < 16; ++dt) {
+                    if (dt < nds) {
+                        uint32_t m4[4];
+                        ldmatrix_x4_trans(m4, base3 + 32 * dt);
+                        mma_m16n8k16_f16(acc3[dt], m4[0], m4[1], m4[2], m4[3], b0, b1);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar + 8 * stage);
+            if (++stage == stages) stage = 0, phase ^= 1;
+        }
+        if (has_head) {
+            __half* o0 = x16 + (static_cast<size_t>(img) * K + 2 * t) * ld16 + hd * d + g;
+            __half* o1 = o0 + ld16;
+            const bool b0ok = 2 * t < K, b1ok = 2 * t + 1 < K;
+#pragma unroll
+            for (int dt = 0; dt < 16; ++dt) {
+                if (dt < nds) {
+                    if (b0ok) {
+                        o0[16 * dt] = __float2half_rn(acc3[dt][0]);
+                        o0[16 * dt + 8] = __float2half_rn(acc3[dt][2]);
+                    }
+                    if (b1ok) {
+                        o1[16 * dt] = __float2half_rn(acc3[dt][1]);
+                        o1[16 * dt + 8] = __float2half_rn(acc3[dt][3]);
+                    }
+                }
+            }
+        }
+        named_bar_sync(1, 256);
+    }
+}
+
 // ================================================================================================ operand assembly
 // After the bookkeeping of a step every row's next GEMM operands are rebuilt: recurrent states are gathered
 // by parent row (the beam reorder of BUTD_Model.py:297-300), the chosen word is embedded (:264), AoA's

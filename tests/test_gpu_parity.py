@@ -147,6 +147,25 @@ def test_greedy_and_multinomial(name):
     dec.close()
 
 
+@pytest.mark.parametrize("env", [{"CAPDEC_GEMM_1CTA": "1"}, {"CAPDEC_ATT_VARIANT": "1"}, {"CAPDEC_ATT_VARIANT": "2"},
+                                 {"CAPDEC_NO_STREAM_ATTENTION": "1", "CAPDEC_ATT_VARIANT": "1"}])
+@pytest.mark.parametrize("name", ["butd_tiny_k3", "butd_full_k3"])
+def test_alternative_kernel_variants_match_golden(name, env, monkeypatch):
+    """The selectable kernel variants (single-CTA GEMM, FFMA / non-persistent attention) stay parity-green too."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    meta, gold = load_case(name)
+    for math in ("f16", "f16x3"):
+        dec, sd, feats, mask = _make(meta, math)
+        tok, score, _ = dec.beam_search(meta["K"], meta["T"])
+        torch.cuda.synchronize()
+        dec.close()
+        res = orc.beam_search_batched(_oracle(meta, sd, feats, mask), meta["K"], meta["T"])
+        verdict = orc.agreement(tok.cpu().numpy(), gold["tokens"], res.min_gap, tol=1e-4)
+        frac = np.mean([v != "diff" for v in verdict])
+        assert frac >= (1.0 if math == "f16x3" else 0.9), (math, env, verdict)
+
+
 def test_empty_and_ragged_inputs_are_rejected_cleanly():
     """Error behaviour of the C ABI: bad sizes come back as RuntimeError with a message, never a crash."""
     capdec = _capdec()

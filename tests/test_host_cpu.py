@@ -27,14 +27,20 @@ def test_build_produces_library_with_all_symbols():
 
 
 def test_sass_is_blackwell_native():
-    """tcgen05.mma / TMA / TMEM loads must be in the shipped SASS (UTCHMMA / UTMALDG / LDTM), no legacy HMMA."""
+    """tcgen05.mma (single-CTA and CTA-pair) / TMA / TMEM loads / bulk copies must be in the shipped SASS
+    (UTCHMMA[.2CTA] / UTMALDG / LDTM / UBLKCP).  The legacy warp-level HMMA path is allowed only inside the HBM-bound
+    attention kernel, never in a GEMM kernel."""
     from simpleimagecaptionzoo_b200 import capdec
     try:
         sass = subprocess.run(["cuobjdump", "-sass", capdec.LIB_PATH], capture_output=True, text=True, check=True).stdout
     except (FileNotFoundError, subprocess.CalledProcessError):
         pytest.skip("cuobjdump not available")
-    assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass
-    assert " HMMA" not in sass
+    assert "UTCHMMA.2CTA" in sass and "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass and "UBLKCP" in sass
+    funcs = re.split(r"\n\s*Function : ", sass)
+    gemm = [f for f in funcs if f.startswith("_ZN6capdec11gemm_kernel") or f.startswith("_ZN6capdec12gemm2_kernel")]
+    assert len(gemm) >= 12
+    for f in gemm:
+        assert "UTCHMMA" in f and " HMMA" not in f, f.split("\n", 1)[0]
 
 
 def test_create_fails_loudly_without_gpu():
