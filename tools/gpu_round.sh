@@ -13,7 +13,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-fil
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/ncu_list_${tag}.log 2>&1
 echo "ncu list rc=$?"
 # one decode step = 6 launches (TD-LSTM, dec_att, attention, LM-LSTM, logits, beam_step); skip warm-up decodes
-ncu --set full --clock-control none --import-source on -k regex:'gemm_kernel|attention|beam_step' -s 400 -c 6 -o gpurun_out/prof_${tag} -f \
+ncu --set full --clock-control none --import-source on -k regex:'gemm2_kernel|attention|beam_step' -s 380 -c 6 -o gpurun_out/prof_${tag} -f \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/ncu_full_${tag}.log 2>&1
 echo "ncu full rc=$?"
 ls -la gpurun_out | tail -8
