@@ -195,6 +195,7 @@ def run_gpu_arm(args, w):
         raise SystemExit("bench.py needs a CUDA device: the caption decoder has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_node = engine.bind_to_gpu_numa_node(local) if world > 1 else None  # NUMA-local pinned buffers per rank
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -317,6 +318,7 @@ def run_gpu_arm(args, w):
         "data": "synthetic",
         "config": {"workload": w["desc"], "images_per_gpu": B, "global_batch": n_total, "beam": K, "max_seq": T, "regions": R,
                    "vocab": dims["vocab_size"], "math": args.math, "parallelism": f"dp{world} (images sharded, one all-gather)",
+                   "host_numa_node": numa_node,
                    "l2": f"inputs larger than L2: {h2d / 1e6:.0f} MB of features + {sum(v.size for v in sd.values()) * 2 / 1e6:.0f} MB "
                          "of fp16 weights are re-read every step"},
         "clocks": clocks,

@@ -349,6 +349,36 @@ def install(engine, state_dict=None, **decoder_kwargs):
     return fast
 
 
+# ---------------------------------------------------------------------------------------------------- host placement
+def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
+    """Pin this process (and therefore the pinned host buffers it allocates afterwards, first-touch) to the NUMA node
+    the GPU hangs off, so that the per-batch host->device copies of the 8 ranks of a box do not cross sockets.
+    Returns the node, or None when the topology cannot be read (the call is then a no-op)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device_index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:  # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:  # noqa: BLE001  (topology files missing, NVML absent, ...)
+        return None
+
+
 # ---------------------------------------------------------------------------------------------------- multi-GPU
 def shard_bounds(n_images: int, rank: int, world: int):
     """Contiguous image shard of ``rank``: images are independent, K rows of an image stay together."""
