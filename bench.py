@@ -299,9 +299,13 @@ def run_gpu_arm(args, w):
     dom = max(gemm_ms, key=gemm_ms.get)
     dms, dfl, dcnt = prof[dom]
     achieved = dfl / (dms * 1e-3) / 1e12
+    traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (same workload)
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath) and args.workload == "butd_det" and B == WORKLOADS["butd_det"]["batch"] and args.math == "f16":
+        traffic = json.load(open(tpath)).get(dom, {}).get("mean_per_launch")
     roofline = {"kernel": f"capdec::gemm2_kernel<{dom}> (tcgen05 cta_group::2, 256x256 tiles)", "bound": "tensor", "achieved": achieved,
                 "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
-                "traffic": None, "peak_source": peaks["source"] + ", sustained bf16 cuBLAS",
+                "traffic": traffic, "peak_source": peaks["source"] + ", sustained bf16 cuBLAS",
                 "flops_per_launch": dfl / dcnt, "us_per_launch": 1e3 * dms / dcnt,
                 "share_of_step": dms / prof_steps / sum(v["ms_per_step"] for v in kern.values())}
     if "attention" in kern:  # HBM-bound companion kernel: algorithmic bytes = R*(A+D)*4 per image-step
