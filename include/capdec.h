@@ -103,17 +103,20 @@ int capdec_prepare(capdec_handle* h, const float* feats, const float* mask, int3
  *   tokens      [B, 1+max_seq] int32: <sta>=1 first, words, <end>=2 when completed, then <pad>=0
  *   seq_logprob [B] fp32 sum of log-probs of the emitted words        (may be NULL)
  *   lengths     [B] int32 valid entries of tokens incl. <sta>/<end>   (may be NULL)
- *   alphas      reserved, pass NULL */
+ *   alphas      [B, max_seq, R] fp32 attention map of the returned hypothesis at every step it took, zero rows after
+ *               its end (BUTD: softmax over regions, BUTD_Model.py:60; AoA: mean over heads, AoA_Model.py:119);
+ *               may be NULL; must be NULL for NIC */
 int capdec_beam_search(capdec_handle* h, int32_t beam, int32_t max_seq, int32_t* tokens, float* seq_logprob,
                        int32_t* lengths, float* alphas, void* stream);
 
 /* Greedy (``sample``) or multinomial (``sample_rl``) rollout, n_per_image rows per prepared image.
  *   tokens   [B*n_per_image, max_seq] int32 (no <sta>)
  *   logprobs [B*n_per_image, max_seq] fp32 log-prob of each stored word (multinomial; may be NULL for greedy)
+ *   alphas   [B*n_per_image, max_seq, R] fp32 attention maps (may be NULL; must be NULL for NIC)
  * The multinomial draw is the Gumbel-max form of torch.multinomial(exp(logprobs),1) with counter-based noise
  * keyed by (seed, row, step, word). */
 int capdec_sample(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t seed, int32_t max_seq, int32_t* tokens,
-                  float* logprobs, void* stream);
+                  float* logprobs, float* alphas, void* stream);
 
 /* Number of kernels the library launched on behalf of this handle since create (bench.py's gpu_launches). */
 int64_t capdec_launch_count(const capdec_handle* h);

@@ -557,6 +557,24 @@ def teacher_forced_logprobs(dec, seq_fed: np.ndarray, seq_scored: np.ndarray):
     return out
 
 
+def forced_alphas(dec, tokens: np.ndarray, lengths: np.ndarray) -> np.ndarray:
+    """Attention maps of given captions: replay ``tokens`` (B, 1+T; <sta> first) through the step function and
+    collect alpha at every step that generated a word (the reference returns this history from
+    beam_search_sample / sample: BUTD_Model.py:176,187,267,303-311; AoA head-mean :119).  Rows after a caption's
+    end are zero.  Returns (B, T, R)."""
+    B, L = tokens.shape
+    T = L - 1
+    st = dec.init_state(1)
+    out = None
+    for t in range(T):
+        _, st, alpha = dec.step(tokens[:, t:t + 1].astype(np.int64), st)
+        if out is None:
+            out = np.zeros((B, T, alpha.shape[-1]), f32)
+        live = (t + 1) < lengths  # position t+1 holds a generated word
+        out[live, t] = alpha[live, 0]
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------
 # the eval driver's id -> word loop
 # ---------------------------------------------------------------------------------------------------

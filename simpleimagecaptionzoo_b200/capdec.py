@@ -58,7 +58,7 @@ def load_library(path: str = LIB_PATH) -> ctypes.CDLL:
     lib.capdec_finalize_weights.argtypes = [vp, vp]
     lib.capdec_prepare.argtypes = [vp, vp, vp, i32, i32, vp]
     lib.capdec_beam_search.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
-    lib.capdec_sample.argtypes = [vp, i32, i32, ctypes.c_uint64, i32, vp, vp, vp]
+    lib.capdec_sample.argtypes = [vp, i32, i32, ctypes.c_uint64, i32, vp, vp, vp, vp]
     lib.capdec_launch_count.argtypes = [vp]
     lib.capdec_launch_count.restype = i64
     lib.capdec_test_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
@@ -139,7 +139,7 @@ class CaptionDecoder:
             raise RuntimeError(f"capdec_create failed ({rc}): {self.lib.capdec_last_error(None).decode()}")
         self._h = handle
         self._keep = None
-        self.B = 0
+        self.B, self.R = 0, 0
         self._load(state_dict)
 
     # ------------------------------------------------------------------ plumbing
@@ -208,27 +208,32 @@ class CaptionDecoder:
             self._check(self.lib.capdec_prepare(self._h, feats.data_ptr(), None if mask is None else mask.data_ptr(), B, R,
                                                 _stream_ptr(self.device)), "capdec_prepare")
         self._keep = (feats, mask)  # the library reads them during decode
-        self.B = B
+        self.B, self.R = B, R
 
-    def beam_search(self, beam: int, max_seq: int = 20):
-        """-> tokens [B,1+max_seq] int32 (<sta> first), seq_logprob [B] fp32, lengths [B] int32 (CUDA tensors)."""
+    def beam_search(self, beam: int, max_seq: int = 20, return_alphas: bool = False):
+        """-> tokens [B,1+max_seq] int32 (<sta> first), seq_logprob [B] fp32, lengths [B] int32 (CUDA tensors)
+        [, alphas [B,max_seq,R] fp32 attention maps of the returned hypotheses]."""
         torch = _torch()
         B = self.B
         tokens = torch.empty((B, 1 + max_seq), dtype=torch.int32, device=self.device)
         scores = torch.empty((B,), dtype=torch.float32, device=self.device)
         lengths = torch.empty((B,), dtype=torch.int32, device=self.device)
+        alphas = torch.empty((B, max_seq, self.R), dtype=torch.float32, device=self.device) if return_alphas else None
         with torch.cuda.device(self.device):
             self._check(self.lib.capdec_beam_search(self._h, beam, max_seq, tokens.data_ptr(), scores.data_ptr(),
-                                                    lengths.data_ptr(), None, _stream_ptr(self.device)), "capdec_beam_search")
-        return tokens, scores, lengths
+                                                    lengths.data_ptr(), alphas.data_ptr() if return_alphas else None,
+                                                    _stream_ptr(self.device)), "capdec_beam_search")
+        return (tokens, scores, lengths, alphas) if return_alphas else (tokens, scores, lengths)
 
-    def sample(self, mode: int, n_per_image: int = 1, seed: int = 0, max_seq: int = 20):
-        """-> tokens [B*n,max_seq] int32, logprobs [B*n,max_seq] fp32 (CUDA tensors)."""
+    def sample(self, mode: int, n_per_image: int = 1, seed: int = 0, max_seq: int = 20, return_alphas: bool = False):
+        """-> tokens [B*n,max_seq] int32, logprobs [B*n,max_seq] fp32 (CUDA tensors) [, alphas [B*n,max_seq,R] fp32]."""
         torch = _torch()
         M = self.B * n_per_image
         tokens = torch.empty((M, max_seq), dtype=torch.int32, device=self.device)
         logprobs = torch.empty((M, max_seq), dtype=torch.float32, device=self.device)
+        alphas = torch.zeros((M, max_seq, self.R), dtype=torch.float32, device=self.device) if return_alphas else None
         with torch.cuda.device(self.device):
-            self._check(self.lib.capdec_sample(self._h, mode, n_per_image, seed, max_seq, tokens.data_ptr(),
-                                               logprobs.data_ptr(), _stream_ptr(self.device)), "capdec_sample")
-        return tokens, logprobs
+            self._check(self.lib.capdec_sample(self._h, mode, n_per_image, seed, max_seq, tokens.data_ptr(), logprobs.data_ptr(),
+                                               alphas.data_ptr() if return_alphas else None, _stream_ptr(self.device)),
+                        "capdec_sample")
+        return (tokens, logprobs, alphas) if return_alphas else (tokens, logprobs)

@@ -100,6 +100,8 @@ struct capdec_handle {
         *live_count = nullptr;
     int* seqs[2] = {nullptr, nullptr};
     float *cum = nullptr, *best_score = nullptr;
+    float* alpha_step = nullptr;  // [Tmax, Mmax, Rmax] per-step attention maps (allocated on first request)
+    int *hist_parent = nullptr, *best_pslot = nullptr;
 };
 
 namespace {
@@ -471,6 +473,8 @@ struct StepCtx {
     uint32_t seed = 0;
     int use_noise = 0;
     bool first_from_c0 = false;
+    float* alphas = nullptr;  // where this step's attention maps go ([row * alpha_stride + region]) or null
+    size_t alpha_stride = 0;
 };
 
 int run_logits(capdec_handle* h, const Act16& a, const StepCtx& c, cudaStream_t st) {
@@ -499,7 +503,7 @@ int launch_butd_att_t(capdec_handle* h, const StepCtx& c, const T* enc, int enc_
     if (smem > 160 * 1024) return fail(h, CAPDEC_ERR_INVALID, "attention tile does not fit shared memory");
     prof_begin(h, CAPDEC_CAT_ATTENTION, 0.0, st);
     kern<<<h->B, 256, smem, st>>>(enc, enc_ld, feats, feats_ld, h->dec_ctx, h->w_aff, h->b_aff, h->R, h->A, h->D, c.K, h->XB.p, h->XB.ld,
-                                  h->XB.lo, nullptr);
+                                  h->XB.lo, c.alphas, c.alpha_stride);
     prof_end(h, st);
     CK(h, cudaGetLastError());
     h->launches++;
@@ -522,7 +526,7 @@ int launch_butd_att_stream_t(capdec_handle* h, const StepCtx& c, const T* enc, c
     const int grid = h->B < h->num_sms * per_sm ? h->B : h->num_sms * per_sm;
     prof_begin(h, CAPDEC_CAT_ATTENTION, 0.0, st);
     kern<<<grid, C::THREADS, smem, st>>>(enc, feats, h->dec_ctx, h->w_aff, h->b_aff, h->B, h->R, h->A, h->D, c.K, h->XB.p, h->XB.ld,
-                                         h->XB.lo);
+                                         h->XB.lo, c.alphas, c.alpha_stride);
     prof_end(h, st);
     CK(h, cudaGetLastError());
     h->launches++;
@@ -544,7 +548,8 @@ int launch_butd_att_mma_t(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
     const int grid = h->B < cap ? h->B : cap;
     prof_begin(h, CAPDEC_CAT_ATTENTION, 0.0, st);
     kern<<<grid, C::THREADS, smem, st>>>(h->enc16.p, h->enc16.ld, h->feats16.p, h->feats16.ld, static_cast<size_t>(h->B) * h->R,
-                                         h->dec_ctx, h->w_aff, h->b_aff, h->B, h->R, h->A, h->D, c.K, h->XB.p, h->XB.ld);
+                                         h->dec_ctx, h->w_aff, h->b_aff, h->B, h->R, h->A, h->D, c.K, h->XB.p, h->XB.ld, c.alphas,
+                                         c.alpha_stride);
     prof_end(h, st);
     CK(h, cudaGetLastError());
     h->launches++;
@@ -595,7 +600,7 @@ int launch_aoa_att_mma(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
     const int grid = h->B < h->num_sms ? h->B : h->num_sms;
     prof_begin(h, CAPDEC_CAT_ATTENTION, 0.0, st);
     kern<<<grid, 288, smem, st>>>(h->k16.p, h->v16.p, h->k16.ld, static_cast<size_t>(h->B) * h->R, h->q16.p, h->q16.ld, h->mask, h->B,
-                                  h->R, h->H, h->NH, c.K, stages, h->XB.p, h->XB.ld);
+                                  h->R, h->H, h->NH, c.K, stages, h->XB.p, h->XB.ld, c.alphas, c.alpha_stride);
     prof_end(h, st);
     CK(h, cudaGetLastError());
     h->launches++;
@@ -614,7 +619,8 @@ int launch_aoa_att(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
     }
     if (smem > 160 * 1024) return fail(h, CAPDEC_ERR_INVALID, "attention tile does not fit shared memory");
     prof_begin(h, CAPDEC_CAT_ATTENTION, 0.0, st);
-    kern<<<h->B, 256, smem, st>>>(h->q32, h->kv32, h->mask, h->R, h->H, h->NH, c.K, h->XB.p, h->XB.ld, h->XB.lo);
+    kern<<<h->B, 256, smem, st>>>(h->q32, h->kv32, h->mask, h->R, h->H, h->NH, c.K, h->XB.p, h->XB.ld, h->XB.lo, c.alphas,
+                                  c.alpha_stride);
     prof_end(h, st);
     CK(h, cudaGetLastError());
     h->launches++;
@@ -1138,8 +1144,13 @@ int capdec_beam_search(capdec_handle* h, int32_t beam, int32_t max_seq, int32_t*
     if (!h->prepared) return fail(h, CAPDEC_ERR_STATE, "capdec_beam_search before capdec_prepare");
     if (beam <= 0 || beam > h->Kmax || max_seq <= 0 || max_seq > h->Tmax || !tokens)
         return fail(h, CAPDEC_ERR_INVALID, "beam_search: beam / max_seq out of range or null tokens");
-    if (alphas) return fail(h, CAPDEC_ERR_INVALID, "alphas output is reserved; pass NULL");
+    if (alphas && h->cfg.arch == CAPDEC_ARCH_NIC) return fail(h, CAPDEC_ERR_INVALID, "NIC has no attention maps; pass alphas = NULL");
     if (static_cast<int64_t>(beam) * h->V < beam) return fail(h, CAPDEC_ERR_INVALID, "beam larger than vocabulary");
+    if (alphas && !h->alpha_step) {  // first request: history buffers (not part of the steady-state workspace)
+        CKS(h, dalloc(h, &h->alpha_step, static_cast<size_t>(h->Tmax) * h->Mmax * h->Rmax));
+        CKS(h, dalloc(h, &h->hist_parent, static_cast<size_t>(h->Tmax) * h->Mmax));
+        CKS(h, dalloc(h, &h->best_pslot, h->Bmax));
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(h, cudaSetDevice(h->cfg.device));
     const int B = h->B, K = beam, M = B * K;
@@ -1149,6 +1160,8 @@ int capdec_beam_search(capdec_handle* h, int32_t beam, int32_t max_seq, int32_t*
     s.tok = h->tok, s.cum = h->cum, s.parent = h->parent, s.n_live = h->n_live;
     s.best_score = h->best_score, s.best_seq = h->best_seq, s.best_len = h->best_len;
     s.seqs_in = h->seqs[0], s.seqs_out = h->seqs[1];
+    s.hist_parent = alphas ? h->hist_parent : nullptr;
+    s.best_pslot = alphas ? h->best_pslot : nullptr;
     const bool nic = h->cfg.arch == CAPDEC_ARCH_NIC;
     // NIC: step 1 reads the primed cell state of the image, so parent[row] starts as the image index into c0
     if (K <= 1) beam_init_kernel<1><<<B, 128, 0, st>>>(s, adv_ops(h, true), nic ? 1 : 0);
@@ -1165,6 +1178,8 @@ int capdec_beam_search(capdec_handle* h, int32_t beam, int32_t max_seq, int32_t*
         c.t = t;
         c.cur = (t - 1) & 1;
         c.first_from_c0 = nic && t == 1;
+        c.alphas = alphas ? h->alpha_step + static_cast<size_t>(t - 1) * M * h->R : nullptr;
+        c.alpha_stride = h->R;
         CKS(h, run_step(h, c, st));
         s.seqs_in = h->seqs[(t + 1) & 1];
         s.seqs_out = h->seqs[t & 1];
@@ -1178,19 +1193,20 @@ int capdec_beam_search(capdec_handle* h, int32_t beam, int32_t max_seq, int32_t*
         CK(h, cudaGetLastError());
         h->launches++;
     }
-    beam_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(s, h->seqs[max_seq & 1], tokens, seq_logprob, lengths);
+    beam_finalize_kernel<<<(B + 3) / 4, 128, 0, st>>>(s, h->seqs[max_seq & 1], tokens, seq_logprob, lengths, h->alpha_step, alphas, h->R);
     CK(h, cudaGetLastError());
     h->launches++;
     return CAPDEC_OK;
 }
 
 int capdec_sample(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t seed, int32_t max_seq, int32_t* tokens,
-                  float* logprobs, void* stream) {
+                  float* logprobs, float* alphas, void* stream) {
     if (!h) return CAPDEC_ERR_INVALID;
     if (!h->prepared) return fail(h, CAPDEC_ERR_STATE, "capdec_sample before capdec_prepare");
     if (n_per_image <= 0 || n_per_image > h->Kmax || max_seq <= 0 || max_seq > h->Tmax || !tokens)
         return fail(h, CAPDEC_ERR_INVALID, "sample: n_per_image / max_seq out of range or null tokens");
     if (mode != CAPDEC_SAMPLE_GREEDY && mode != CAPDEC_SAMPLE_MULTINOMIAL) return fail(h, CAPDEC_ERR_INVALID, "unknown sample mode");
+    if (alphas && h->cfg.arch == CAPDEC_ARCH_NIC) return fail(h, CAPDEC_ERR_INVALID, "NIC has no attention maps; pass alphas = NULL");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(h, cudaSetDevice(h->cfg.device));
     const int B = h->B, n = n_per_image, M = B * n;
@@ -1219,6 +1235,8 @@ int capdec_sample(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t 
         c.t = t;
         c.cur = (t - 1) & 1;
         c.first_from_c0 = nic && t == 1;
+        c.alphas = alphas ? alphas + static_cast<size_t>(t - 1) * h->R : nullptr;  // [row, t, region]
+        c.alpha_stride = static_cast<size_t>(max_seq) * h->R;
         CKS(h, run_step(h, c, st));
         prof_begin(h, CAPDEC_CAT_BOOKKEEPING, 0.0, st);
         if (n <= 1) sample_step_kernel<1><<<B, 128, 0, st>>>(h->part, n_slots, s, t - 1, ops);

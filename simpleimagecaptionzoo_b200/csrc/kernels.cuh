@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(256) butd_attention_kernel(const T* __restrict
                                                              int feats_ld, const float* __restrict__ dec_ctx,
                                                              const float* __restrict__ w_aff, float b_aff, int R, int A, int D,
                                                              int K, __half* __restrict__ ctx16, int ld16, int lo16,
-                                                             float* __restrict__ alphas_out) {
+                                                             float* __restrict__ alphas_out, size_t alpha_stride) {
     using C = AttCfg<KR>;
     constexpr int GR = C::GR, NV = C::NV, NP = C::NP, LB = C::LB;
     extern __shared__ float sm[];
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(256) butd_attention_kernel(const T* __restrict
         for (int r = lane; r < R; r += 32) {
             const float al = s_e[k * R + r] / s;
             s_e[k * R + r] = al;
-            if (alphas_out) alphas_out[(static_cast<size_t>(img) * K + k) * R + r] = al;
+            if (alphas_out) alphas_out[(static_cast<size_t>(img) * K + k) * alpha_stride + r] = al;
         }
     }
     __syncthreads();
@@ -378,7 +378,7 @@ template <int KR, typename T>
 __global__ void __launch_bounds__(288, AttStreamCfg<KR, T>::CTAS_PER_SM)
 butd_attention_stream_kernel(const T* __restrict__ enc_ctx, const T* __restrict__ feats, const float* __restrict__ dec_ctx,
                              const float* __restrict__ w_aff, float b_aff, int B, int R, int A, int D, int K,
-                             __half* __restrict__ ctx16, int ld16, int lo16) {
+                             __half* __restrict__ ctx16, int ld16, int lo16, float* __restrict__ alphas_out, size_t alpha_stride) {
     using C = AttStreamCfg<KR, T>;
     constexpr int GR = C::GR, NV = C::NV, NP = C::NP, RC3 = C::RC3, STAGES = C::STAGES;
     extern __shared__ uint8_t att_smem_raw[];
@@ -515,7 +515,11 @@ butd_attention_stream_kernel(const T* __restrict__ enc_ctx, const T* __restrict_
                 s += ex;
             }
             s = warp_sum(s);
-            for (int r = lane; r < R; r += 32) s_e[k * R + r] = s_e[k * R + r] / s;
+            for (int r = lane; r < R; r += 32) {
+                const float al = s_e[k * R + r] / s;
+                s_e[k * R + r] = al;
+                if (alphas_out) alphas_out[(static_cast<size_t>(img) * K + k) * alpha_stride + r] = al;
+            }
         }
         named_bar_sync(1, 256);
         // ---------------- phase 3: weighted feature sum, one ring stage per RC3 regions
@@ -621,7 +625,8 @@ template <int KR, int CTAS>
 __global__ void __launch_bounds__(288, CTAS)
 butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __half* __restrict__ feats16, int ld_feats,
                           size_t total_rows, const float* __restrict__ dec_ctx, const float* __restrict__ w_aff, float b_aff, int B,
-                          int R, int A, int D, int K, __half* __restrict__ ctx16, int ld16) {
+                          int R, int A, int D, int K, __half* __restrict__ ctx16, int ld16, float* __restrict__ alphas_out,
+                          size_t alpha_stride) {
     constexpr int STAGES = AttMmaCfg<KR, CTAS>::STAGES;
     const AttMmaShape sh = att_mma_shape(R, ld_enc, ld_feats);
     extern __shared__ __align__(128) uint8_t att_smem[];
@@ -774,7 +779,11 @@ butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __
             }
             s = warp_sum(s);
             const float inv = 1.0f / s;
-            for (int r = lane; r < R; r += 32) s_alpha[k * (sh.rp + 8) + r] = __float2half_rn(s_e[k * sh.rp + r] * inv);
+            for (int r = lane; r < R; r += 32) {
+                const float al = s_e[k * sh.rp + r] * inv;
+                s_alpha[k * (sh.rp + 8) + r] = __float2half_rn(al);
+                if (alphas_out) alphas_out[(static_cast<size_t>(img) * K + k) * alpha_stride + r] = al;
+            }
         }
         named_bar_sync(1, 256);
         // ---------------- phase 3: ctx = alpha * feats
@@ -856,7 +865,8 @@ __global__ void aoa_layernorm_kernel(const float* __restrict__ h, int M, int H, 
 template <int KR>
 __global__ void __launch_bounds__(256) aoa_attention_kernel(const float* __restrict__ q, const float* __restrict__ kv,
                                                             const float* __restrict__ mask, int R, int H, int nh, int K,
-                                                            __half* __restrict__ x16, int ld16, int lo16) {
+                                                            __half* __restrict__ x16, int ld16, int lo16,
+                                                            float* __restrict__ alphas_out, size_t alpha_stride) {
     extern __shared__ float sm[];
     float* s_q = sm;               // [KR][H]
     float* s_p = s_q + KR * H;     // [KR][nh][R]
@@ -937,6 +947,14 @@ __global__ void __launch_bounds__(256) aoa_attention_kernel(const float* __restr
         for (int r = lane; r < R; r += 32) p[r] = p[r] / s;
     }
     __syncthreads();
+    if (alphas_out) {  // mean over heads (AoA_Model.py:119)
+        for (int i = tid; i < K * R; i += blockDim.x) {
+            const int k = i / R, r = i - k * R;
+            float a = 0.f;
+            for (int hh = 0; hh < nh; ++hh) a += s_p[(k * nh + hh) * R + r];
+            alphas_out[(static_cast<size_t>(img) * K + k) * alpha_stride + r] = a / static_cast<float>(nh);
+        }
+    }
 
     for (int i = tid; i < nf4; i += blockDim.x) {
         const int hd = i / G;
@@ -988,7 +1006,8 @@ template <int KR>
 __global__ void __launch_bounds__(288, 1)
 aoa_attention_mma_kernel(const __half* __restrict__ k16, const __half* __restrict__ v16, int ld_kv, size_t total_rows,
                          const __half* __restrict__ q16, int ld_q, const float* __restrict__ mask, int B, int R, int H, int nh,
-                         int K, int stages, __half* __restrict__ x16, int ld16) {
+                         int K, int stages, __half* __restrict__ x16, int ld16, float* __restrict__ alphas_out,
+                         size_t alpha_stride) {
     const int row_bytes = ld_kv * 2;
     const int stage_bytes = 16 * row_bytes;
     const int rp = (R + 15) / 16 * 16;
@@ -1103,9 +1122,21 @@ aoa_attention_mma_kernel(const __half* __restrict__ k16, const __half* __restric
             }
             sum = warp_sum(sum);
             const float inv = 1.0f / sum;
-            for (int r = lane; r < R; r += 32) s_p[kh * (rp + 8) + r] = __float2half_rn(sr[r] * inv);
+            for (int r = lane; r < R; r += 32) {
+                const float pr = sr[r] * inv;
+                sr[r] = pr;
+                s_p[kh * (rp + 8) + r] = __float2half_rn(pr);
+            }
         }
         named_bar_sync(1, 256);
+        if (alphas_out) {  // attention map returned by the reference: mean over heads (AoA_Model.py:119)
+            for (int i = tid; i < K * R; i += 256) {
+                const int k = i / R, r = i - k * R;
+                float a = 0.f;
+                for (int hh = 0; hh < nh; ++hh) a += s_s[(k * nh + hh) * rp + r];
+                alphas_out[(static_cast<size_t>(img) * K + k) * alpha_stride + r] = a / static_cast<float>(nh);
+            }
+        }
         // ---------------- phase 3: weighted value sum
         float acc3[16][4];
 #pragma unroll
@@ -1253,6 +1284,8 @@ struct BeamState {
     float* best_score; // [B] best COMPLETED hypothesis so far (-inf = none)
     int* best_seq;     // [B, T+1]
     int* best_len;     // [B]
+    int* hist_parent;  // [T, B*K] parent SLOT of every slot at every step (attention-map backtracking) or null
+    int* best_pslot;   // [B] parent slot of the best completed hypothesis at its last step
 };
 
 // t = 0: initial state (all K slots <sta>, cum 0; BUTD_Model.py:247-250); no partials are read.
@@ -1376,6 +1409,7 @@ __global__ void __launch_bounds__(128) beam_step_kernel(const float* __restrict_
                     bs[t] = TOK_END;
                     for (int i = t + 1; i < L; ++i) bs[i] = TOK_PAD;
                     s.best_len[img] = t + 1;
+                    if (s.best_pslot) s.best_pslot[img] = br;
                 }
             } else {
                 for (int i = 0; i < t; ++i) sout[n_new * L + i] = sin[br * L + i];
@@ -1398,22 +1432,42 @@ __global__ void __launch_bounds__(128) beam_step_kernel(const float* __restrict_
     if (threadIdx.x < K) {
         s.parent[img * K + threadIdx.x] = s_parent[threadIdx.x];
         s.tok[img * K + threadIdx.x] = s_tok[threadIdx.x];
+        if (s.hist_parent) s.hist_parent[static_cast<size_t>(t - 1) * s.B * K + img * K + threadIdx.x] = s_parent[threadIdx.x] - img * K;
     }
     advance_image<KR>(ops, img, K, s_parent, s_tok, threadIdx.x, blockDim.x);
 }
 
 // Result selection (BUTD_Model.py:306-315): the best COMPLETED hypothesis if any, else live slot 0 (slots stay
 // sorted by score).  seqs = the buffer written by the last step.
+// alphas_out [B, T, R]: attention map of the returned hypothesis at every step it took (zero rows after its end),
+// reconstructed by walking the per-step parent slots back from its last step (the reference reorders a per-beam
+// alpha history instead, BUTD_Model.py:280-281,303).  One warp per image.
 __global__ void beam_finalize_kernel(BeamState s, const int* __restrict__ seqs, int* __restrict__ tokens,
-                                     float* __restrict__ seq_logprob, int* __restrict__ lengths) {
-    const int img = blockIdx.x * blockDim.x + threadIdx.x;
+                                     float* __restrict__ seq_logprob, int* __restrict__ lengths,
+                                     const float* __restrict__ alpha_step, float* __restrict__ alphas_out, int R) {
+    const int img = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (img >= s.B) return;
     const int L = s.T + 1;
     const bool done = s.best_score[img] > -INFINITY;
     const int* src = done ? s.best_seq + static_cast<size_t>(img) * L : seqs + static_cast<size_t>(img) * s.K * L;
-    for (int i = 0; i < L; ++i) tokens[static_cast<size_t>(img) * L + i] = src[i];
-    if (seq_logprob) seq_logprob[img] = done ? s.best_score[img] : s.cum[img * s.K];
-    if (lengths) lengths[img] = done ? s.best_len[img] : L;
+    for (int i = lane; i < L; i += 32) tokens[static_cast<size_t>(img) * L + i] = src[i];
+    if (lane == 0) {
+        if (seq_logprob) seq_logprob[img] = done ? s.best_score[img] : s.cum[img * s.K];
+        if (lengths) lengths[img] = done ? s.best_len[img] : L;
+    }
+    if (alphas_out) {
+        const size_t MK = static_cast<size_t>(s.B) * s.K;
+        int t_end = done ? s.best_len[img] - 1 : s.T;        // number of generated words
+        int cur = done ? s.best_pslot[img] : s.hist_parent[static_cast<size_t>(s.T - 1) * MK + img * s.K];  // live slot 0
+        for (int t = s.T; t > t_end; --t)
+            for (int r = lane; r < R; r += 32) alphas_out[(static_cast<size_t>(img) * s.T + t - 1) * R + r] = 0.f;
+        for (int t = t_end; t >= 1; --t) {
+            const float* a = alpha_step + (static_cast<size_t>(t - 1) * MK + img * s.K + cur) * R;
+            for (int r = lane; r < R; r += 32) alphas_out[(static_cast<size_t>(img) * s.T + t - 1) * R + r] = a[r];
+            if (t > 1) cur = s.hist_parent[static_cast<size_t>(t - 2) * MK + img * s.K + cur];
+        }
+    }
 }
 
 // ================================================================================================ sampling

@@ -181,6 +181,30 @@ class B200Captioner:
         tokens, _ = self.decoder.sample(capdec.SAMPLE_GREEDY, 1, 0, max_len)
         return tokens.long()
 
+    def eval_test_image(self, visual_inputs, caption_vocab, max_len: int = 20, eval_beam_size: int = -1):
+        """Single-image test path (``eval_test_image``, BUTD_Model.py:518-544 / AoA_Model.py:755-786 / NIC_Model.py:306-332):
+        -> (caption words, [alphas]) with alphas (1, n_words, R) -- the attention map per generated word that
+        ``show_additional_rlt`` plots -- or (caption, []) for NIC."""
+        feats, mask = self._features(visual_inputs)
+        assert feats.shape[0] == 1
+        self.decoder.prepare(feats, mask)
+        want = self.arch != "NIC"
+        if eval_beam_size != -1:
+            out = self.decoder.beam_search(eval_beam_size, self.max_seq, return_alphas=want)
+            tokens, lengths = out[0], out[2]
+            n_words = int(lengths[0]) - 1
+        else:
+            out = self.decoder.sample(capdec.SAMPLE_GREEDY, 1, 0, max_len, return_alphas=want)
+            tokens, n_words = out[0], max_len
+        caption = []
+        for word_id in tokens[0].cpu().numpy():
+            word = caption_vocab.ix2word[int(word_id)]
+            if word == END_WORD:
+                break
+            if word != STA_WORD:
+                caption.append(word)
+        return caption, ([out[-1][:, :n_words]] if want else [])
+
     def sampler_rl(self, visual_inputs, max_len: int = 20, n_per_image: int = 1, seed: Optional[int] = None):
         """Multinomial rollout (eval-mode numerics; forward only -- the SCST backward pass is out of scope).
         ``n_per_image`` > 1 draws several samples per image while reading its features once (BASELINE config 5)."""
@@ -346,6 +370,7 @@ def install(engine, state_dict=None, **decoder_kwargs):
     fast = B200Captioner(model_type, engine.settings, len(engine.caption_vocab), sd, feature_fn=feature_fn,
                          device=int(dev.split(":")[1]) if ":" in dev else 0, **decoder_kwargs)
     ref.sampler, ref.sampler_rl, ref.beam_search_sampler = fast.sampler, fast.sampler_rl, fast.beam_search_sampler
+    ref.eval_test_image = fast.eval_test_image
     return fast
 
 

@@ -166,6 +166,63 @@ def test_alternative_kernel_variants_match_golden(name, env, monkeypatch):
         assert frac >= (1.0 if math == "f16x3" else 0.9), (math, env, verdict)
 
 
+@pytest.mark.parametrize("name", ["butd_tiny_k3", "butd_tiny_k5", "aoa_tiny_k3", "aoa_tiny_k3_masked", "butd_full_k3", "aoa_full_k3"])
+@pytest.mark.parametrize("math", ["f16x3", "f16"])
+def test_attention_maps(name, math):
+    """alphas of the returned hypothesis (beam: per-step maps walked back through the parent slots; greedy: direct)
+    against a replay of the same caption through the oracle's step function."""
+    capdec = _capdec()
+    meta, gold = load_case(name)
+    dec, sd, feats, mask = _make(meta, math)
+    tok, _, length, alphas = dec.beam_search(meta["K"], meta["T"], return_alphas=True)
+    gtok, _, galphas = dec.sample(capdec.SAMPLE_GREEDY, 1, 0, meta["T"], return_alphas=True)
+    torch.cuda.synchronize()
+    tok, length, alphas = tok.cpu().numpy(), length.cpu().numpy(), alphas.cpu().numpy()
+    gtok, galphas = gtok.cpu().numpy(), galphas.cpu().numpy()
+    dec.close()
+    o = _oracle(meta, sd, feats, mask)
+    tol = 2e-3 if math == "f16x3" else 3e-2
+    want = orc.forced_alphas(o, tok, length)
+    assert alphas.shape == want.shape
+    assert np.abs(alphas - want).max() <= tol, np.abs(alphas - want).max()
+    for b in range(meta["B"]):  # rows after the caption's end are zero; rows before it are distributions
+        n = length[b] - 1
+        assert np.all(alphas[b, n:] == 0)
+        assert np.allclose(alphas[b, :n].sum(-1), 1.0, atol=2e-3)
+    gfull = np.concatenate([np.full((meta["B"], 1), orc.STA, np.int32), gtok], 1)
+    gwant = orc.forced_alphas(o, gfull, np.full(meta["B"], meta["T"] + 1))
+    assert np.abs(galphas - gwant).max() <= tol
+
+
+def test_nic_has_no_attention_maps():
+    meta, _ = load_case("nic_tiny_k3")
+    dec, *_ = _make(meta, "f16")
+    with pytest.raises(RuntimeError, match="attention maps"):
+        dec.beam_search(meta["K"], meta["T"], return_alphas=True)
+    dec.close()
+
+
+def test_eval_test_image_mirror():
+    """Engine.test's model call: (caption words, [alphas (1, n_words, R)])."""
+    from simpleimagecaptionzoo_b200 import engine
+    meta, gold = load_case("butd_tiny_k3")
+    sd, feats, _ = rebuild(meta)
+    d = meta["dims"]
+
+    class Vocab:
+        ix2word = {0: "<pad>", 1: "<sta>", 2: "<end>", 3: "<unk>", **{i: f"w{i}" for i in range(4, d["vocab_size"])}}
+
+    settings = dict(model_type="BUTDDetection", embed_dim=d["embed_dim"], hidden_dim=d["hidden_dim"], atten_dim=d["atten_dim"])
+    cap = engine.B200Captioner("BUTDDetection", settings, d["vocab_size"], sd, enc_dim=d["enc_dim"], max_batch=1,
+                               max_regions=meta["R"], max_rows=3, max_seq=meta["T"], math="f16x3")
+    for img in (0, 3, 7):
+        caption, extra = cap.eval_test_image({"bu_feats": torch.from_numpy(feats[img:img + 1])}, Vocab, eval_beam_size=3)
+        assert caption == orc.ids_to_caption(gold["tokens"][img], Vocab.ix2word).split()
+        assert extra[0].shape == (1, int(gold["lengths"][img]) - 1, meta["R"])
+        caption, extra = cap.eval_test_image({"bu_feats": torch.from_numpy(feats[img:img + 1])}, Vocab, max_len=meta["T"])
+        assert extra[0].shape == (1, meta["T"], meta["R"])
+
+
 def test_empty_and_ragged_inputs_are_rejected_cleanly():
     """Error behaviour of the C ABI: bad sizes come back as RuntimeError with a message, never a crash."""
     capdec = _capdec()
