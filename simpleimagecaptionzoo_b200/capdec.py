@@ -215,6 +215,8 @@ class CaptionDecoder:
         [, alphas [B,max_seq,R] fp32 attention maps of the returned hypotheses]."""
         torch = _torch()
         B = self.B
+        if return_alphas and self.arch == "NIC":
+            raise RuntimeError("NIC has no attention maps (its decoder has no attention); call without return_alphas")
         tokens = torch.empty((B, 1 + max_seq), dtype=torch.int32, device=self.device)
         scores = torch.empty((B,), dtype=torch.float32, device=self.device)
         lengths = torch.empty((B,), dtype=torch.int32, device=self.device)
@@ -229,6 +231,8 @@ class CaptionDecoder:
         """-> tokens [B*n,max_seq] int32, logprobs [B*n,max_seq] fp32 (CUDA tensors) [, alphas [B*n,max_seq,R] fp32]."""
         torch = _torch()
         M = self.B * n_per_image
+        if return_alphas and self.arch == "NIC":
+            raise RuntimeError("NIC has no attention maps (its decoder has no attention); call without return_alphas")
         tokens = torch.empty((M, max_seq), dtype=torch.int32, device=self.device)
         logprobs = torch.empty((M, max_seq), dtype=torch.float32, device=self.device)
         alphas = torch.zeros((M, max_seq, self.R), dtype=torch.float32, device=self.device) if return_alphas else None
