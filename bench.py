@@ -50,6 +50,10 @@ WORKLOADS = {
                          desc="BUTDSpatial beam=5 over a 14x14x2048 feature grid (configs[2], decoder only)"),
     "nic": dict(arch="NIC", model_type="NIC", R=0, beam=3, batch=1536,
                 desc="NIC LSTM decoder beam=3 on synthetic image embeddings (configs[1] without the ResNet-101 encoder)"),
+    # configs[4]: SCST rollout -- 5 multinomial samples + 1 greedy baseline per image; a "caption" here is one image's rollout set
+    "scst": dict(arch="BUTD", model_type="BUTDDetection", R=36, beam=5, batch=921, scst=True,
+                 desc="BUTDDetection SCST sampling rollout (5 multinomial samples/image + greedy baseline), forward values only "
+                      "(configs[4] per-GPU shard)"),
     "aoa": dict(arch="AOA", model_type="AoADetection", R=36, beam=3, batch=1536,
                 desc="AoADetection 8-head AoA decoder beam=3 (configs[3] per-GPU shard, refined feats synthetic)"),
 }
@@ -220,17 +224,34 @@ def run_gpu_arm(args, w):
     dev_feats = host_feats.to(dev)
     n_total = B * world
 
+    scst = bool(w.get("scst"))
+
     def step_device():
         dec.prepare(dev_feats)
-        tok, _, _ = dec.beam_search(K, T)
+        if scst:  # Engine.SCST_training_epoch's two rollouts (Engine.py:258-262), forward values
+            greedy, _ = dec.sample(capdec.SAMPLE_GREEDY, 1, 0, T)
+            tok, _ = dec.sample(capdec.SAMPLE_MULTINOMIAL, K, step_device.calls, T)
+            step_device.calls += 1
+            tok = tok.view(B, K * T)
+        else:
+            tok, _, _ = dec.beam_search(K, T)
         if world > 1:
             tok = engine.all_gather_captions(tok, n_total)
         return tok
+
+    step_device.calls = 0
 
     def run_e2e(n_steps):
         """n_steps batches through the pipelined captioner API: every step's features start in pinned HOST memory and
         every step's captions end in host memory (H2D of step i+1 overlaps the decode of step i)."""
         last = None
+        if scst:  # the rollout API has no streaming form: H2D, both rollouts and the read-back run back to back
+            for _ in range(n_steps):
+                vi = {key: host_feats}
+                cap.sampler(vi, max_len=T)
+                seq, _ = cap.sampler_rl(vi, max_len=T, n_per_image=K)
+                last = seq.view(B, K * T).to(torch.int32).cpu().numpy()
+            return last
         for tok in cap.beam_search_stream(({key: host_feats} for _ in range(n_steps)), beam_size=K, max_seq=T):
             last = tok
         if world > 1:  # the gathered captions of the last batch (one NCCL all-gather per batch in a real eval loop)
@@ -333,7 +354,7 @@ def run_gpu_arm(args, w):
         "kernels": kern,
     }
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not scst:
         n_cpu = args.cpu_images
         feats_np = host_feats[:n_cpu].numpy()
         dt, res = time_reference_form(w, sd, feats_np, K, T)

@@ -232,6 +232,31 @@ __device__ __forceinline__ void epi_lstm(uint32_t taddr, int row, int n_base, in
     }
 }
 
+// Issued by an epilogue thread as soon as it knows its next tile, i.e. while the tile's MMAs are still running:
+// pulls the thread's additive rows (embedding-gate row of its word: a random 16 KB row of a 155 MB table, i.e. an
+// HBM miss; per-image hoisted row; previous cell state) into L2 so that the epilogue proper sees L2 latency.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+template <int BLOCK_N>
+__device__ __forceinline__ void epi_lstm_prefetch(int row, int n_base, int c0, int c1, const GemmParams& p) {
+    const EpiParams& e = p.epi;
+    if (row >= p.M) return;
+    const int n0 = n_base + c0 * 32;
+    if (n0 >= p.N) return;
+    const int lines = (c1 - c0);  // 32 fp32 columns = one 128-byte line per chunk
+    if (e.gather) {
+        const float* g = e.gather + static_cast<size_t>(__ldg(e.gather_idx + row)) * e.gather_ld + n0;
+        for (int i = 0; i < lines; ++i) prefetch_l2(g + 32 * i);
+    }
+    if (e.rowadd) {
+        const float* r = e.rowadd + static_cast<size_t>(row / e.rows_per_group) * e.rowadd_ld + n0;
+        for (int i = 0; i < lines; ++i) prefetch_l2(r + 32 * i);
+    }
+    if (e.c_in) {
+        const int prow = e.parent ? __ldg(e.parent + row) : row;
+        prefetch_l2(e.c_in + static_cast<size_t>(prow) * e.ldc + (n0 >> 2));
+    }
+}
+
 // Columns are packed (a_j, gate_j)-interleaved: n = 2*j + s.  nn.GLU: a * sigmoid(gate).
 template <int BLOCK_N>
 __device__ __forceinline__ void epi_glu(uint32_t taddr, int row, int n_base, int c0, int c1, const GemmParams& p) {
@@ -553,11 +578,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         bool first, last;
         while (it.next(first, last)) {
             const int m_blk = it.m_blk, n_blk = it.n_blk;
+            const int row = m_blk * BLOCK_M + quarter * 32 + lane;
+            const int n_base = n_blk * BLOCK_N;
+            if constexpr (EPI == EPI_LSTM) epi_lstm_prefetch<BLOCK_N>(row, n_base, c0, c1, p);
             mbar_wait(tfull_bar + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quarter * 32) << 16);
-            const int row = m_blk * BLOCK_M + quarter * 32 + lane;
-            const int n_base = n_blk * BLOCK_N;
             if constexpr (EPI == EPI_STORE) epi_store<BLOCK_N>(taddr, row, n_base, c0, c1, p);
             else if constexpr (EPI == EPI_LSTM) epi_lstm<BLOCK_N>(taddr, row, n_base, c0, c1, p);
             else if constexpr (EPI == EPI_GLU) epi_glu<BLOCK_N>(taddr, row, n_base, c0, c1, p);
@@ -723,11 +749,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         bool first, last;
         while (it.next(first, last)) {
             const int m_blk = 2 * it.m_blk + static_cast<int>(rank), n_blk = it.n_blk;
+            const int row = m_blk * BLOCK_M + quarter * 32 + lane;
+            const int n_base = n_blk * BLOCK_N;
+            if constexpr (EPI == EPI_LSTM) epi_lstm_prefetch<BLOCK_N>(row, n_base, c0, c1, p);
             mbar_wait(tfull_bar + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quarter * 32) << 16);
-            const int row = m_blk * BLOCK_M + quarter * 32 + lane;
-            const int n_base = n_blk * BLOCK_N;
             if constexpr (EPI == EPI_STORE) epi_store<BLOCK_N>(taddr, row, n_base, c0, c1, p);
             else if constexpr (EPI == EPI_LSTM) epi_lstm<BLOCK_N>(taddr, row, n_base, c0, c1, p);
             else if constexpr (EPI == EPI_GLU) epi_glu<BLOCK_N>(taddr, row, n_base, c0, c1, p);

@@ -5,8 +5,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from simpleimagecaptionzoo_b200 import capdec
 torch.cuda.init()
-shapes = [("td_lstm", 3072, 4096, 3072, 1), ("lm_lstm", 3072, 4096, 4096, 1), ("logits", 3072, 9487, 1024, 3),
-          ("dec_att", 3072, 1024, 1024, 0), ("proj", 36864, 1024, 2048, 0), ("lm_store", 3072, 4096, 4096, 0),
+M = int(sys.argv[1]) if len(sys.argv) > 1 else 4608
+shapes = [("td_lstm", M, 4096, 2048, 1), ("lm_lstm", M, 4096, 4096, 1), ("logits", M, 9487, 1024, 3),
+          ("dec_att", M, 1024, 1024, 0), ("proj", M * 12, 1024, 2048, 0), ("td_store", M, 4096, 2048, 0), ("lm_store", M, 4096, 4096, 0),
           ("big_store", 8192, 8192, 4096, 0)]
 for name, m, n, k, epi in shapes:
     us = capdec.gemm_time_us(m, n, k, epi, "f16", 30)
