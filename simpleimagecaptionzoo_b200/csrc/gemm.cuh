@@ -104,11 +104,19 @@ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
     h ^= h >> 16;
     return h;
 }
-// Gumbel(0,1) noise shared bit-for-bit (in the uniforms) with oracle/capdec_oracle.py:gumbel_noise.
+// Gumbel(0,1) noise g = -log(-log(u)) on the counter-based uniforms of oracle/capdec_oracle.py:gumbel_noise, computed
+// with two MUFU.LG2 instead of two libm logf calls (the draw runs once per vocabulary entry per row-step inside the
+// logit GEMM's epilogue).  lg2.approx has ~2^-22 ABSOLUTE error, which is useless for -log(u) when u -> 1 (exactly the
+// draws that win the arg-max), so that range uses the series of -log(1 - t), t = 1 - u (exact by Sterbenz):
+// |g - exact| <= ~1e-5 everywhere, far below the 1e-3 tie tolerance of the sampling parity tests.
 __device__ __forceinline__ float gumbel_from_hash(uint32_t row_step_hash, uint32_t v) {
     const uint32_t x = fmix32(row_step_hash ^ (v * 0xC2B2AE3Du));
     const float u = (static_cast<float>(x >> 8) + 0.5f) * 5.9604644775390625e-08f;  // 2^-24
-    return -logf(-logf(u));
+    const float t = 1.0f - u;
+    const float e_series = t * fmaf(t, fmaf(t, fmaf(t, 0.25f, 0.33333334f), 0.5f), 1.0f);  // -log(1-t), t < 2^-6: rel err < 1e-8
+    const float e_lg2 = -LN2 * __log2f(u);
+    const float e = t < 0.015625f ? e_series : e_lg2;                                       // E = -log(u) ~ Exp(1)
+    return -LN2 * __log2f(e);
 }
 __device__ __forceinline__ uint32_t gumbel_row_step_hash(uint32_t seed, uint32_t row, uint32_t t) {
     uint32_t h = fmix32(seed ^ (row * 0x9E3779B1u));
