@@ -138,6 +138,8 @@ class CaptionDecoder:
         if rc != 0:
             raise RuntimeError(f"capdec_create failed ({rc}): {self.lib.capdec_last_error(None).decode()}")
         self._h = handle
+        # decode work runs on an own (capturable) stream, ordered after / before the caller's current stream
+        self.stream = torch.cuda.Stream(self.device)
         self._keep = None
         self.B, self.R = 0, 0
         self._load(state_dict)
@@ -205,8 +207,10 @@ class CaptionDecoder:
         B = feats.shape[0]
         R = feats.shape[1] if feats.dim() == 3 else 0
         with torch.cuda.device(self.device):
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
             self._check(self.lib.capdec_prepare(self._h, feats.data_ptr(), None if mask is None else mask.data_ptr(), B, R,
-                                                _stream_ptr(self.device)), "capdec_prepare")
+                                                self.stream.cuda_stream), "capdec_prepare")
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
         self._keep = (feats, mask)  # the library reads them during decode
         self.B, self.R = B, R
 
@@ -222,9 +226,11 @@ class CaptionDecoder:
         lengths = torch.empty((B,), dtype=torch.int32, device=self.device)
         alphas = torch.empty((B, max_seq, self.R), dtype=torch.float32, device=self.device) if return_alphas else None
         with torch.cuda.device(self.device):
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
             self._check(self.lib.capdec_beam_search(self._h, beam, max_seq, tokens.data_ptr(), scores.data_ptr(),
                                                     lengths.data_ptr(), alphas.data_ptr() if return_alphas else None,
-                                                    _stream_ptr(self.device)), "capdec_beam_search")
+                                                    self.stream.cuda_stream), "capdec_beam_search")
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
         return (tokens, scores, lengths, alphas) if return_alphas else (tokens, scores, lengths)
 
     def sample(self, mode: int, n_per_image: int = 1, seed: int = 0, max_seq: int = 20, return_alphas: bool = False):
@@ -237,7 +243,9 @@ class CaptionDecoder:
         logprobs = torch.empty((M, max_seq), dtype=torch.float32, device=self.device)
         alphas = torch.zeros((M, max_seq, self.R), dtype=torch.float32, device=self.device) if return_alphas else None
         with torch.cuda.device(self.device):
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
             self._check(self.lib.capdec_sample(self._h, mode, n_per_image, seed, max_seq, tokens.data_ptr(), logprobs.data_ptr(),
-                                               alphas.data_ptr() if return_alphas else None, _stream_ptr(self.device)),
+                                               alphas.data_ptr() if return_alphas else None, self.stream.cuda_stream),
                         "capdec_sample")
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
         return (tokens, logprobs, alphas) if return_alphas else (tokens, logprobs)

@@ -100,6 +100,22 @@ struct capdec_handle {
         *live_count = nullptr;
     int* seqs[2] = {nullptr, nullptr};
     float *cum = nullptr, *best_score = nullptr;
+    // CUDA graph of one whole beam-search decode (all steps), replayed while the shapes / buffers stay the same
+    bool use_graphs = true;  // CAPDEC_NO_GRAPH=1 disables
+    cudaGraphExec_t graph_exec = nullptr;
+    struct GraphKey {
+        int B, R, K, T;
+        const void* feats;  // fp32-grade mode reads the caller's features inside the loop
+        bool masked;
+        bool operator==(const GraphKey& o) const {
+            return B == o.B && R == o.R && K == o.K && T == o.T && feats == o.feats && masked == o.masked;
+        }
+    } graph_key{};
+    int64_t graph_launches = 0;
+    float* mask_buf = nullptr;  // library-owned copy of the region mask (stable address for the captured decode)
+    int* out_tokens = nullptr;
+    float* out_scores = nullptr;
+    int* out_lengths = nullptr;
     float* alpha_step = nullptr;  // [Tmax, Mmax, Rmax] per-step attention maps (allocated on first request)
     int *hist_parent = nullptr, *best_pslot = nullptr;
 };
@@ -856,6 +872,7 @@ int64_t capdec_launch_count(const capdec_handle* h) { return h ? h->launches : 0
 void capdec_destroy(capdec_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     for (void* p : h->allocs) cudaFree(p);
     for (auto& kv : h->raw) cudaFree(kv.second.d);
     delete h;
@@ -890,6 +907,8 @@ static int create_impl(capdec_handle* h) {
         h->no_stream_attention = e && e[0] == '1';
         const char* g1 = getenv("CAPDEC_GEMM_1CTA");
         h->pair_gemm = !(g1 && g1[0] == '1');
+        const char* ng = getenv("CAPDEC_NO_GRAPH");
+        h->use_graphs = !(ng && ng[0] == '1');
         const char* v = getenv("CAPDEC_ATT_VARIANT");
         h->att_variant = v ? atoi(v) : 0;
     }
@@ -919,6 +938,10 @@ static int create_impl(capdec_handle* h) {
     CKS(h, dalloc(h, &h->best_seq, static_cast<size_t>(h->Bmax) * (h->Tmax + 1)));
     CKS(h, dalloc(h, &h->seqs[0], static_cast<size_t>(M) * (h->Tmax + 1)));
     CKS(h, dalloc(h, &h->seqs[1], static_cast<size_t>(M) * (h->Tmax + 1)));
+    CKS(h, dalloc(h, &h->out_tokens, static_cast<size_t>(h->Bmax) * (h->Tmax + 1)));
+    if (c.arch == CAPDEC_ARCH_AOA) CKS(h, dalloc(h, &h->mask_buf, static_cast<size_t>(h->Bmax) * h->Rmax));
+    CKS(h, dalloc(h, &h->out_scores, h->Bmax));
+    CKS(h, dalloc(h, &h->out_lengths, h->Bmax));
 
     if (c.arch == CAPDEC_ARCH_BUTD) {
         const int A = h->A, D = h->D;
@@ -1039,6 +1062,10 @@ int capdec_finalize_weights(capdec_handle* h, void* stream) {
     else if (h->cfg.arch == CAPDEC_ARCH_NIC) CKS(h, finalize_nic(h, st));
     else CKS(h, finalize_aoa(h, st));
     CK(h, cudaStreamSynchronize(st));  // b_aff is read back; packing is a one-time load cost
+    if (h->graph_exec) {  // kernel parameters baked into the captured decode (e.g. b_aff) may have changed
+        cudaGraphExecDestroy(h->graph_exec);
+        h->graph_exec = nullptr;
+    }
     h->weights_ready = true;
     return CAPDEC_OK;
 }
@@ -1133,10 +1160,17 @@ int capdec_prepare(capdec_handle* h, const float* feats, const float* mask, int3
     }
     h->B = batch;
     h->feats = feats;
-    h->mask = mask;
+    h->mask = nullptr;
+    if (mask) {  // keep a copy: the decode loop (possibly a replayed graph) reads it at a fixed address
+        CK(h, cudaMemcpyAsync(h->mask_buf, mask, static_cast<size_t>(batch) * regions * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        h->mask = h->mask_buf;
+    }
     h->prepared = true;
     return CAPDEC_OK;
 }
+
+static int enqueue_beam_search(capdec_handle* h, int32_t beam, int32_t max_seq, int32_t* tokens, float* seq_logprob,
+                               int32_t* lengths, float* alphas, cudaStream_t st);
 
 int capdec_beam_search(capdec_handle* h, int32_t beam, int32_t max_seq, int32_t* tokens, float* seq_logprob, int32_t* lengths,
                        float* alphas, void* stream) {
@@ -1153,6 +1187,45 @@ int capdec_beam_search(capdec_handle* h, int32_t beam, int32_t max_seq, int32_t*
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(h, cudaSetDevice(h->cfg.device));
+    // Replay the whole decode (6 launches x max_seq steps) as one CUDA graph while shapes and buffers are unchanged.
+    // Not on the legacy default stream (cannot be captured), not while profiling, not with the attention-map output.
+    if (!h->use_graphs || h->prof || alphas || st == nullptr)
+        return enqueue_beam_search(h, beam, max_seq, tokens, seq_logprob, lengths, alphas, st);
+    const capdec_handle::GraphKey key{h->B, h->R, beam, max_seq, h->split ? static_cast<const void*>(h->feats) : nullptr,
+                                      h->mask != nullptr};
+    if (!h->graph_exec || !(key == h->graph_key)) {
+        if (h->graph_exec) {
+            cudaGraphExecDestroy(h->graph_exec);
+            h->graph_exec = nullptr;
+        }
+        cudaGraph_t graph = nullptr;
+        CK(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const int64_t l0 = h->launches;
+        const int status = enqueue_beam_search(h, beam, max_seq, h->out_tokens, h->out_scores, h->out_lengths, nullptr, st);
+        const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        h->graph_launches = h->launches - l0;
+        h->launches = l0;
+        if (status != CAPDEC_OK) {
+            if (graph) cudaGraphDestroy(graph);
+            return status;
+        }
+        CK(h, ce);
+        const cudaError_t ie = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        CK(h, ie);
+        h->graph_key = key;
+    }
+    CK(h, cudaGraphLaunch(h->graph_exec, st));
+    h->launches += h->graph_launches;
+    const int B = h->B;
+    CK(h, cudaMemcpyAsync(tokens, h->out_tokens, static_cast<size_t>(B) * (max_seq + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    if (seq_logprob) CK(h, cudaMemcpyAsync(seq_logprob, h->out_scores, static_cast<size_t>(B) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (lengths) CK(h, cudaMemcpyAsync(lengths, h->out_lengths, static_cast<size_t>(B) * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    return CAPDEC_OK;
+}
+
+static int enqueue_beam_search(capdec_handle* h, int32_t beam, int32_t max_seq, int32_t* tokens, float* seq_logprob,
+                               int32_t* lengths, float* alphas, cudaStream_t st) {
     const int B = h->B, K = beam, M = B * K;
     CKS(h, reset_state(h, M, st));
     BeamState s{};
