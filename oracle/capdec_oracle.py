@@ -297,6 +297,52 @@ class AoaOracle:
         return logits, dict(h=h, c=c, ctx=ctx), p.mean(axis=2, dtype=f32)  # alphas = head mean :119
 
 
+def reference_layer_norm(x, gain, bias, eps=1e-6):
+    """LayerNorm of the reference (AoA_Model.py:14-25): unbiased std, eps added to the STD."""
+    mu = x.mean(-1, keepdims=True, dtype=f32)
+    sd_ = x.std(-1, keepdims=True, ddof=1, dtype=f32)
+    return (gain * (x - mu) / (sd_ + f32(eps)) + bias).astype(f32)
+
+
+def aoa_project_refine(sd: dict, bu_feats, mask=None, num_heads=8, operand_round=None):
+    """Encoder-side half of AoADetection_Captioner / AoASpatial_Captioner in front of the decoder
+    (AoA_Model.py:748-751, 598-601): ``img_feats_porjection`` = Linear(2048->H) + ReLU (:661-665; dropout = identity in
+    eval) applied under ``pack_wrapper`` (:650-655 -- with a mask only the valid prefix rows go through the module and
+    ``pad_packed_sequence`` leaves ZEROS in the padded rows), then ``AoA_Refine_Core`` (:140-162): six
+    ``x = x + AoABlock(LN(x), LN(x), LN(x), mask)`` layers (:27-38, 122-138; AoABlock :90-120 with multi-head
+    ``DotProductAttention`` :41-69, keys masked with -1e9) and a final LayerNorm.
+    bu_feats (B,R,D) fp32, mask (B,R) float {0,1} prefix mask or None -> refined features (B,R,H) fp32."""
+    mm = _Mat(operand_round)
+    x = np.ascontiguousarray(bu_feats, dtype=f32)
+    B, R, _ = x.shape
+    Wp, bp = sd["img_feats_porjection.0.weight"], sd["img_feats_porjection.0.bias"]
+    x = np.maximum(mm(x, Wp) + bp, 0).astype(f32)
+    if mask is not None:
+        mask = np.ascontiguousarray(mask, dtype=f32)
+        x = (x * (mask[:, :, None] != 0)).astype(f32)  # padded rows are zeros after pad_packed_sequence (:647)
+    H = x.shape[-1]
+    nh = num_heads
+    d = H // nh
+    layer = 0
+    while f"aoa_refine.aoa_layers.{layer}.aoa_block.linear_Q.weight" in sd:
+        p = f"aoa_refine.aoa_layers.{layer}."
+        n = reference_layer_norm(x, sd[p + "sublayer.norm.gain"], sd[p + "sublayer.norm.bias"])  # :37 (norm first)
+        g = lambda nm: (sd[p + "aoa_block." + nm + ".weight"], sd[p + "aoa_block." + nm + ".bias"])
+        (WQ, bQ), (WK, bK), (WV, bV), (WA, bA) = g("linear_Q"), g("linear_K"), g("linear_V"), g("aoa_module.0")
+        Q = (mm(n, WQ) + bQ).astype(f32).reshape(B, R, nh, d)  # :113-115
+        K = (mm(n, WK) + bK).astype(f32).reshape(B, R, nh, d)
+        V = (mm(n, WV) + bV).astype(f32).reshape(B, R, nh, d)
+        s = (np.einsum("bqhd,brhd->bhqr", Q, K, dtype=f32) / f32(math.sqrt(d))).astype(f32)  # :62
+        if mask is not None:
+            s = np.where(mask[:, None, None, :] == 0, f32(-1e9), s)  # :63-64
+        pr = softmax(s)  # :65
+        att = np.einsum("bhqr,brhd->bqhd", pr, V, dtype=f32).astype(f32).reshape(B, R, H)  # :68,117
+        a = (mm(np.concatenate([att, n], axis=-1), WA) + bA).astype(f32)  # :118
+        x = (x + a[..., :H] * sigmoid(a[..., H:])).astype(f32)  # nn.GLU + residual (:38)
+        layer += 1
+    return reference_layer_norm(x, sd["aoa_refine.norm.gain"], sd["aoa_refine.norm.bias"])  # :162
+
+
 def make_decoder(arch, sd, operand_round=None, num_heads=8):
     arch = arch.upper()
     if arch == "BUTD":

@@ -110,6 +110,35 @@ def make_state_dict(arch: str, *, vocab_size: int, hidden_dim: int, embed_dim: i
     return sd
 
 
+def make_refiner_state_dict(*, hidden_dim: int, enc_dim: int = 2048, num_layers: int = 6, seed: int = 0,
+                            chaotic: float = 0.0) -> dict:
+    """Encoder-side ``state_dict`` entries of ``AoADetection_Captioner`` / ``AoASpatial_Captioner`` (numpy fp32, the
+    reference's key names): ``img_feats_porjection`` (Models/AoA_Model.py:661-665, Linear 2048->H + ReLU) and the
+    ``aoa_refine`` stack (:122-162: 6 x [pre-LayerNorm, AoABlock self-attention, residual] + final LayerNorm).
+    PyTorch default Linear init; LayerNorm gain 1 / bias 0 (:18-19) unless ``chaotic``."""
+    rng = _rng(7_000_003 + seed)
+    sd: dict = {}
+    H = hidden_dim
+    _linear(rng, sd, "img_feats_porjection.0", H, enc_dim, chaotic)
+
+    def norm(name):
+        if chaotic:
+            sd[name + ".gain"] = (1.0 + _u(rng, (H,), 0.5)).astype(np.float32)
+            sd[name + ".bias"] = _u(rng, (H,), 0.5)
+        else:
+            sd[name + ".gain"] = np.ones(H, np.float32)
+            sd[name + ".bias"] = np.zeros(H, np.float32)
+
+    for i in range(num_layers):
+        p = f"aoa_refine.aoa_layers.{i}."
+        for nm in ("linear_Q", "linear_K", "linear_V"):
+            _linear(rng, sd, p + "aoa_block." + nm, H, H, chaotic)
+        _linear(rng, sd, p + "aoa_block.aoa_module.0", 2 * H, 2 * H, chaotic)
+        norm(p + "sublayer.norm")
+    norm("aoa_refine.norm")
+    return sd
+
+
 def make_region_feats(batch: int, regions: int, dim: int, seed: int = 0) -> np.ndarray:
     """|N(0,1)| region features, (B,R,D) fp32: post-ReLU-like bottom-up / CNN-grid features."""
     return np.abs(_rng(1_000_003 + seed).standard_normal((batch, regions, dim))).astype(np.float32)

@@ -189,6 +189,60 @@ CASES = [
     ("aoa_full_k3", "AOA", "full", 8, 36, 3, 20, 0, False, False),      # configs[3] decoder
 ]
 
+
+def run_refiner_case(name, dims_key, B, R, K, T, seed, chaotic, masked, end_boost=0.0, store_stride=1):
+    """AoADetection_Captioner end to end from the bottom-up features (AoA_Model.py:657-753): the refined features of
+    ``aoa_refine(pack_wrapper(img_feats_porjection, bu_feats, bu_masks), bu_masks)``, greedy ids of the batched
+    ``sampler`` and beam tokens of ``beam_search_sampler``.  Beam search is called the way the reference's evaluation
+    does: one image per call, its features cut to its own number of regions and no mask
+    (AoA_Engine.modify_visual_inputs builds the mask per batch and drops it when every region is valid)."""
+    dims = dict((synth.TINY_DIMS if dims_key == "tiny" else synth.DIMS)["AOA"])
+    sd = synth.make_state_dict("AOA", seed=seed, chaotic=chaotic, end_boost=end_boost, **dims)
+    sd.update(synth.make_refiner_state_dict(hidden_dim=dims["hidden_dim"], enc_dim=2048, seed=seed, chaotic=chaotic))
+    m = load_reference("AoA_Model")
+    cap = m.AoADetection_Captioner(vocab_size=dims["vocab_size"], num_heads=dims["num_heads"], hidden_dim=dims["hidden_dim"],
+                                   embed_dim=dims["embed_dim"])
+    cap.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in sd.items()}, strict=True)
+    cap.eval()
+    cap.decoder.max_step_limit = T
+    bu = synth.make_region_feats(B, R, 2048, seed)
+    mask = synth.make_region_mask(B, R, max(1, R // 3), seed) if masked else None
+    if mask is not None:
+        bu = bu * mask[:, :, None]  # AoA_Engine.py:36-41: padded regions are zero
+    tb = torch.from_numpy(bu)
+    tm = None if mask is None else torch.from_numpy(mask)
+    tokens = np.zeros((B, 1 + T), np.int32)
+    lengths = np.zeros(B, np.int32)
+    with torch.no_grad():
+        refined = cap.aoa_refine(x=m.pack_wrapper(module=cap.img_feats_porjection, bu_feats=tb, bu_masks=tm), bu_mask=tm)
+        gids = cap.sampler({"bu_feats": tb, "bu_masks": tm}, max_len=T)
+        for b in range(B):
+            n = R if mask is None else int(mask[b].sum())
+            seq_t = cap.beam_search_sampler({"bu_feats": tb[b:b + 1, :n], "bu_masks": None}, beam_size=K)
+            seq = [int(x) for x in seq_t[0].tolist()]
+            tokens[b, :len(seq)] = seq
+            lengths[b] = len(seq)
+    out = dict(
+        tokens=tokens, lengths=lengths, greedy=gids.numpy().astype(np.int32),
+        refined=refined.numpy().astype(np.float32)[:, :, ::store_stride],
+        meta=np.array(json.dumps(dict(name=name, arch="AOA", dims_key=dims_key, dims=dims, B=B, R=R, K=K, T=T, seed=seed,
+                                      chaotic=chaotic, masked=masked, end_boost=end_boost, refiner=True, enc_dim=2048,
+                                      store_stride=store_stride, torch=torch.__version__))),
+    )
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(path, **out)
+    ncomp = int((tokens == orc.END).any(1).sum())
+    print(f"{name}: B={B} completed={ncomp} lens {lengths.min()}..{lengths.max()} -> {os.path.relpath(path, ROOT)}")
+
+
+REFINER_CASES = [
+    # name, dims, B, R, K, T, seed, chaotic, masked, end_boost, store_stride
+    ("aoaref_tiny_k3", "tiny", 16, 9, 3, 20, 4, 0.3, False, 0.6, 1),
+    ("aoaref_tiny_k3_masked", "tiny", 16, 9, 3, 20, 5, 0.3, True, 0.9, 1),
+    ("aoaref_full_k3", "full", 4, 36, 3, 20, 0, False, False, 0.0, 8),     # BASELINE configs[3] from bu_feats
+    ("aoaref_full_k3_masked", "full", 4, 36, 3, 20, 1, False, True, 0.0, 8),
+]
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
@@ -197,3 +251,7 @@ if __name__ == "__main__":
         if only and c[0] not in only:
             continue
         run_case(*c)
+    for c in REFINER_CASES:
+        if only and c[0] not in only:
+            continue
+        run_refiner_case(*c)

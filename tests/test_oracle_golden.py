@@ -99,3 +99,44 @@ def test_weight_norm_fold():
     g = rng.standard_normal((7, 1)).astype(np.float32)
     w = orc.fold_weight_norm(g, v)
     assert np.allclose(np.linalg.norm(w, axis=1), np.abs(g[:, 0]), rtol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------
+# AoA encoder side (img_feats_porjection + aoa_refine) in front of the decoder: SURVEY.md section 8f row 1
+# ---------------------------------------------------------------------------------------------------
+from tests.golden_util import rebuild_refiner  # noqa: E402
+
+REFINER = case_names("aoaref")
+
+
+@pytest.mark.parametrize("name", REFINER)
+def test_refiner_matches_golden(name):
+    """The oracle's projection + 6-layer AoA refiner against the reference's refined features (fp32 re-association
+    through six residual layers: 2e-4 absolute on LayerNorm-ed, O(1) outputs)."""
+    meta, gold = load_case(name)
+    sd, bu, mask = rebuild_refiner(meta)
+    ref = orc.aoa_project_refine(sd, bu, mask, num_heads=meta["dims"]["num_heads"])
+    got = ref[:, :, ::meta["store_stride"]]
+    valid = np.ones(got.shape[:2], bool) if mask is None else mask.astype(bool)
+    assert np.abs(got - gold["refined"])[valid].max() < 2e-4
+    # padded regions: the reference runs them through the layers too (they only see the valid keys); same here
+    assert np.abs(got - gold["refined"]).max() < 2e-4
+
+
+@pytest.mark.parametrize("name", REFINER)
+def test_refiner_then_decode_matches_golden(name):
+    """Whole AoADetection path from bottom-up features: batched masked decode == the reference's one-image-per-call
+    beam search on the image's own regions, and the reference's batched greedy ``sampler``."""
+    meta, gold = load_case(name)
+    sd, bu, mask = rebuild_refiner(meta)
+    dec = orc.make_decoder("AOA", sd, num_heads=meta["dims"]["num_heads"])
+    dec.prepare(orc.aoa_project_refine(sd, bu, mask, num_heads=meta["dims"]["num_heads"]), mask)
+    res = orc.beam_search_batched(dec, meta["K"], meta["T"])
+    verdict = orc.agreement(res.tokens, gold["tokens"], res.min_gap, tol=1e-4)
+    assert "diff" not in verdict, verdict
+    assert np.mean([v == "exact" for v in verdict]) >= 0.9
+    ids, gaps, _ = orc.greedy_sample(dec, meta["T"])
+    for b in range(meta["B"]):
+        if not np.array_equal(ids[b], gold["greedy"][b]):
+            t = int(np.argmax(ids[b] != gold["greedy"][b]))
+            assert gaps[b, t] < 1e-4, (b, t, gaps[b, t])
