@@ -56,6 +56,10 @@ WORKLOADS = {
                       "(configs[4] per-GPU shard)"),
     "aoa": dict(arch="AOA", model_type="AoADetection", R=36, beam=3, batch=1536,
                 desc="AoADetection 8-head AoA decoder beam=3 (configs[3] per-GPU shard, refined feats synthetic)"),
+    # configs[3] from the bottom-up features: img_feats_porjection + 6-layer aoa_refine + decoder, all in the library
+    "aoa_bu": dict(arch="AOA", model_type="AoADetection", R=36, beam=3, batch=1536, refiner=True,
+                   desc="AoADetection beam=3 from synthetic 36x2048 bottom-up feats: projection + 6-layer AoA refiner + 8-head "
+                        "AoA decoder (configs[3] per-GPU shard)"),
 }
 
 
@@ -70,8 +74,8 @@ def load_peaks():
 
 def make_inputs(w, batch, seed):
     dims = synth.DIMS[w["arch"]]
-    if w["arch"] == "BUTD":
-        return synth.make_region_feats(batch, w["R"], dims["enc_dim"], seed)
+    if w["arch"] == "BUTD" or w.get("refiner"):
+        return synth.make_region_feats(batch, w["R"], dims.get("enc_dim", 2048), seed)
     if w["arch"] == "NIC":
         return synth.make_image_embed(batch, dims["embed_dim"], seed)
     return synth.make_refined_feats(batch, w["R"], dims["hidden_dim"], seed)
@@ -149,9 +153,19 @@ def time_reference_form(w, sd, feats, beam, max_seq):
         _ORACLE_CACHE[id(sd)] = oracle_decoder(w, sd)
     orc, dec = _ORACLE_CACHE[id(sd)]
     t0 = time.perf_counter()
+    if w.get("refiner"):  # AoA_Model.py:748-751: projection + refiner run on every sampler call
+        feats = orc.aoa_project_refine(sd, feats, None)
     dec.prepare(feats)
     res = orc.beam_search_reference_form(dec, beam, max_seq)
     return time.perf_counter() - t0, res
+
+
+def make_weights(w):
+    dims = synth.DIMS[w["arch"]]
+    sd = synth.make_state_dict(w["arch"], seed=0, **dims)
+    if w.get("refiner"):
+        sd.update(synth.make_refiner_state_dict(hidden_dim=dims["hidden_dim"], enc_dim=2048, seed=0))
+    return sd
 
 
 def run_reference_arm(args, w):
@@ -159,7 +173,7 @@ def run_reference_arm(args, w):
     if rank != 0:
         return 0
     dims = synth.DIMS[w["arch"]]
-    sd = synth.make_state_dict(w["arch"], seed=0, **dims)
+    sd = make_weights(w)
     n_img = args.ref_images
     for i in range(args.warmup):
         time_reference_form(w, sd, make_inputs(w, n_img, 100 + i), w["beam"], args.max_seq)
@@ -207,17 +221,18 @@ def run_gpu_arm(args, w):
 
     dims = synth.DIMS[w["arch"]]
     B, K, T, R = args.batch, w["beam"], args.max_seq, w["R"]
-    sd = synth.make_state_dict(w["arch"], seed=0, **dims)
+    sd = make_weights(w)
     settings = dict(model_type=w["model_type"], embed_dim=dims["embed_dim"], hidden_dim=dims["hidden_dim"],
                     atten_dim=dims.get("atten_dim", 0))
     feature_fn = None
-    if w["model_type"] != "BUTDDetection":  # encoder / refiner side is outside the decode path: features are the input
+    raw_bu = w["model_type"] == "BUTDDetection" or bool(w.get("refiner"))
+    if not raw_bu:  # CNN encoder (or a synthetic stand-in for the refined features): the decoder's input is the input
         feature_fn = lambda vi: vi["feats"]  # noqa: E731
     cap = engine.B200Captioner(w["model_type"], settings, dims["vocab_size"], sd, feature_fn=feature_fn, max_batch=B,
                                max_regions=max(R, 1), max_rows=K, max_seq=T, math=args.math, device=local,
                                enc_dim=dims.get("enc_dim", 2048), num_heads=dims.get("num_heads", 8))
     dec = cap.decoder
-    key = "bu_feats" if w["model_type"] == "BUTDDetection" else "feats"
+    key = "bu_feats" if raw_bu else "feats"
 
     # rank-local shard of the global batch (weak scaling: B images per GPU), distinct per rank
     host_feats = torch.from_numpy(make_inputs(w, B, 1000 + rank)).pin_memory()
@@ -227,7 +242,7 @@ def run_gpu_arm(args, w):
     scst = bool(w.get("scst"))
 
     def step_device():
-        dec.prepare(dev_feats)
+        cap._prepare(dev_feats, None)
         if scst:  # Engine.SCST_training_epoch's two rollouts (Engine.py:258-262), forward values
             greedy, _ = dec.sample(capdec.SAMPLE_GREEDY, 1, 0, T)
             tok, _ = dec.sample(capdec.SAMPLE_MULTINOMIAL, K, step_device.calls, T)

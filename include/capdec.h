@@ -59,7 +59,8 @@ typedef struct capdec_config {
     int32_t hidden_dim;    /* H */
     int32_t embed_dim;     /* E */
     int32_t atten_dim;     /* A   (BUTD only) */
-    int32_t enc_dim;       /* D   (BUTD: region feature width, 2048) */
+    int32_t enc_dim;       /* D   (BUTD: region feature width, 2048; AoA: width of the bottom-up features fed to
+                              capdec_prepare_bottom_up, 2048 -- may be 0 when only refined features are decoded) */
     int32_t vocab_size;    /* V */
     int32_t num_heads;     /* AoA only */
     int32_t max_batch;     /* largest number of images per prepare() */
@@ -97,6 +98,20 @@ int capdec_finalize_weights(capdec_handle* h, void* stream);
  *   NIC : feats = image embedding [B,E] (R ignored) -> priming LSTM step (NIC_Model.py:52-56).
  * feats (and mask) are DEVICE pointers and must stay valid until the following decode call has completed. */
 int capdec_prepare(capdec_handle* h, const float* feats, const float* mask, int32_t batch, int32_t regions, void* stream);
+
+/* AoADetection_Captioner / AoASpatial_Captioner from the bottom-up (or CNN grid) features: the encoder-side half the
+ * reference runs in front of AoA_Decoder on every sampler call (AoA_Model.py:748-751, 598-601) --
+ *   img_feats_porjection = Linear(enc_dim -> H) + ReLU under pack_wrapper (:650-655, 661-665: rows where mask == 0
+ *   come out as zeros), then AoA_Refine_Core (:140-162): N x [x += GLU(Linear([MHA(LN x), LN x]))] + final LayerNorm --
+ * followed by what capdec_prepare does on the refined features.  Needs the checkpoint's "img_feats_porjection.*" and
+ * "aoa_refine.*" entries (loaded under those names; the number of layers is taken from the checkpoint) and
+ * cfg.enc_dim = width of bu_feats.  bu_feats [B,R,enc_dim] fp32 and mask [B,R] float {0,1} (prefix mask, or NULL) are
+ * DEVICE pointers; both may be released once the stream work of this call has completed.  AoA only. */
+int capdec_prepare_bottom_up(capdec_handle* h, const float* bu_feats, const float* mask, int32_t batch, int32_t regions,
+                             void* stream);
+/* Copy the refined features [B,R,H] fp32 of the batch prepared by capdec_prepare_bottom_up to dst (device memory):
+ * what aoa_refine returns in the reference (AoA_Model.py:751).  Test / inspection hook. */
+int capdec_get_refined(capdec_handle* h, float* dst, void* stream);
 
 /* Batched beam search with the reference's exact bookkeeping (shrinking beam, best COMPLETED hypothesis wins,
  * no length normalisation; BUTD_Model.py:236-318) for the prepared batch.  Device outputs:

@@ -24,6 +24,7 @@ SYMBOLS = (
     "capdec_abi_version", "capdec_create", "capdec_destroy", "capdec_last_error", "capdec_load_weight",
     "capdec_finalize_weights", "capdec_prepare", "capdec_beam_search", "capdec_sample", "capdec_launch_count",
     "capdec_test_gemm", "capdec_profile", "capdec_profile_read", "capdec_test_gemm_time",
+    "capdec_prepare_bottom_up", "capdec_get_refined",
 )
 CATEGORIES = ("gemm_lstm", "gemm_store", "gemm_glu", "gemm_logits", "attention", "bookkeeping", "other")
 
@@ -57,6 +58,8 @@ def load_library(path: str = LIB_PATH) -> ctypes.CDLL:
     lib.capdec_load_weight.argtypes = [vp, ctypes.c_char_p, vp, ctypes.POINTER(i64), i32, vp]
     lib.capdec_finalize_weights.argtypes = [vp, vp]
     lib.capdec_prepare.argtypes = [vp, vp, vp, i32, i32, vp]
+    lib.capdec_prepare_bottom_up.argtypes = [vp, vp, vp, i32, i32, vp]
+    lib.capdec_get_refined.argtypes = [vp, vp, vp]
     lib.capdec_beam_search.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
     lib.capdec_sample.argtypes = [vp, i32, i32, ctypes.c_uint64, i32, vp, vp, vp, vp]
     lib.capdec_launch_count.argtypes = [vp]
@@ -130,7 +133,7 @@ class CaptionDecoder:
         self.V, self.H, self.E = vocab_size, hidden_dim, embed_dim
         self.max_batch, self.max_rows, self.max_seq, self.max_regions = max_batch, max_rows, max_seq, max_regions
         self.math = math
-        cfg = CapdecConfig(ARCH[self.arch], hidden_dim, embed_dim, atten_dim, enc_dim if self.arch == "BUTD" else 0,
+        cfg = CapdecConfig(ARCH[self.arch], hidden_dim, embed_dim, atten_dim, enc_dim if self.arch != "NIC" else 0,
                            vocab_size, num_heads if self.arch == "AOA" else 0, max_batch,
                            0 if self.arch == "NIC" else max_regions, max_rows, max_seq, MATH[math], device)
         handle = ctypes.c_void_p()
@@ -142,6 +145,7 @@ class CaptionDecoder:
         self.stream = torch.cuda.Stream(self.device)
         self._keep = None
         self.B, self.R = 0, 0
+        self.has_refiner = False
         self._load(state_dict)
 
     # ------------------------------------------------------------------ plumbing
@@ -157,8 +161,11 @@ class CaptionDecoder:
             for key, val in state_dict.items():
                 if key.startswith("decoder."):
                     name = key[len("decoder."):]
+                elif self.arch == "AOA" and key.split(".")[0] in ("img_feats_porjection", "aoa_refine"):
+                    name = key  # AoA encoder side (projection + refiner): runs in the library too (prepare_bottom_up)
+                    self.has_refiner = True
                 elif "." in key and key.split(".")[0] in ("encoder", "img_feats_porjection", "aoa_refine"):
-                    continue  # encoder-side entries of the full captioner checkpoint are not part of the decode loop
+                    continue  # CNN encoder entries of the full captioner checkpoint are not part of this path
                 else:
                     name = key
                 if isinstance(val, np.ndarray):
@@ -213,6 +220,34 @@ class CaptionDecoder:
             torch.cuda.current_stream(self.device).wait_stream(self.stream)
         self._keep = (feats, mask)  # the library reads them during decode
         self.B, self.R = B, R
+
+    def prepare_bottom_up(self, bu_feats, mask=None):
+        """AoA only: bu_feats CUDA fp32 [B,R,enc_dim] (bottom-up / CNN grid features), mask [B,R] float prefix mask or
+        None -> img_feats_porjection + aoa_refine + prepare, all inside the library (AoA_Model.py:748-751)."""
+        torch = _torch()
+        if not self.has_refiner:
+            raise RuntimeError("prepare_bottom_up needs the checkpoint's img_feats_porjection.* / aoa_refine.* entries")
+        bu_feats = bu_feats.to(self.device, torch.float32).contiguous()
+        if mask is not None:
+            mask = mask.to(self.device, torch.float32).contiguous()
+        B, R = bu_feats.shape[0], bu_feats.shape[1]
+        with torch.cuda.device(self.device):
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            self._check(self.lib.capdec_prepare_bottom_up(self._h, bu_feats.data_ptr(), None if mask is None else mask.data_ptr(),
+                                                          B, R, self.stream.cuda_stream), "capdec_prepare_bottom_up")
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        self._keep = (bu_feats, mask)
+        self.B, self.R = B, R
+
+    def refined_features(self):
+        """Refined features [B,R,H] fp32 of the batch prepared by ``prepare_bottom_up`` (what aoa_refine returns)."""
+        torch = _torch()
+        out = torch.empty((self.B, self.R, self.H), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            self._check(self.lib.capdec_get_refined(self._h, out.data_ptr(), self.stream.cuda_stream), "capdec_get_refined")
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        return out
 
     def beam_search(self, beam: int, max_seq: int = 20, return_alphas: bool = False):
         """-> tokens [B,1+max_seq] int32 (<sta> first), seq_logprob [B] fp32, lengths [B] int32 (CUDA tensors)

@@ -118,6 +118,19 @@ struct capdec_handle {
     int* out_lengths = nullptr;
     float* alpha_step = nullptr;  // [Tmax, Mmax, Rmax] per-step attention maps (allocated on first request)
     int *hist_parent = nullptr, *best_pslot = nullptr;
+
+    // AoA encoder side in front of the decoder (img_feats_porjection + aoa_refine, AoA_Model.py:122-162,661-665):
+    // present when the checkpoint carries those entries; workspace allocated when they are finalized
+    struct RefineLayer {
+        Act16 W_qkv, W_glu;  // [3H, H] = linear_Q ; linear_K ; linear_V stacked, [2H, 2H] (a, gate)-interleaved
+        float *b_qkv = nullptr, *b_glu = nullptr;
+        const float *ln_gain = nullptr, *ln_bias = nullptr;
+    };
+    std::vector<RefineLayer> refine;
+    bool refiner_ready = false;
+    Act16 W_proj, bu16, XR, qkv16;  // projection weight [H, D]; fp16 bottom-up features; [att | LN(x)] operand; Q|K|V (fp16 mode)
+    float *b_proj = nullptr, *qkv32 = nullptr, *xres = nullptr, *refined = nullptr;
+    const float *rfinal_gain = nullptr, *rfinal_bias = nullptr;
 };
 
 namespace {
@@ -476,6 +489,192 @@ int finalize_aoa(capdec_handle* h, cudaStream_t st) {
     h->ln_gain = gn->d;
     h->ln_bias = bs->d;
     return build_embedding_gates(h, emb, 1, st);  // embed = Embedding + ReLU (AoA_Model.py:206-210)
+}
+
+// ------------------------------------------------------------------------------------------------ AoA encoder side
+bool has_refiner_weights(capdec_handle* h) { return find_raw(h, "img_feats_porjection.0.weight") != nullptr; }
+
+// Pack img_feats_porjection + every aoa_refine layer found in the checkpoint; allocate the refiner workspace (once).
+int finalize_refiner(capdec_handle* h, cudaStream_t st) {
+    const int H = h->H, D = h->D;
+    if (D <= 0 || D % 64) return fail(h, CAPDEC_ERR_INVALID, "AoA refiner needs enc_dim (bottom-up feature width) as a multiple of 64");
+    const Raw *w, *b, *gn, *bs;
+    const bool first = h->refine.empty();
+    if (first) {
+        CKS(h, alloc_act(h, &h->W_proj, H, D));
+        CKS(h, dalloc(h, &h->b_proj, H));
+    }
+    CKS(h, need(h, "img_feats_porjection.0.weight", {H, D}, &w));
+    CKS(h, need(h, "img_feats_porjection.0.bias", {H}, &b));
+    CKS(h, pack_segment(h, w, 0, D, nullptr, h->W_proj, 0, 0, 0, st));
+    CKS(h, pack_bias(h, b, nullptr, h->b_proj, H, 0, 0, st));
+    int n_layers = 0;
+    while (find_raw(h, "aoa_refine.aoa_layers." + std::to_string(n_layers) + ".aoa_block.linear_Q.weight")) ++n_layers;
+    if (n_layers == 0) return fail(h, CAPDEC_ERR_WEIGHT, "missing state_dict entry: aoa_refine.aoa_layers.0.aoa_block.linear_Q.weight");
+    if (!first && static_cast<int>(h->refine.size()) != n_layers) return fail(h, CAPDEC_ERR_WEIGHT, "number of aoa_refine layers changed");
+    if (first) h->refine.resize(n_layers);
+    for (int l = 0; l < n_layers; ++l) {
+        capdec_handle::RefineLayer& L = h->refine[l];
+        const std::string p = "aoa_refine.aoa_layers." + std::to_string(l) + ".";
+        if (first) {
+            CKS(h, alloc_act(h, &L.W_qkv, 3 * H, H));
+            CKS(h, alloc_act(h, &L.W_glu, 2 * H, 2 * H));
+            CKS(h, dalloc(h, &L.b_qkv, 3 * H));
+            CKS(h, dalloc(h, &L.b_glu, 2 * H));
+        }
+        const char* names[3] = {"linear_Q", "linear_K", "linear_V"};
+        for (int part = 0; part < 3; ++part) {  // one fused projection GEMM per layer: rows [Q ; K ; V]
+            CKS(h, need(h, p + "aoa_block." + names[part] + ".weight", {H, H}, &w));
+            CKS(h, need(h, p + "aoa_block." + names[part] + ".bias", {H}, &b));
+            Act16 blk = L.W_qkv;
+            blk.rows = H;
+            blk.p = L.W_qkv.p + static_cast<size_t>(part) * H * L.W_qkv.ld;
+            CKS(h, pack_segment(h, w, 0, H, nullptr, blk, 0, 0, 0, st));
+            CKS(h, pack_bias(h, b, nullptr, L.b_qkv + part * H, H, 0, 0, st));
+        }
+        CKS(h, need(h, p + "aoa_block.aoa_module.0.weight", {2 * H, 2 * H}, &w));
+        CKS(h, need(h, p + "aoa_block.aoa_module.0.bias", {2 * H}, &b));
+        CKS(h, pack_segment(h, w, 0, 2 * H, nullptr, L.W_glu, 0, 2, H, st));
+        CKS(h, pack_bias(h, b, nullptr, L.b_glu, 2 * H, 2, H, st));
+        CKS(h, need(h, p + "sublayer.norm.gain", {H}, &gn));
+        CKS(h, need(h, p + "sublayer.norm.bias", {H}, &bs));
+        L.ln_gain = gn->d;
+        L.ln_bias = bs->d;
+    }
+    CKS(h, need(h, "aoa_refine.norm.gain", {H}, &gn));
+    CKS(h, need(h, "aoa_refine.norm.bias", {H}, &bs));
+    h->rfinal_gain = gn->d;
+    h->rfinal_bias = bs->d;
+    if (first) {
+        const size_t BR = static_cast<size_t>(h->Bmax) * h->Rmax;
+        CKS(h, alloc_act(h, &h->bu16, static_cast<int>(BR), D));
+        CKS(h, alloc_act(h, &h->XR, static_cast<int>(BR), 2 * H));
+        if (h->split) CKS(h, dalloc(h, &h->qkv32, BR * 3 * H));
+        else CKS(h, alloc_act(h, &h->qkv16, static_cast<int>(BR), 3 * H));
+        CKS(h, dalloc(h, &h->xres, BR * H));
+        CKS(h, dalloc(h, &h->refined, BR * H));
+    }
+    h->refiner_ready = true;
+    return CAPDEC_OK;
+}
+
+template <int NKT, int DH>
+int launch_refine_att_mma_t(capdec_handle* h, int B, int R, const float* mask, cudaStream_t st) {
+    using C = RefineMmaCfg<NKT, DH>;
+    static bool attr_set = false;
+    auto kern = refine_attention_mma_kernel<NKT, DH>;
+    if (!attr_set) {
+        CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int units = B * h->NH;
+    const int per_sm = (227 * 1024) / (C::SMEM_BYTES + 1024) > 0 ? (227 * 1024) / (C::SMEM_BYTES + 1024) : 1;
+    int grid = (units + C::WARPS - 1) / C::WARPS;
+    if (grid > h->num_sms * per_sm) grid = h->num_sms * per_sm;
+    kern<<<grid, 32 * C::WARPS, C::SMEM_BYTES, st>>>(h->qkv16.p, h->qkv16.ld, mask, B, R, h->H, h->NH, h->XR.p, h->XR.ld);
+    return CAPDEC_OK;
+}
+template <int DH>
+int launch_refine_att_mma(capdec_handle* h, int B, int R, const float* mask, cudaStream_t st) {
+    if (R <= 48) return launch_refine_att_mma_t<3, DH>(h, B, R, mask, st);
+    if (R <= 64) return launch_refine_att_mma_t<4, DH>(h, B, R, mask, st);
+    if (R <= 112) return launch_refine_att_mma_t<7, DH>(h, B, R, mask, st);
+    return launch_refine_att_mma_t<13, DH>(h, B, R, mask, st);
+}
+
+// self-attention of one refiner layer: qkv -> XR[:, 0:H]
+int launch_refine_att(capdec_handle* h, int B, int R, const float* mask, cudaStream_t st) {
+    const int H = h->H, nh = h->NH, d = H / nh;
+    prof_begin(h, CAPDEC_CAT_ATTENTION, 0.0, st);
+    int status = CAPDEC_OK;
+    if (!h->split && R <= 208 && (d == 128 || d == 64) && h->att_variant != 1) {
+        status = d == 128 ? launch_refine_att_mma<128>(h, B, R, mask, st) : launch_refine_att_mma<64>(h, B, R, mask, st);
+    } else {
+        const size_t smem = (static_cast<size_t>(R) * (2 * d + 1) + 4 * (d + R)) * sizeof(float);
+        if (smem > 227 * 1024) return fail(h, CAPDEC_ERR_INVALID, "refiner attention tile does not fit shared memory");
+        if (h->split) {
+            static bool attr_set = false;
+            if (!attr_set) {
+                CK(h, cudaFuncSetAttribute(refine_attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                attr_set = true;
+            }
+            refine_attention_kernel<float><<<B * nh, 128, smem, st>>>(h->qkv32, 3 * H, mask, R, H, nh, h->XR.p, h->XR.ld, h->XR.lo);
+        } else {
+            static bool attr_set = false;
+            if (!attr_set) {
+                CK(h, cudaFuncSetAttribute(refine_attention_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                attr_set = true;
+            }
+            refine_attention_kernel<__half><<<B * nh, 128, smem, st>>>(h->qkv16.p, h->qkv16.ld, mask, R, H, nh, h->XR.p, h->XR.ld, h->XR.lo);
+        }
+    }
+    prof_end(h, st);
+    CKS(h, status);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    return CAPDEC_OK;
+}
+
+// bu_feats [B,R,D] fp32 (+ prefix mask [B,R]) -> h->refined [B*R, H] fp32
+int run_refiner(capdec_handle* h, const float* bu, const float* mask, int B, int R, cudaStream_t st) {
+    const int H = h->H, D = h->D;
+    const size_t BR = static_cast<size_t>(B) * R;
+    const int N = static_cast<int>(BR);
+    CUtensorMap ma, mb;
+    cvt_f16_kernel<<<grid_for(BR * D / 4), 256, 0, st>>>(bu, BR, D, h->bu16.p, h->bu16.ld, h->bu16.lo, 0);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    {  // x = relu(W_p bu + b_p), zeros in the padded rows (pack_wrapper, AoA_Model.py:650-655)
+        CKS(h, map_a(h, &ma, h->bu16));
+        CKS(h, map_b(h, &mb, h->W_proj));
+        EpiParams e{};
+        e.bias = h->b_proj;
+        e.out32 = h->xres;
+        e.ld32 = H;
+        e.relu = 1;
+        e.row_keep = mask;
+        CKS(h, launch_gemm(h, EPI_STORE, 1, ma, h->bu16.lo, mb, h->W_proj.lo, N, H, D, e, st));
+    }
+    for (auto& L : h->refine) {
+        // n = LN(x) -> XR[:, H:2H]  (SublayerConnection: norm first, AoA_Model.py:37)
+        prof_begin(h, CAPDEC_CAT_OTHER, 0.0, st);
+        aoa_layernorm_kernel<<<(N + 7) / 8, 256, 0, st>>>(h->xres, N, H, L.ln_gain, L.ln_bias, 1e-6f, h->XR.p + H, h->XR.ld, h->XR.lo);
+        prof_end(h, st);
+        CK(h, cudaGetLastError());
+        h->launches++;
+        {  // Q | K | V = n W^T + b  (AoA_Model.py:113-115), one GEMM
+            CKS(h, map_a(h, &ma, h->XR, H));
+            CKS(h, map_b(h, &mb, L.W_qkv));
+            EpiParams e{};
+            e.bias = L.b_qkv;
+            if (h->split) {
+                e.out32 = h->qkv32;
+                e.ld32 = 3 * H;
+            } else {
+                e.out16 = h->qkv16.p;
+                e.ld16 = h->qkv16.ld;
+            }
+            CKS(h, launch_gemm(h, EPI_STORE, 1, ma, h->XR.lo, mb, L.W_qkv.lo, N, 3 * H, H, e, st));
+        }
+        CKS(h, launch_refine_att(h, B, R, mask, st));
+        {  // x += GLU(W [att, n] + b)  (AoA_Model.py:118 + residual :38)
+            CKS(h, map_a(h, &ma, h->XR));
+            CKS(h, map_b(h, &mb, L.W_glu));
+            EpiParams e{};
+            e.bias = L.b_glu;
+            e.out32 = h->xres;
+            e.ld32 = H;
+            e.resid = h->xres;
+            e.ld_resid = H;
+            CKS(h, launch_gemm(h, EPI_GLU, 1, ma, h->XR.lo, mb, L.W_glu.lo, N, 2 * H, 2 * H, e, st));
+        }
+    }
+    prof_begin(h, CAPDEC_CAT_OTHER, 0.0, st);
+    aoa_layernorm_kernel<<<(N + 7) / 8, 256, 0, st>>>(h->xres, N, H, h->rfinal_gain, h->rfinal_bias, 1e-6f, nullptr, 0, 0, h->refined);
+    prof_end(h, st);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    return CAPDEC_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ per-arch steps
@@ -1060,7 +1259,10 @@ int capdec_finalize_weights(capdec_handle* h, void* stream) {
     CKS(h, finalize_predict(h, st));
     if (h->cfg.arch == CAPDEC_ARCH_BUTD) CKS(h, finalize_butd(h, st));
     else if (h->cfg.arch == CAPDEC_ARCH_NIC) CKS(h, finalize_nic(h, st));
-    else CKS(h, finalize_aoa(h, st));
+    else {
+        CKS(h, finalize_aoa(h, st));
+        if (has_refiner_weights(h)) CKS(h, finalize_refiner(h, st));
+    }
     CK(h, cudaStreamSynchronize(st));  // b_aff is read back; packing is a one-time load cost
     if (h->graph_exec) {  // kernel parameters baked into the captured decode (e.g. b_aff) may have changed
         cudaGraphExecDestroy(h->graph_exec);
@@ -1070,12 +1272,48 @@ int capdec_finalize_weights(capdec_handle* h, void* stream) {
     return CAPDEC_OK;
 }
 
+static int prepare_impl(capdec_handle* h, const float* feats, const float* mask, int32_t batch, int32_t regions, cudaStream_t st);
+
 int capdec_prepare(capdec_handle* h, const float* feats, const float* mask, int32_t batch, int32_t regions, void* stream) {
     if (!h) return CAPDEC_ERR_INVALID;
     if (!h->weights_ready) return fail(h, CAPDEC_ERR_STATE, "capdec_prepare before capdec_finalize_weights");
     if (!feats || batch <= 0 || batch > h->Bmax) return fail(h, CAPDEC_ERR_INVALID, "prepare: batch out of range or null feats");
+    CK(h, cudaSetDevice(h->cfg.device));
+    return prepare_impl(h, feats, mask, batch, regions, static_cast<cudaStream_t>(stream));
+}
+
+int capdec_prepare_bottom_up(capdec_handle* h, const float* bu_feats, const float* mask, int32_t batch, int32_t regions,
+                             void* stream) {
+    if (!h) return CAPDEC_ERR_INVALID;
+    if (!h->weights_ready) return fail(h, CAPDEC_ERR_STATE, "capdec_prepare_bottom_up before capdec_finalize_weights");
+    if (h->cfg.arch != CAPDEC_ARCH_AOA) return fail(h, CAPDEC_ERR_INVALID, "prepare_bottom_up: only the AoA captioners have an encoder-side refiner");
+    if (!h->refiner_ready)
+        return fail(h, CAPDEC_ERR_STATE, "prepare_bottom_up: the checkpoint carried no img_feats_porjection / aoa_refine entries");
+    if (!bu_feats || batch <= 0 || batch > h->Bmax) return fail(h, CAPDEC_ERR_INVALID, "prepare_bottom_up: batch out of range or null feats");
+    if (regions <= 0 || regions > h->Rmax) return fail(h, CAPDEC_ERR_INVALID, "prepare_bottom_up: regions out of range");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(h, cudaSetDevice(h->cfg.device));
+    h->prepared = false;
+    const float* m = nullptr;
+    if (mask) {  // library-owned copy first: the refiner and the (possibly replayed) decode read it at a fixed address
+        CK(h, cudaMemcpyAsync(h->mask_buf, mask, static_cast<size_t>(batch) * regions * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        m = h->mask_buf;
+    }
+    CKS(h, run_refiner(h, bu_feats, m, batch, regions, st));
+    return prepare_impl(h, h->refined, m, batch, regions, st);
+}
+
+int capdec_get_refined(capdec_handle* h, float* dst, void* stream) {
+    if (!h || !dst) return h ? fail(h, CAPDEC_ERR_INVALID, "get_refined: null destination") : CAPDEC_ERR_INVALID;
+    if (!h->refiner_ready || !h->prepared || h->feats != h->refined)
+        return fail(h, CAPDEC_ERR_STATE, "get_refined: no batch prepared with capdec_prepare_bottom_up");
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaMemcpyAsync(dst, h->refined, static_cast<size_t>(h->B) * h->R * h->H * sizeof(float), cudaMemcpyDeviceToDevice,
+                          static_cast<cudaStream_t>(stream)));
+    return CAPDEC_OK;
+}
+
+static int prepare_impl(capdec_handle* h, const float* feats, const float* mask, int32_t batch, int32_t regions, cudaStream_t st) {
     const int H = h->H, E = h->E;
     h->prepared = false;
     CUtensorMap ma, mb;
@@ -1162,7 +1400,8 @@ int capdec_prepare(capdec_handle* h, const float* feats, const float* mask, int3
     h->feats = feats;
     h->mask = nullptr;
     if (mask) {  // keep a copy: the decode loop (possibly a replayed graph) reads it at a fixed address
-        CK(h, cudaMemcpyAsync(h->mask_buf, mask, static_cast<size_t>(batch) * regions * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        if (mask != h->mask_buf)
+            CK(h, cudaMemcpyAsync(h->mask_buf, mask, static_cast<size_t>(batch) * regions * sizeof(float), cudaMemcpyDeviceToDevice, st));
         h->mask = h->mask_buf;
     }
     h->prepared = true;

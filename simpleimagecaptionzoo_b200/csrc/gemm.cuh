@@ -39,6 +39,10 @@ struct EpiParams {
     __half* out16;          // fp16 output (hi at col, lo at col+lo16 when lo16 > 0) or null
     int ld16;
     int lo16;
+    int relu;               // STORE: max(x, 0) after the bias (img_feats_porjection, AoA_Model.py:661-665)
+    const float* row_keep;  // STORE: per-row {0,1} flags or null; rows flagged 0 are stored as zeros (pack_wrapper's padding)
+    const float* resid;     // GLU: residual added to the gated output (SublayerConnection, AoA_Model.py:38); may alias out32
+    int ld_resid;
     // LSTM
     const float* rowadd;    // additive per-row-group term [M/rows_per_group, N] or null (hoisted, step-invariant part)
     int rowadd_ld;
@@ -141,6 +145,7 @@ __device__ __forceinline__ void epi_store(uint32_t taddr, int row, int n_base, i
     const EpiParams& e = p.epi;
     const bool row_ok = row < p.M;
     const bool vec_ok = (p.N & 3) == 0;
+    const bool keep = !(e.row_keep && row_ok && __ldg(e.row_keep + row) == 0.f);
 #pragma unroll 1
     for (int c = c0; c < c1; ++c) {
         const int n0 = n_base + c * 32;
@@ -152,6 +157,14 @@ __device__ __forceinline__ void epi_store(uint32_t taddr, int row, int n_base, i
 #pragma unroll
             for (int i = 0; i < 32; ++i)
                 if (n0 + i < p.N) v[i] += __ldg(e.bias + n0 + i);
+        }
+        if (e.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (!keep) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
         if (e.out32) {
             float* o = e.out32 + static_cast<size_t>(row) * e.ld32 + n0;
@@ -286,6 +299,14 @@ __device__ __forceinline__ void epi_glu(uint32_t taddr, int row, int n_base, int
         float y[16];
 #pragma unroll
         for (int u = 0; u < 16; ++u) y[u] = v[2 * u] * sigmoidf_acc(v[2 * u + 1]);
+        if (e.resid) {
+            const float* r = e.resid + static_cast<size_t>(row) * e.ld_resid + j0;
+#pragma unroll
+            for (int u = 0; u < 16; u += 4) {
+                const float4 q = *reinterpret_cast<const float4*>(r + u);
+                y[u] += q.x, y[u + 1] += q.y, y[u + 2] += q.z, y[u + 3] += q.w;
+            }
+        }
         if (e.out32) {
             float* o = e.out32 + static_cast<size_t>(row) * e.ld32 + j0;
 #pragma unroll

@@ -832,9 +832,10 @@ butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __
 
 // ================================================================================================ AoA pieces
 // LayerNorm of the reference (AoA_Model.py:14-25): gain*(x-mean)/(std_unbiased + eps) + bias.  One warp per row;
-// writes the fp16 operand (query for linear_Q and for the AoA gate GEMM).
+// writes the fp16 operand (query for linear_Q and for the AoA gate GEMM) and/or an fp32 copy (refined features).
 __global__ void aoa_layernorm_kernel(const float* __restrict__ h, int M, int H, const float* __restrict__ gain,
-                                     const float* __restrict__ bias, float eps, __half* __restrict__ q16, int ld16, int lo16) {
+                                     const float* __restrict__ bias, float eps, __half* __restrict__ q16, int ld16, int lo16,
+                                     float* __restrict__ out32 = nullptr) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -851,10 +852,222 @@ __global__ void aoa_layernorm_kernel(const float* __restrict__ h, int M, int H, 
     const float inv = 1.0f / (sd + eps);
     for (int i = lane; i < H; i += 32) {
         const float y = gain[i] * (x[i] - mean) * inv + bias[i];
-        __half hi, lo;
-        split_f16(y, hi, lo);
-        q16[static_cast<size_t>(row) * ld16 + i] = hi;
-        if (lo16 > 0) q16[static_cast<size_t>(row) * ld16 + lo16 + i] = lo;
+        if (out32) out32[static_cast<size_t>(row) * H + i] = y;
+        if (q16) {
+            __half hi, lo;
+            split_f16(y, hi, lo);
+            q16[static_cast<size_t>(row) * ld16 + i] = hi;
+            if (lo16 > 0) q16[static_cast<size_t>(row) * ld16 + lo16 + i] = lo;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ AoA refiner
+// Multi-head SELF-attention of one AoA_Refine_Block (AoA_Model.py:41-69, 90-117, 136-138): queries = keys = values =
+// the R regions of an image, per head  S = Q K^T / sqrt(d), masked_fill(mask == 0, -1e9), softmax over keys, X = P V.
+// q/k/v are column blocks of the fused projection output qkv [B*R, 3H] (Q | K | V).  Output: the "att" half of the
+// gate GEMM's operand [att | LN(x)].
+//
+// Generic form (fp32-grade mode, or head dims the fragment kernel does not take): one CTA per (image, head), K and V of
+// the head in shared memory as fp32, one warp per query row: lanes <-> keys for the scores, lanes <-> columns for P V.
+template <typename T>
+__device__ __forceinline__ float ld_as_float(const T* p);
+template <>
+__device__ __forceinline__ float ld_as_float<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float ld_as_float<__half>(const __half* p) { return __half2float(*p); }
+
+template <typename T>
+__global__ void __launch_bounds__(128) refine_attention_kernel(const T* __restrict__ qkv, int ld, const float* __restrict__ mask,
+                                                               int R, int H, int nh, __half* __restrict__ x16, int ld16,
+                                                               int lo16) {
+    extern __shared__ float rsm[];
+    const int d = H / nh;
+    const int img = blockIdx.x / nh, hd = blockIdx.x - img * nh;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    float* s_k = rsm;                     // [R][d+1]
+    float* s_v = s_k + R * (d + 1);       // [R][d]
+    float* s_q = s_v + R * d;             // [nwarp][d]
+    float* s_p = s_q + nwarp * d;         // [nwarp][R]
+    const T* base = qkv + static_cast<size_t>(img) * R * ld + hd * d;
+    for (int i = threadIdx.x; i < R * d; i += blockDim.x) {
+        const int r = i / d, c = i - r * d;
+        s_k[r * (d + 1) + c] = ld_as_float<T>(base + static_cast<size_t>(r) * ld + H + c);
+        s_v[r * d + c] = ld_as_float<T>(base + static_cast<size_t>(r) * ld + 2 * H + c);
+    }
+    __syncthreads();
+    const float inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(d));
+    float* q = s_q + warp * d;
+    float* p = s_p + warp * R;
+    for (int qr = warp; qr < R; qr += nwarp) {
+        for (int c = lane; c < d; c += 32) q[c] = ld_as_float<T>(base + static_cast<size_t>(qr) * ld + c);
+        __syncwarp();
+        float m = -INFINITY;
+        for (int r = lane; r < R; r += 32) {
+            float acc = 0.f;
+            const float* kr = s_k + r * (d + 1);
+            for (int c = 0; c < d; ++c) acc = fmaf(q[c], kr[c], acc);
+            acc *= inv_sqrt_d;
+            if (mask && mask[static_cast<size_t>(img) * R + r] == 0.f) acc = -1e9f;
+            p[r] = acc;
+            m = fmaxf(m, acc);
+        }
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int r = lane; r < R; r += 32) {
+            const float ex = expf(p[r] - m);
+            p[r] = ex;
+            sum += ex;
+        }
+        sum = warp_sum(sum);
+        __syncwarp();
+        for (int c = lane; c < d; c += 32) {
+            float acc = 0.f;
+            for (int r = 0; r < R; ++r) acc = fmaf(p[r] / sum, s_v[r * d + c], acc);
+            __half hi, lo;
+            split_f16(acc, hi, lo);
+            __half* o = x16 + (static_cast<size_t>(img) * R + qr) * ld16 + hd * d + c;
+            *o = hi;
+            if (lo16 > 0) o[lo16] = lo;
+        }
+        __syncwarp();
+    }
+}
+
+// Fragment form (fp16 mode): one warp per (image, head).  The head's Q, K, V slices ([R, DH] fp16 each) are copied to
+// the warp's own shared-memory tiles (rows padded by 16 B -> conflict-free ldmatrix) with cp.async; then per 16-query
+// tile  S = Q K^T  (m16n8k16: A = Q via ldmatrix, B = K rows via ldmatrix), the softmax over the keys on the accumulator
+// fragments (row statistics via quad shuffles), P re-packed in registers as the A operand of  X = P V  (B = V via
+// ldmatrix.trans).  NKT = ceil(R / 16) key tiles (template), DH = head dim.
+template <int NKT, int DH>
+struct RefineMmaCfg {
+    static constexpr int ROWS = 16 * NKT;
+    static constexpr int LDS = DH + 8;                       // halves per shared-memory row
+    static constexpr int WARP_BYTES = 3 * ROWS * LDS * 2;    // Q, K, V tiles of one warp
+    static constexpr int WARPS = (200 * 1024 / WARP_BYTES) >= 4 ? 4 : ((200 * 1024 / WARP_BYTES) >= 2 ? 2 : 1);
+    static constexpr int SMEM_BYTES = WARPS * WARP_BYTES;
+};
+
+template <int NKT, int DH>
+__global__ void __launch_bounds__(32 * RefineMmaCfg<NKT, DH>::WARPS)
+refine_attention_mma_kernel(const __half* __restrict__ qkv, int ld, const float* __restrict__ mask, int B, int R, int H, int nh,
+                            __half* __restrict__ x16, int ld16) {
+    using C = RefineMmaCfg<NKT, DH>;
+    extern __shared__ __align__(128) uint8_t rf_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    __half* tile = reinterpret_cast<__half*>(rf_smem + warp * C::WARP_BYTES);
+    const uint32_t sq = smem_u32(tile), sk = sq + C::ROWS * C::LDS * 2, sv = sk + C::ROWS * C::LDS * 2;
+    // rows R .. ROWS-1 are never written by the copies: zero them once (0 * garbage must not become NaN)
+    for (int i = lane; i < 3 * C::ROWS * C::LDS / 2; i += 32) reinterpret_cast<uint32_t*>(tile)[i] = 0u;
+    __syncwarp();
+    // ldmatrix lane offsets: "a" = 16x16 block as the A operand / V^T via .trans; "b" = two 8-key groups as the B operand
+    const uint32_t off_a = (((lane & 7) + ((lane >> 3) & 1) * 8) * C::LDS + (lane >> 4) * 8) * 2;
+    const uint32_t off_b = (((lane & 7) + ((lane >> 4) & 1) * 8) * C::LDS + ((lane >> 3) & 1) * 8) * 2;
+    const float scale = rsqrtf(static_cast<float>(DH)) * LOG2E;  // exp(x) = exp2(x * log2 e)
+    constexpr int CH = DH / 8;                                     // 16-byte chunks per row slice
+    const int units = B * nh;
+    for (int u = blockIdx.x * C::WARPS + warp; u < units; u += gridDim.x * C::WARPS) {
+        const int img = u / nh, hd = u - img * nh;
+        const __half* src = qkv + static_cast<size_t>(img) * R * ld + hd * DH;
+        for (int i = lane; i < 3 * R * CH; i += 32) {
+            const int part = i / (R * CH), rem = i - part * (R * CH);
+            const int r = rem / CH, c = rem - r * CH;
+            cp_async_16(sq + (part * C::ROWS * C::LDS + r * C::LDS + c * 8) * 2, src + static_cast<size_t>(r) * ld + part * H + c * 8);
+        }
+        cp_async_commit();
+        // key status bits of this lane's columns: bit (2*nt + e) <-> key nt*8 + 2t + e
+        uint64_t in_range = 0, keep = 0;
+#pragma unroll
+        for (int nt = 0; nt < 2 * NKT; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int key = nt * 8 + 2 * t + e;
+                if (key < R) {
+                    in_range |= 1ull << (2 * nt + e);
+                    if (!mask || __ldg(mask + static_cast<size_t>(img) * R + key) != 0.f) keep |= 1ull << (2 * nt + e);
+                }
+            }
+        }
+        cp_async_wait_all();
+        __syncwarp();
+        for (int mt = 0; mt * 16 < R; ++mt) {
+            float s[2 * NKT][4];
+#pragma unroll
+            for (int nt = 0; nt < 2 * NKT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < DH / 16; ++ks) {
+                uint32_t a[4];
+                ldmatrix_x4(a, sq + (mt * 16 * C::LDS + ks * 16) * 2 + off_a);
+#pragma unroll
+                for (int kt = 0; kt < NKT; ++kt) {
+                    uint32_t b[4];
+                    ldmatrix_x4(b, sk + (kt * 16 * C::LDS + ks * 16) * 2 + off_b);
+                    mma_m16n8k16_f16(s[2 * kt], a[0], a[1], a[2], a[3], b[0], b[1]);
+                    mma_m16n8k16_f16(s[2 * kt + 1], a[0], a[1], a[2], a[3], b[2], b[3]);
+                }
+            }
+            // softmax over the keys for rows g (elements 0,1) and g+8 (elements 2,3), in the log2 domain
+            float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < 2 * NKT; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const bool in = (in_range >> (2 * nt + e)) & 1, kp = (keep >> (2 * nt + e)) & 1;
+                    const float lo = in ? (kp ? 0.f : -1e9f * LOG2E) : -INFINITY;
+                    s[nt][e] = (in && kp) ? s[nt][e] * scale : lo;
+                    s[nt][2 + e] = (in && kp) ? s[nt][2 + e] * scale : lo;
+                    m0 = fmaxf(m0, s[nt][e]);
+                    m1 = fmaxf(m1, s[nt][2 + e]);
+                }
+            }
+            m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+            m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+            m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+            m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+            float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 2 * NKT; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    s[nt][e] = exp2f(s[nt][e] - m0);
+                    s[nt][2 + e] = exp2f(s[nt][2 + e] - m1);
+                    sum0 += s[nt][e];
+                    sum1 += s[nt][2 + e];
+                }
+            }
+            sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+            sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+            sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+            sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+            const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+            float o[DH / 8][4];
+#pragma unroll
+            for (int j = 0; j < DH / 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+#pragma unroll
+            for (int kt = 0; kt < NKT; ++kt) {
+                const uint32_t a0 = pack_h2(s[2 * kt][0] * inv0, s[2 * kt][1] * inv0);
+                const uint32_t a1 = pack_h2(s[2 * kt][2] * inv1, s[2 * kt][3] * inv1);
+                const uint32_t a2 = pack_h2(s[2 * kt + 1][0] * inv0, s[2 * kt + 1][1] * inv0);
+                const uint32_t a3 = pack_h2(s[2 * kt + 1][2] * inv1, s[2 * kt + 1][3] * inv1);
+#pragma unroll
+                for (int dn = 0; dn < DH / 16; ++dn) {
+                    uint32_t b[4];
+                    ldmatrix_x4_trans(b, sv + (kt * 16 * C::LDS + dn * 16) * 2 + off_a);
+                    mma_m16n8k16_f16(o[2 * dn], a0, a1, a2, a3, b[0], b[1]);
+                    mma_m16n8k16_f16(o[2 * dn + 1], a0, a1, a2, a3, b[2], b[3]);
+                }
+            }
+            const int q0 = mt * 16 + g, q1 = q0 + 8;
+            __half* o0 = x16 + (static_cast<size_t>(img) * R + q0) * ld16 + hd * DH + 2 * t;
+            __half* o1 = o0 + static_cast<size_t>(8) * ld16;
+#pragma unroll
+            for (int j = 0; j < DH / 8; ++j) {
+                if (q0 < R) *reinterpret_cast<uint32_t*>(o0 + 8 * j) = pack_h2(o[j][0], o[j][1]);
+                if (q1 < R) *reinterpret_cast<uint32_t*>(o1 + 8 * j) = pack_h2(o[j][2], o[j][3]);
+            }
+        }
+        __syncwarp();  // all lanes are done with the tiles before the next unit's copies land
     }
 }
 

@@ -83,6 +83,12 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc
                  "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// 16-byte asynchronous copy global -> shared (per thread), grouped and awaited by the issuing thread.
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(gsrc)) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

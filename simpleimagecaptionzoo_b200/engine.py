@@ -15,8 +15,9 @@ Utils.py:72-73); the beam step limit is ``max_seq`` (default 20, BASELINE.json) 
 float32 CPU tensor of ragged length when a hypothesis completed, BUTD_Model.py:309) -- ``Engine.py:288-296`` stops at
 <end> and skips <sta>, so the id->word loop downstream is unchanged.
 
-The decode loop itself runs in libcapdec.so (``capdec.CaptionDecoder``); encoders that sit in front of it (ResNet-101,
-the AoA refiner) are out of this path's scope and are taken as a plain callable ``feature_fn(visual_inputs)``.
+The decode loop itself runs in libcapdec.so (``capdec.CaptionDecoder``), and so does the AoA captioners' encoder-side
+half (``img_feats_porjection`` + ``aoa_refine``, AoA_Model.py:748-751) whenever the checkpoint carries its entries.  The
+CNN encoders (ResNet-101) stay outside this path and are taken as a plain callable ``feature_fn(visual_inputs)``.
 """
 from __future__ import annotations
 
@@ -46,7 +47,8 @@ class B200Captioner:
     """Extension-backed stand-in for the reference's ``*_Captioner`` modules on the decode path."""
 
     def __init__(self, model_type: str, settings: Mapping[str, object], vocab_size: int, state_dict: Mapping[str, object], *,
-                 feature_fn: Optional[Callable] = None, max_batch: int = 64, max_regions: Optional[int] = None,
+                 feature_fn: Optional[Callable] = None, feature_fn_returns: str = "decoder_input", max_batch: int = 64,
+                 max_regions: Optional[int] = None,
                  max_rows: int = 5, max_seq: int = 20, math: str = "f16", device: int = 0, enc_dim: int = 2048,
                  num_heads: int = 8, sample_seed: int = 0):
         if model_type not in MODEL_ARCH:
@@ -67,6 +69,21 @@ class B200Captioner:
             atten_dim=int(self.settings.get("atten_dim", 0) or 0), enc_dim=enc_dim, num_heads=num_heads,
             max_batch=max_batch, max_regions=max_regions, max_rows=max_rows, max_seq=max_seq, math=math, device=device)
         self.device = self.decoder.device
+        # AoA: run img_feats_porjection + aoa_refine in the library when the checkpoint has them and the features handed
+        # over are the bottom-up / CNN-grid ones (``feature_fn_returns="bottom_up"``, or no feature_fn for AoADetection)
+        if feature_fn_returns not in ("decoder_input", "bottom_up"):
+            raise ValueError("feature_fn_returns must be 'decoder_input' or 'bottom_up'")
+        self.native_refiner = (self.arch == "AOA" and self.decoder.has_refiner
+                               and (feature_fn is None or feature_fn_returns == "bottom_up"))
+        if self.arch == "AOA" and feature_fn is None and not self.decoder.has_refiner and model_type == "AoADetection":
+            raise RuntimeError("AoADetection: the checkpoint has no img_feats_porjection / aoa_refine entries; pass a "
+                               "feature_fn that returns the refined features")
+
+    def _prepare(self, feats, mask):
+        if self.native_refiner:
+            self.decoder.prepare_bottom_up(feats, mask)
+        else:
+            self.decoder.prepare(feats, mask)
 
     # nn.Module surface the Engine touches
     def eval(self):
@@ -106,7 +123,7 @@ class B200Captioner:
     # ------------------------------------------------------------------ the three decode methods
     def beam_search_sampler(self, visual_inputs, beam_size: int = 5, max_seq: Optional[int] = None):
         feats, mask = self._features(visual_inputs)
-        self.decoder.prepare(feats, mask)
+        self._prepare(feats, mask)
         tokens, self.last_scores, self.last_lengths = self.decoder.beam_search(beam_size, max_seq or self.max_seq)
         return tokens.long()
 
@@ -156,7 +173,7 @@ class B200Captioner:
             except StopIteration:
                 nxt = None
             main.wait_event(cur["ready"])
-            self.decoder.prepare(cur["buf"], cur["mask"])
+            self._prepare(cur["buf"], cur["mask"])
             tokens, _, _ = self.decoder.beam_search(beam_size, T)
             cur["free"] = torch.cuda.Event()
             cur["free"].record(main)
@@ -177,7 +194,7 @@ class B200Captioner:
 
     def sampler(self, visual_inputs, max_len: int = 20):
         feats, mask = self._features(visual_inputs)
-        self.decoder.prepare(feats, mask)
+        self._prepare(feats, mask)
         tokens, _ = self.decoder.sample(capdec.SAMPLE_GREEDY, 1, 0, max_len)
         return tokens.long()
 
@@ -187,7 +204,7 @@ class B200Captioner:
         ``show_additional_rlt`` plots -- or (caption, []) for NIC."""
         feats, mask = self._features(visual_inputs)
         assert feats.shape[0] == 1
-        self.decoder.prepare(feats, mask)
+        self._prepare(feats, mask)
         want = self.arch != "NIC"
         if eval_beam_size != -1:
             out = self.decoder.beam_search(eval_beam_size, self.max_seq, return_alphas=want)
@@ -209,7 +226,7 @@ class B200Captioner:
         """Multinomial rollout (eval-mode numerics; forward only -- the SCST backward pass is out of scope).
         ``n_per_image`` > 1 draws several samples per image while reading its features once (BASELINE config 5)."""
         feats, mask = self._features(visual_inputs)
-        self.decoder.prepare(feats, mask)
+        self._prepare(feats, mask)
         if seed is None:
             seed = self._seed + self._calls
             self._calls += 1
@@ -359,15 +376,13 @@ def install(engine, state_dict=None, **decoder_kwargs):
         feature_fn = lambda vi: ref.encoder(vi["img_tensors"])  # noqa: E731  NIC_Model.py:277
     elif model_type == "BUTDSpatial":
         feature_fn = lambda vi: ref.encoder(vi["img_tensors"])  # noqa: E731  BUTD_Model.py:382
-    elif model_type == "AoADetection":
-        def feature_fn(vi):  # AoA_Model.py:748-751
-            masks = vi.get("bu_masks")
-            return ref.aoa_refine(ref.img_feats_porjection(vi["bu_feats"]), masks), masks
     elif model_type == "AoASpatial":
-        def feature_fn(vi):  # AoA_Model.py:588-593
-            return ref.aoa_refine(ref.img_feats_porjection(ref.encoder(vi["img_tensors"])), None), None
+        # the CNN grid features; img_feats_porjection + aoa_refine (AoA_Model.py:598-601) run inside the library
+        feature_fn = lambda vi: ref.encoder(vi["img_tensors"])  # noqa: E731
+    # AoADetection: no feature_fn -- bu_feats / bu_masks go straight to the library (AoA_Model.py:748-751)
     dev = str(engine.device)
     fast = B200Captioner(model_type, engine.settings, len(engine.caption_vocab), sd, feature_fn=feature_fn,
+                         feature_fn_returns="bottom_up" if model_type == "AoASpatial" else "decoder_input",
                          device=int(dev.split(":")[1]) if ":" in dev else 0, **decoder_kwargs)
     ref.sampler, ref.sampler_rl, ref.beam_search_sampler = fast.sampler, fast.sampler_rl, fast.beam_search_sampler
     ref.eval_test_image = fast.eval_test_image

@@ -307,3 +307,104 @@ def test_engine_mirror_generates_reference_format():
     assert same >= 38
     greedy = eng.eval_captions_json_generation(loader, eval_beam_size=-1)
     assert len(greedy) == 40 and all(isinstance(o["caption"], str) for o in greedy)
+
+
+# ---------------------------------------------------------------------------------------------------
+# AoA encoder side (img_feats_porjection + aoa_refine) in the library: SURVEY.md section 8f row 1
+# ---------------------------------------------------------------------------------------------------
+from tests.golden_util import rebuild_refiner  # noqa: E402
+
+REFINER = case_names("aoaref")
+# stated bounds on |refined - reference| (LayerNorm-ed, O(1) values after six residual layers)
+REFINED_BOUND = {"f16x3": 1e-3, "f16": 6e-2}
+
+
+def _make_refiner(meta, math, env=None):
+    capdec = _capdec()
+    sd, bu, mask = rebuild_refiner(meta)
+    d = meta["dims"]
+    dec = capdec.CaptionDecoder("AOA", sd, hidden_dim=d["hidden_dim"], embed_dim=d["embed_dim"], vocab_size=d["vocab_size"],
+                                enc_dim=meta["enc_dim"], num_heads=d["num_heads"], max_batch=meta["B"], max_regions=meta["R"],
+                                max_rows=meta["K"], max_seq=meta["T"], math=math)
+    assert dec.has_refiner
+    dec.prepare_bottom_up(torch.from_numpy(bu).cuda(), None if mask is None else torch.from_numpy(mask).cuda())
+    return dec, sd, bu, mask
+
+
+@pytest.mark.parametrize("name", REFINER)
+@pytest.mark.parametrize("math", ["f16x3", "f16"])
+def test_refined_features_match_reference(name, math):
+    """capdec_prepare_bottom_up's refined features against the reference's ``aoa_refine`` output (golden) and the oracle."""
+    meta, gold = load_case(name)
+    dec, sd, bu, mask = _make_refiner(meta, math)
+    got = dec.refined_features().cpu().numpy()
+    valid = np.ones(got.shape[:2], bool) if mask is None else mask.astype(bool)
+    err_gold = np.abs(got[:, :, ::meta["store_stride"]] - gold["refined"])[valid].max()
+    ref = orc.aoa_project_refine(sd, bu, mask, num_heads=meta["dims"]["num_heads"])
+    err_orc = np.abs(got - ref)[valid].max()
+    assert err_gold < REFINED_BOUND[math] and err_orc < REFINED_BOUND[math], (err_gold, err_orc)
+    dec.close()
+
+
+@pytest.mark.parametrize("name", REFINER)
+def test_bottom_up_to_caption_fp32_grade(name):
+    """Whole AoADetection path (projection, refiner, beam search / greedy) in the f16x3 mode against the reference's
+    tokens: the reference decodes one image per call on the image's own regions, the library a masked batch."""
+    meta, gold = load_case(name)
+    dec, sd, bu, mask = _make_refiner(meta, "f16x3")
+    tok, score, length = dec.beam_search(meta["K"], meta["T"])
+    greedy, _ = dec.sample(_capdec().SAMPLE_GREEDY, 1, 0, meta["T"])
+    torch.cuda.synchronize()
+    o = orc.make_decoder("AOA", sd, num_heads=meta["dims"]["num_heads"])
+    o.prepare(orc.aoa_project_refine(sd, bu, mask, num_heads=meta["dims"]["num_heads"]), mask)
+    res = orc.beam_search_batched(o, meta["K"], meta["T"])
+    verdict = orc.agreement(tok.cpu().numpy(), gold["tokens"], res.min_gap, tol=1e-4)
+    assert "diff" not in verdict, verdict
+    assert np.mean([v == "exact" for v in verdict]) >= 0.9
+    ids, gaps, _ = orc.greedy_sample(o, meta["T"])
+    g = greedy.cpu().numpy()
+    for b in range(meta["B"]):
+        if not np.array_equal(g[b], gold["greedy"][b]):
+            t = int(np.argmax(g[b] != gold["greedy"][b]))
+            assert gaps[b, t] < 1e-4, (b, t, gaps[b, t])
+    dec.close()
+
+
+def test_bottom_up_fp16_mode_full_dims():
+    """Throughput mode at BASELINE dims: captions from bottom-up features agree with the oracle or are tie-justified at the
+    fp16 operand-rounding level (gap below the stated score bound)."""
+    meta, gold = load_case("aoaref_full_k3")
+    dec, sd, bu, mask = _make_refiner(meta, "f16")
+    tok, score, _ = dec.beam_search(meta["K"], meta["T"])
+    torch.cuda.synchronize()
+    o = orc.make_decoder("AOA", sd, num_heads=meta["dims"]["num_heads"])
+    o.prepare(orc.aoa_project_refine(sd, bu, mask, num_heads=meta["dims"]["num_heads"]), mask)
+    res = orc.beam_search_batched(o, meta["K"], meta["T"])
+    verdict = orc.agreement(tok.cpu().numpy(), res.tokens, res.min_gap, tol=F16_SCORE_BOUND)
+    assert "diff" not in verdict, verdict
+    exact = np.array([v == "exact" for v in verdict])
+    assert np.allclose(score.cpu().numpy()[exact], res.scores[exact], atol=F16_SCORE_BOUND)
+    dec.close()
+
+
+def test_refiner_generic_attention_kernel_matches(monkeypatch):
+    """The non-fragment self-attention kernel (CAPDEC_ATT_VARIANT=1) gives the same refined features in fp16 mode."""
+    meta, gold = load_case("aoaref_full_k3_masked")
+    dec, sd, bu, mask = _make_refiner(meta, "f16")
+    a = dec.refined_features().cpu().numpy()
+    dec.close()
+    monkeypatch.setenv("CAPDEC_ATT_VARIANT", "1")
+    dec, *_ = _make_refiner(meta, "f16")
+    b = dec.refined_features().cpu().numpy()
+    dec.close()
+    valid = mask.astype(bool)
+    assert np.abs(a - b)[valid].max() < 2e-2
+
+
+def test_bottom_up_needs_refiner_weights():
+    meta, _ = load_case("aoa_tiny_k3")
+    dec, *_ = _make(meta, "f16")
+    assert not dec.has_refiner
+    with pytest.raises(RuntimeError, match="img_feats_porjection"):
+        dec.prepare_bottom_up(torch.zeros(2, meta["R"], 2048).cuda())
+    dec.close()
