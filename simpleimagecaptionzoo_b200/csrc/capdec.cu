@@ -226,10 +226,12 @@ int launch_gemm_t(capdec_handle* h, const CUtensorMap& ma, const CUtensorMap& mb
     }
     const int tiles = p.runs > 0 ? p.num_m_blocks * p.runs : p.num_m_blocks * p.num_n_blocks;
     const int grid = tiles < h->num_sms ? tiles : h->num_sms;
+    GemmParams pg = p;
+    pg.m_group = grid;
     const int cat = EPI == EPI_LSTM ? CAPDEC_CAT_GEMM_LSTM : EPI == EPI_STORE ? CAPDEC_CAT_GEMM_STORE
                   : EPI == EPI_GLU ? CAPDEC_CAT_GEMM_GLU : CAPDEC_CAT_GEMM_LOGITS;
     prof_begin(h, cat, 2.0 * p.M * p.N * (static_cast<double>(p.k_blocks) * BLOCK_K), st);
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, pg);
     prof_end(h, st);
     CK(h, cudaGetLastError());
     h->launches++;
@@ -247,10 +249,12 @@ int launch_gemm2_t(capdec_handle* h, const CUtensorMap& ma, const CUtensorMap& m
     }
     const int items = p.runs > 0 ? p.num_m_blocks * p.runs : p.num_m_blocks * p.num_n_blocks;
     const int pairs = items < h->num_sms / 2 ? items : h->num_sms / 2;
+    GemmParams pg = p;
+    pg.m_group = pairs;
     const int cat = EPI == EPI_LSTM ? CAPDEC_CAT_GEMM_LSTM : EPI == EPI_STORE ? CAPDEC_CAT_GEMM_STORE
                   : EPI == EPI_GLU ? CAPDEC_CAT_GEMM_GLU : CAPDEC_CAT_GEMM_LOGITS;
     prof_begin(h, cat, 2.0 * p.M * p.N * (static_cast<double>(p.k_blocks) * BLOCK_K), st);
-    kern<<<2 * pairs, GEMM_THREADS, GemmCfg2::SMEM_BYTES, st>>>(ma, mb, p);
+    kern<<<2 * pairs, GEMM_THREADS, GemmCfg2::SMEM_BYTES, st>>>(ma, mb, pg);
     prof_end(h, st);
     CK(h, cudaGetLastError());
     h->launches++;
@@ -491,6 +495,19 @@ int finalize_aoa(capdec_handle* h, cudaStream_t st) {
     return build_embedding_gates(h, emb, 1, st);  // embed = Embedding + ReLU (AoA_Model.py:206-210)
 }
 
+// reference LayerNorm over the rows of x [M, H] -> fp16 operand and/or fp32 copy
+int launch_layernorm(capdec_handle* h, const float* x, int M, const float* gain, const float* bias, __half* q16, int ld16, int lo16,
+                     float* out32, cudaStream_t st) {
+    prof_begin(h, CAPDEC_CAT_OTHER, 0.0, st);
+    if (h->H == 1024) aoa_layernorm_vec_kernel<8><<<(M + 7) / 8, 256, 0, st>>>(x, M, gain, bias, 1e-6f, q16, ld16, lo16, out32);
+    else if (h->H == 512) aoa_layernorm_vec_kernel<4><<<(M + 7) / 8, 256, 0, st>>>(x, M, gain, bias, 1e-6f, q16, ld16, lo16, out32);
+    else aoa_layernorm_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, M, h->H, gain, bias, 1e-6f, q16, ld16, lo16, out32);
+    prof_end(h, st);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    return CAPDEC_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ AoA encoder side
 bool has_refiner_weights(capdec_handle* h) { return find_raw(h, "img_feats_porjection.0.weight") != nullptr; }
 
@@ -558,28 +575,29 @@ int finalize_refiner(capdec_handle* h, cudaStream_t st) {
     return CAPDEC_OK;
 }
 
-template <int NKT, int DH>
+template <int NKT, int DH, int G>
 int launch_refine_att_mma_t(capdec_handle* h, int B, int R, const float* mask, cudaStream_t st) {
-    using C = RefineMmaCfg<NKT, DH>;
+    using C = RefineMmaCfg<NKT, DH, G>;
     static bool attr_set = false;
-    auto kern = refine_attention_mma_kernel<NKT, DH>;
+    auto kern = refine_attention_mma_kernel<NKT, DH, G>;
     if (!attr_set) {
         CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_set = true;
     }
-    const int units = B * h->NH;
-    const int per_sm = (227 * 1024) / (C::SMEM_BYTES + 1024) > 0 ? (227 * 1024) / (C::SMEM_BYTES + 1024) : 1;
-    int grid = (units + C::WARPS - 1) / C::WARPS;
-    if (grid > h->num_sms * per_sm) grid = h->num_sms * per_sm;
-    kern<<<grid, 32 * C::WARPS, C::SMEM_BYTES, st>>>(h->qkv16.p, h->qkv16.ld, mask, B, R, h->H, h->NH, h->XR.p, h->XR.ld);
+    const int items = B * (h->NH / G);
+    const int cap = h->num_sms * C::CTAS_PER_SM;
+    kern<<<items < cap ? items : cap, 32 * C::WARPS, C::SMEM_BYTES, st>>>(h->qkv16.p, h->qkv16.ld, mask, B, R, h->H, h->NH, h->XR.p,
+                                                                           h->XR.ld);
     return CAPDEC_OK;
 }
+// (query/key tiles, heads per CTA)
 template <int DH>
 int launch_refine_att_mma(capdec_handle* h, int B, int R, const float* mask, cudaStream_t st) {
-    if (R <= 48) return launch_refine_att_mma_t<3, DH>(h, B, R, mask, st);
-    if (R <= 64) return launch_refine_att_mma_t<4, DH>(h, B, R, mask, st);
-    if (R <= 112) return launch_refine_att_mma_t<7, DH>(h, B, R, mask, st);
-    return launch_refine_att_mma_t<13, DH>(h, B, R, mask, st);
+    const int nh = h->NH;
+    if (R <= 48) return launch_refine_att_mma_t<3, DH, 1>(h, B, R, mask, st);
+    if (R <= 64 && nh % 2 == 0) return launch_refine_att_mma_t<4, DH, 2>(h, B, R, mask, st);
+    if (R <= 112 && nh % 2 == 0) return launch_refine_att_mma_t<7, DH, 2>(h, B, R, mask, st);
+    return launch_refine_att_mma_t<13, DH, 1>(h, B, R, mask, st);
 }
 
 // self-attention of one refiner layer: qkv -> XR[:, 0:H]
@@ -637,11 +655,7 @@ int run_refiner(capdec_handle* h, const float* bu, const float* mask, int B, int
     }
     for (auto& L : h->refine) {
         // n = LN(x) -> XR[:, H:2H]  (SublayerConnection: norm first, AoA_Model.py:37)
-        prof_begin(h, CAPDEC_CAT_OTHER, 0.0, st);
-        aoa_layernorm_kernel<<<(N + 7) / 8, 256, 0, st>>>(h->xres, N, H, L.ln_gain, L.ln_bias, 1e-6f, h->XR.p + H, h->XR.ld, h->XR.lo);
-        prof_end(h, st);
-        CK(h, cudaGetLastError());
-        h->launches++;
+        CKS(h, launch_layernorm(h, h->xres, N, L.ln_gain, L.ln_bias, h->XR.p + H, h->XR.ld, h->XR.lo, nullptr, st));
         {  // Q | K | V = n W^T + b  (AoA_Model.py:113-115), one GEMM
             CKS(h, map_a(h, &ma, h->XR, H));
             CKS(h, map_b(h, &mb, L.W_qkv));
@@ -669,12 +683,7 @@ int run_refiner(capdec_handle* h, const float* bu, const float* mask, int B, int
             CKS(h, launch_gemm(h, EPI_GLU, 1, ma, h->XR.lo, mb, L.W_glu.lo, N, 2 * H, 2 * H, e, st));
         }
     }
-    prof_begin(h, CAPDEC_CAT_OTHER, 0.0, st);
-    aoa_layernorm_kernel<<<(N + 7) / 8, 256, 0, st>>>(h->xres, N, H, h->rfinal_gain, h->rfinal_bias, 1e-6f, nullptr, 0, 0, h->refined);
-    prof_end(h, st);
-    CK(h, cudaGetLastError());
-    h->launches++;
-    return CAPDEC_OK;
+    return launch_layernorm(h, h->xres, N, h->rfinal_gain, h->rfinal_bias, nullptr, 0, 0, h->refined, st);
 }
 
 // ------------------------------------------------------------------------------------------------ per-arch steps
@@ -976,12 +985,7 @@ int step_aoa(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
         e.ldh32 = H;
         CKS(h, launch_gemm(h, EPI_LSTM, 1, ma, h->XA.lo, mb, h->W_l1.lo, c.M, 4 * H, H + H, e, st));
     }
-    prof_begin(h, CAPDEC_CAT_OTHER, 0.0, st);
-    aoa_layernorm_kernel<<<(c.M + 7) / 8, 256, 0, st>>>(h->h32, c.M, H, h->ln_gain, h->ln_bias, 1e-6f, h->XB.p + H, h->XB.ld,
-                                                        h->XB.lo);
-    prof_end(h, st);
-    CK(h, cudaGetLastError());
-    h->launches++;
+    CKS(h, launch_layernorm(h, h->h32, c.M, h->ln_gain, h->ln_bias, h->XB.p + H, h->XB.ld, h->XB.lo, nullptr, st));
     {  // linear_Q (AoA_Model.py:113)
         CKS(h, map_a(h, &ma, h->XB, H));
         CKS(h, map_b(h, &mb, h->W_aux1));

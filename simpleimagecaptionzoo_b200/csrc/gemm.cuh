@@ -71,6 +71,7 @@ struct GemmParams {
     int a_lo_off, b_lo_off; // column offset of the lo halves (elements)
     int num_m_blocks, num_n_blocks;
     int runs;               // > 0: (row block, vocabulary-tile run) work items, see TileIter
+    int m_group;            // > 0: output tiles are walked in groups of m_group row blocks, see TileIter
     EpiParams epi;
 };
 
@@ -154,9 +155,17 @@ __device__ __forceinline__ void epi_store(uint32_t taddr, int row, int n_base, i
         tmem_ld_32x32(taddr + c * 32, v);
         if (!row_ok) continue;
         if (e.bias) {
+            if (vec_ok && n0 + 32 <= p.N) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (n0 + i < p.N) v[i] += __ldg(e.bias + n0 + i);
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + i));
+                    v[i] += b.x, v[i + 1] += b.y, v[i + 2] += b.z, v[i + 3] += b.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (n0 + i < p.N) v[i] += __ldg(e.bias + n0 + i);
+            }
         }
         if (e.relu) {
 #pragma unroll
@@ -456,16 +465,20 @@ struct DrawState {
     }
 };
 
-// Work decomposition.  runs == 0: output tiles in M-fastest order, round-robin over the CTAs (CTAs resident at the
-// same time share weight tiles in L2).  runs > 0 (logit GEMM): a work item is (row block, run) = a contiguous range of
-// vocabulary tiles of one row block, so the epilogue's per-row state persists across the item's tiles.
+// Work decomposition.  runs == 0: output tiles round-robin over the CTAs, M-fastest inside a GROUP of m_group row blocks
+// and all column blocks of the group before the next group.  With m_group = number of resident CTAs (pairs) every CTA
+// keeps its row block while it walks the columns, so the A operand is read from HBM once (a group's A rows stay in L2)
+// and the co-resident CTAs share each weight tile; a plain M-fastest sweep re-reads A once per column block as soon as
+// A outgrows L2 (the refiner's GEMMs: A = 113-226 MB).  runs > 0 (logit GEMM): a work item is (row block, run) = a
+// contiguous range of vocabulary tiles of one row block, so the epilogue's per-row state persists across the item's tiles.
 struct TileIter {
-    int item, items, step, runs, num_m, num_n;
+    int item, items, step, runs, num_m, num_n, m_group;
     int m_blk, n_blk, n_end, run;
     __device__ __forceinline__ TileIter(const GemmParams& p, int first = blockIdx.x, int stride = gridDim.x)
-        : item(first), step(stride), runs(p.runs), num_m(p.num_m_blocks), num_n(p.num_n_blocks) {
+        : item(first), step(stride), runs(p.runs), num_m(p.num_m_blocks), num_n(p.num_n_blocks), m_group(p.m_group) {
         items = runs > 0 ? num_m * runs : num_m * num_n;
         n_blk = 0, n_end = 0, m_blk = 0, run = 0;
+        if (m_group <= 0 || m_group > num_m) m_group = num_m;
     }
     // advance to the next tile of this CTA; returns false when done.  first_of_item / last_of_item delimit a run.
     __device__ __forceinline__ bool next(bool& first_of_item, bool& last_of_item) {
@@ -488,8 +501,12 @@ struct TileIter {
         if (n_end != 0) item += step;
         n_end = 1;
         if (item >= items) return false;
-        m_blk = item % num_m;
-        n_blk = item / num_m;
+        const int per = m_group * num_n;
+        const int grp = item / per, rem = item - grp * per;
+        const int m0 = grp * m_group;
+        const int gm = num_m - m0 < m_group ? num_m - m0 : m_group;  // the last group may be short
+        n_blk = rem / gm;
+        m_blk = m0 + rem - n_blk * gm;
         first_of_item = last_of_item = true;
         return true;
     }

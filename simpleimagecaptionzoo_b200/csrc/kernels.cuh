@@ -862,6 +862,52 @@ __global__ void aoa_layernorm_kernel(const float* __restrict__ h, int M, int H, 
     }
 }
 
+// Same LayerNorm for H = 128 * NV4: the row lives in registers (one global read), 16-byte loads, 8-byte fp16 stores.
+template <int NV4>
+__global__ void __launch_bounds__(256) aoa_layernorm_vec_kernel(const float* __restrict__ h, int M, const float* __restrict__ gain,
+                                                                const float* __restrict__ bias, float eps, __half* __restrict__ q16,
+                                                                int ld16, int lo16, float* __restrict__ out32) {
+    constexpr int H = 128 * NV4;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float4* x4 = reinterpret_cast<const float4*>(h + static_cast<size_t>(row) * H);
+    float4 v[NV4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+        v[i] = x4[lane + 32 * i];
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) / static_cast<float>(H);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+        v[i].x -= mean, v[i].y -= mean, v[i].z -= mean, v[i].w -= mean;
+        q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    const float inv = 1.0f / (sqrtf(warp_sum(q) / static_cast<float>(H - 1)) + eps);
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+        const int c = 4 * (lane + 32 * i);
+        const float4 gn = __ldg(reinterpret_cast<const float4*>(gain + c)), bs = __ldg(reinterpret_cast<const float4*>(bias + c));
+        const float y0 = gn.x * v[i].x * inv + bs.x, y1 = gn.y * v[i].y * inv + bs.y, y2 = gn.z * v[i].z * inv + bs.z,
+                    y3 = gn.w * v[i].w * inv + bs.w;
+        if (out32) *reinterpret_cast<float4*>(out32 + static_cast<size_t>(row) * H + c) = make_float4(y0, y1, y2, y3);
+        if (q16) {
+            __align__(8) __half hi[4];
+            __align__(8) __half lo[4];
+            split_f16(y0, hi[0], lo[0]);
+            split_f16(y1, hi[1], lo[1]);
+            split_f16(y2, hi[2], lo[2]);
+            split_f16(y3, hi[3], lo[3]);
+            __half* d = q16 + static_cast<size_t>(row) * ld16 + c;
+            *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(hi);
+            if (lo16 > 0) *reinterpret_cast<uint2*>(d + lo16) = *reinterpret_cast<const uint2*>(lo);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ AoA refiner
 // Multi-head SELF-attention of one AoA_Refine_Block (AoA_Model.py:41-69, 90-117, 136-138): queries = keys = values =
 // the R regions of an image, per head  S = Q K^T / sqrt(d), masked_fill(mask == 0, -1e9), softmax over keys, X = P V.
@@ -934,48 +980,73 @@ __global__ void __launch_bounds__(128) refine_attention_kernel(const T* __restri
     }
 }
 
-// Fragment form (fp16 mode): one warp per (image, head).  The head's Q, K, V slices ([R, DH] fp16 each) are copied to
-// the warp's own shared-memory tiles (rows padded by 16 B -> conflict-free ldmatrix) with cp.async; then per 16-query
-// tile  S = Q K^T  (m16n8k16: A = Q via ldmatrix, B = K rows via ldmatrix), the softmax over the keys on the accumulator
-// fragments (row statistics via quad shuffles), P re-packed in registers as the A operand of  X = P V  (B = V via
-// ldmatrix.trans).  NKT = ceil(R / 16) key tiles (template), DH = head dim.
-template <int NKT, int DH>
+// Fragment form (fp16 mode).  A CTA works on (image, group of G heads) items: the K and V slices of the group
+// ([R, G*DH] fp16 each, 1 KB contiguous per row) are copied with cp.async into per-head shared-memory tiles (rows padded
+// by 16 B -> conflict-free ldmatrix); one warp per (head, 16-query tile), so an SM holds 24 warps and the per-warp
+// dependency chains overlap.  Per warp:  S = Q K^T  (m16n8k16: A = Q fragments read straight from global memory while
+// the copies are in flight, B = K rows via ldmatrix), softmax over the keys on the accumulator fragments (row statistics
+// via quad shuffles), P re-packed in registers as the A operand of  X = P V  (B = V via ldmatrix.trans).
+// NKT = ceil(R / 16) key tiles = query tiles, DH = head dim.
+template <int NKT, int DH, int G>
 struct RefineMmaCfg {
     static constexpr int ROWS = 16 * NKT;
-    static constexpr int LDS = DH + 8;                       // halves per shared-memory row
-    static constexpr int WARP_BYTES = 3 * ROWS * LDS * 2;    // Q, K, V tiles of one warp
-    static constexpr int WARPS = (200 * 1024 / WARP_BYTES) >= 4 ? 4 : ((200 * 1024 / WARP_BYTES) >= 2 ? 2 : 1);
-    static constexpr int SMEM_BYTES = WARPS * WARP_BYTES;
+    static constexpr int LDS = DH + 8;                        // halves per shared-memory row
+    static constexpr int TILE_BYTES = ROWS * LDS * 2;         // one head's K (or V) tile
+    static constexpr int SMEM_BYTES = 2 * G * TILE_BYTES;     // K tiles then V tiles
+    static constexpr int WARPS = NKT * G;
+    // small key counts: many small CTAs per SM (up to 24 warps under the 64 K register file) so that the copy phase of
+    // one CTA overlaps the MMA phase of its neighbours; larger ones need the registers for the score fragments
+    static constexpr int SMEM_LIMIT = (227 * 1024) / (SMEM_BYTES + 1024);
+    static constexpr int CTAS_PER_SM = NKT <= 3 ? (SMEM_LIMIT < 24 / WARPS ? SMEM_LIMIT : 24 / WARPS) : 1;
 };
 
-template <int NKT, int DH>
-__global__ void __launch_bounds__(32 * RefineMmaCfg<NKT, DH>::WARPS)
+template <int NKT, int DH, int G>
+__global__ void __launch_bounds__(32 * RefineMmaCfg<NKT, DH, G>::WARPS, RefineMmaCfg<NKT, DH, G>::CTAS_PER_SM)
 refine_attention_mma_kernel(const __half* __restrict__ qkv, int ld, const float* __restrict__ mask, int B, int R, int H, int nh,
                             __half* __restrict__ x16, int ld16) {
-    using C = RefineMmaCfg<NKT, DH>;
+    using C = RefineMmaCfg<NKT, DH, G>;
     extern __shared__ __align__(128) uint8_t rf_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
-    __half* tile = reinterpret_cast<__half*>(rf_smem + warp * C::WARP_BYTES);
-    const uint32_t sq = smem_u32(tile), sk = sq + C::ROWS * C::LDS * 2, sv = sk + C::ROWS * C::LDS * 2;
-    // rows R .. ROWS-1 are never written by the copies: zero them once (0 * garbage must not become NaN)
-    for (int i = lane; i < 3 * C::ROWS * C::LDS / 2; i += 32) reinterpret_cast<uint32_t*>(tile)[i] = 0u;
-    __syncwarp();
-    // ldmatrix lane offsets: "a" = 16x16 block as the A operand / V^T via .trans; "b" = two 8-key groups as the B operand
+    const int hl = warp / NKT, mt = warp - hl * NKT;  // head within the group, query tile
+    const uint32_t s_base = smem_u32(rf_smem);
+    const uint32_t sk = s_base + hl * C::TILE_BYTES, sv = s_base + (G + hl) * C::TILE_BYTES;
+    // rows R .. ROWS-1 are never written by the copies: zero everything once (0 * garbage must not become NaN)
+    for (int i = threadIdx.x; i < C::SMEM_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(rf_smem)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    // ldmatrix lane offsets: "a" = 16x16 block in A-operand order (V^T via .trans); "b" = two 8-key groups as the B operand
     const uint32_t off_a = (((lane & 7) + ((lane >> 3) & 1) * 8) * C::LDS + (lane >> 4) * 8) * 2;
     const uint32_t off_b = (((lane & 7) + ((lane >> 4) & 1) * 8) * C::LDS + ((lane >> 3) & 1) * 8) * 2;
     const float scale = rsqrtf(static_cast<float>(DH)) * LOG2E;  // exp(x) = exp2(x * log2 e)
-    constexpr int CH = DH / 8;                                     // 16-byte chunks per row slice
-    const int units = B * nh;
-    for (int u = blockIdx.x * C::WARPS + warp; u < units; u += gridDim.x * C::WARPS) {
-        const int img = u / nh, hd = u - img * nh;
-        const __half* src = qkv + static_cast<size_t>(img) * R * ld + hd * DH;
-        for (int i = lane; i < 3 * R * CH; i += 32) {
-            const int part = i / (R * CH), rem = i - part * (R * CH);
-            const int r = rem / CH, c = rem - r * CH;
-            cp_async_16(sq + (part * C::ROWS * C::LDS + r * C::LDS + c * 8) * 2, src + static_cast<size_t>(r) * ld + part * H + c * 8);
+    constexpr int CH = DH / 8;                                     // 16-byte chunks per head row
+    const int groups = nh / G;
+    const int items = B * groups;
+    const int q0 = mt * 16 + g, q1 = q0 + 8;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int img = item / groups, h0 = (item - img * groups) * G;
+        const __half* src = qkv + static_cast<size_t>(img) * R * ld + h0 * DH;
+        for (int i = threadIdx.x; i < 2 * R * G * CH; i += blockDim.x) {  // K then V rows of the head group
+            const int part = i >= R * G * CH;
+            const int rem = i - part * R * G * CH;
+            const int r = rem / (G * CH), c = rem - r * (G * CH);
+            const int hh = c / CH, cc = c - hh * CH;
+            cp_async_16(s_base + ((part * G + hh) * C::TILE_BYTES) + (r * C::LDS + cc * 8) * 2,
+                        src + static_cast<size_t>(r) * ld + (1 + part) * H + c * 8);
         }
         cp_async_commit();
+        // this warp's Q fragments (rows q0 / q1 of head h0 + hl), straight from global memory
+        uint32_t qa[DH / 16][4];
+        {
+            const __half* qr0 = src + static_cast<size_t>(q0) * ld + hl * DH + 2 * t;
+            const __half* qr1 = src + static_cast<size_t>(q1) * ld + hl * DH + 2 * t;
+#pragma unroll
+            for (int ks = 0; ks < DH / 16; ++ks) {
+                qa[ks][0] = q0 < R ? __ldg(reinterpret_cast<const uint32_t*>(qr0 + ks * 16)) : 0u;
+                qa[ks][1] = q1 < R ? __ldg(reinterpret_cast<const uint32_t*>(qr1 + ks * 16)) : 0u;
+                qa[ks][2] = q0 < R ? __ldg(reinterpret_cast<const uint32_t*>(qr0 + ks * 16 + 8)) : 0u;
+                qa[ks][3] = q1 < R ? __ldg(reinterpret_cast<const uint32_t*>(qr1 + ks * 16 + 8)) : 0u;
+            }
+        }
         // key status bits of this lane's columns: bit (2*nt + e) <-> key nt*8 + 2t + e
         uint64_t in_range = 0, keep = 0;
 #pragma unroll
@@ -990,21 +1061,19 @@ refine_attention_mma_kernel(const __half* __restrict__ qkv, int ld, const float*
             }
         }
         cp_async_wait_all();
-        __syncwarp();
-        for (int mt = 0; mt * 16 < R; ++mt) {
+        __syncthreads();
+        if (mt * 16 < R) {
             float s[2 * NKT][4];
 #pragma unroll
             for (int nt = 0; nt < 2 * NKT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
 #pragma unroll
             for (int ks = 0; ks < DH / 16; ++ks) {
-                uint32_t a[4];
-                ldmatrix_x4(a, sq + (mt * 16 * C::LDS + ks * 16) * 2 + off_a);
 #pragma unroll
                 for (int kt = 0; kt < NKT; ++kt) {
                     uint32_t b[4];
                     ldmatrix_x4(b, sk + (kt * 16 * C::LDS + ks * 16) * 2 + off_b);
-                    mma_m16n8k16_f16(s[2 * kt], a[0], a[1], a[2], a[3], b[0], b[1]);
-                    mma_m16n8k16_f16(s[2 * kt + 1], a[0], a[1], a[2], a[3], b[2], b[3]);
+                    mma_m16n8k16_f16(s[2 * kt], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b[0], b[1]);
+                    mma_m16n8k16_f16(s[2 * kt + 1], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b[2], b[3]);
                 }
             }
             // softmax over the keys for rows g (elements 0,1) and g+8 (elements 2,3), in the log2 domain
@@ -1014,7 +1083,7 @@ refine_attention_mma_kernel(const __half* __restrict__ qkv, int ld, const float*
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const bool in = (in_range >> (2 * nt + e)) & 1, kp = (keep >> (2 * nt + e)) & 1;
-                    const float lo = in ? (kp ? 0.f : -1e9f * LOG2E) : -INFINITY;
+                    const float lo = in ? -1e9f * LOG2E : -INFINITY;  // masked_fill(mask == 0, -1e9) / key beyond R
                     s[nt][e] = (in && kp) ? s[nt][e] * scale : lo;
                     s[nt][2 + e] = (in && kp) ? s[nt][2 + e] * scale : lo;
                     m0 = fmaxf(m0, s[nt][e]);
@@ -1058,8 +1127,7 @@ refine_attention_mma_kernel(const __half* __restrict__ qkv, int ld, const float*
                     mma_m16n8k16_f16(o[2 * dn + 1], a0, a1, a2, a3, b[2], b[3]);
                 }
             }
-            const int q0 = mt * 16 + g, q1 = q0 + 8;
-            __half* o0 = x16 + (static_cast<size_t>(img) * R + q0) * ld16 + hd * DH + 2 * t;
+            __half* o0 = x16 + (static_cast<size_t>(img) * R + q0) * ld16 + (h0 + hl) * DH + 2 * t;
             __half* o1 = o0 + static_cast<size_t>(8) * ld16;
 #pragma unroll
             for (int j = 0; j < DH / 8; ++j) {
@@ -1067,7 +1135,7 @@ refine_attention_mma_kernel(const __half* __restrict__ qkv, int ld, const float*
                 if (q1 < R) *reinterpret_cast<uint32_t*>(o1 + 8 * j) = pack_h2(o[j][2], o[j][3]);
             }
         }
-        __syncwarp();  // all lanes are done with the tiles before the next unit's copies land
+        __syncthreads();  // every warp is done with the tiles before the next item's copies land
     }
 }
 
