@@ -56,6 +56,11 @@ WORKLOADS = {
                       "(configs[4] per-GPU shard)"),
     "aoa": dict(arch="AOA", model_type="AoADetection", R=36, beam=3, batch=1536,
                 desc="AoADetection 8-head AoA decoder beam=3 (configs[3] per-GPU shard, refined feats synthetic)"),
+    # configs[1] as BASELINE.json states it: 224x224 images -> ResNet-101 (cuDNN via torchvision, channels-last fp16, CUDA
+    # graph: library code) -> weight-normed Linear -> this repo's NIC decoder; batch 256
+    "nic_images": dict(arch="NIC", model_type="NIC", R=0, beam=3, batch=256, images=True,
+                       desc="NIC (ResNet-101 encoder + LSTM) beam=3 on synthetic 224x224 images, batch 256 (configs[1]); encoder = "
+                            "torchvision/cuDNN fp16 channels-last under a CUDA graph, decoder = libcapdec"),
     # configs[3] from the bottom-up features: img_feats_porjection + 6-layer aoa_refine + decoder, all in the library
     "aoa_bu": dict(arch="AOA", model_type="AoADetection", R=36, beam=3, batch=1536, refiner=True,
                    desc="AoADetection beam=3 from synthetic 36x2048 bottom-up feats: projection + 6-layer AoA refiner + 8-head "
@@ -74,6 +79,8 @@ def load_peaks():
 
 def make_inputs(w, batch, seed):
     dims = synth.DIMS[w["arch"]]
+    if w.get("images"):
+        return np.random.Generator(np.random.PCG64(6_000_003 + seed)).standard_normal((batch, 3, 224, 224), dtype=np.float32)
     if w["arch"] == "BUTD" or w.get("refiner"):
         return synth.make_region_feats(batch, w["R"], dims.get("enc_dim", 2048), seed)
     if w["arch"] == "NIC":
@@ -153,6 +160,17 @@ def time_reference_form(w, sd, feats, beam, max_seq):
         _ORACLE_CACHE[id(sd)] = oracle_decoder(w, sd)
     orc, dec = _ORACLE_CACHE[id(sd)]
     t0 = time.perf_counter()
+    if w.get("images"):  # the reference's own encoder on the CPU: torchvision ResNet-101 fp32 + img_embedding (NIC_Model.py:27-37)
+        import torch
+        from simpleimagecaptionzoo_b200 import cnn_feed
+        if "cnn" not in _ORACLE_CACHE:
+            fx = cnn_feed.build_feature_extractor()
+            fx.load_state_dict({k[len("encoder.feature_extractor."):]: v for k, v in sd.items() if k.startswith("encoder.feature_extractor.")})
+            v, g = sd["encoder.img_embedding.weight_v"].double(), sd["encoder.img_embedding.weight_g"].double()
+            _ORACLE_CACHE["cnn"] = (fx.eval(), (v * (g / v.norm(dim=1, keepdim=True))).float(), sd["encoder.img_embedding.bias"].float())
+        fx, W, b = _ORACLE_CACHE["cnn"]
+        with torch.no_grad():
+            feats = torch.addmm(b, fx(torch.from_numpy(feats)).mean(dim=(2, 3)), W.t()).numpy()
     if w.get("refiner"):  # AoA_Model.py:748-751: projection + refiner run on every sampler call
         feats = orc.aoa_project_refine(sd, feats, None)
     dec.prepare(feats)
@@ -165,6 +183,9 @@ def make_weights(w):
     sd = synth.make_state_dict(w["arch"], seed=0, **dims)
     if w.get("refiner"):
         sd.update(synth.make_refiner_state_dict(hidden_dim=dims["hidden_dim"], enc_dim=2048, seed=0))
+    if w.get("images"):
+        from simpleimagecaptionzoo_b200 import cnn_feed
+        sd.update(cnn_feed.make_encoder_state_dict(embed_dim=dims["embed_dim"], seed=0))
     return sd
 
 
@@ -233,6 +254,10 @@ def run_gpu_arm(args, w):
                                enc_dim=dims.get("enc_dim", 2048), num_heads=dims.get("num_heads", 8))
     dec = cap.decoder
     key = "bu_feats" if raw_bu else "feats"
+    if w.get("images"):
+        from simpleimagecaptionzoo_b200 import cnn_feed
+        cnn_feed.attach(cap, sd)
+        key = "img_tensors"
 
     # rank-local shard of the global batch (weak scaling: B images per GPU), distinct per rank
     host_feats = torch.from_numpy(make_inputs(w, B, 1000 + rank)).pin_memory()
@@ -242,7 +267,10 @@ def run_gpu_arm(args, w):
     scst = bool(w.get("scst"))
 
     def step_device():
-        cap._prepare(dev_feats, None)
+        if w.get("images"):
+            cap._prepare(cap.feature_fn({key: dev_feats}), None)
+        else:
+            cap._prepare(dev_feats, None)
         if scst:  # Engine.SCST_training_epoch's two rollouts (Engine.py:258-262), forward values
             greedy, _ = dec.sample(capdec.SAMPLE_GREEDY, 1, 0, T)
             tok, _ = dec.sample(capdec.SAMPLE_MULTINOMIAL, K, step_device.calls, T)
@@ -359,7 +387,7 @@ def run_gpu_arm(args, w):
         "config": {"workload": w["desc"], "images_per_gpu": B, "global_batch": n_total, "beam": K, "max_seq": T, "regions": R,
                    "vocab": dims["vocab_size"], "math": args.math, "parallelism": f"dp{world} (images sharded, one all-gather)",
                    "host_numa_node": numa_node,
-                   "l2": f"inputs larger than L2: {h2d / 1e6:.0f} MB of features + {sum(v.size for v in sd.values()) * 2 / 1e6:.0f} MB "
+                   "l2": f"inputs larger than L2: {h2d / 1e6:.0f} MB of features + {sum(int(np.prod(v.shape)) for v in sd.values()) * 2 / 1e6:.0f} MB "
                          "of fp16 weights are re-read every step"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
