@@ -133,6 +133,14 @@ int capdec_beam_search(capdec_handle* h, int32_t beam, int32_t max_seq, int32_t*
 int capdec_sample(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t seed, int32_t max_seq, int32_t* tokens,
                   float* logprobs, float* alphas, void* stream);
 
+/* Teacher-forced scoring of given word sequences for the prepared batch: what the reference's decoder ``forward`` computes
+ * for given captions (BUTD_Model.py:97-151, NIC_Model.py:58-98, AoA_Model.py:229-293) followed by log_softmax + gather --
+ * the ``seqLogprobs`` of an arbitrary rollout (Utils.py:290-317 RewardCriterion's input), forward values only.
+ *   tokens   [B*n_per_image, max_seq] int32 words WITHOUT <sta> (the layout capdec_sample returns); word t is scored
+ *            given <sta> and words 0..t-1 of the same row, and fed back as the next input whatever it is (0 = <pad> too)
+ *   logprobs [B*n_per_image, max_seq] fp32 log p(word t | image, previous words) */
+int capdec_score(capdec_handle* h, const int32_t* tokens, int32_t n_per_image, int32_t max_seq, float* logprobs, void* stream);
+
 /* Number of kernels the library launched on behalf of this handle since create (bench.py's gpu_launches). */
 int64_t capdec_launch_count(const capdec_handle* h);
 

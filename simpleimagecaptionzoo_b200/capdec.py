@@ -24,7 +24,7 @@ SYMBOLS = (
     "capdec_abi_version", "capdec_create", "capdec_destroy", "capdec_last_error", "capdec_load_weight",
     "capdec_finalize_weights", "capdec_prepare", "capdec_beam_search", "capdec_sample", "capdec_launch_count",
     "capdec_test_gemm", "capdec_profile", "capdec_profile_read", "capdec_test_gemm_time",
-    "capdec_prepare_bottom_up", "capdec_get_refined",
+    "capdec_prepare_bottom_up", "capdec_get_refined", "capdec_score",
 )
 CATEGORIES = ("gemm_lstm", "gemm_store", "gemm_glu", "gemm_logits", "attention", "bookkeeping", "other")
 
@@ -62,6 +62,7 @@ def load_library(path: str = LIB_PATH) -> ctypes.CDLL:
     lib.capdec_get_refined.argtypes = [vp, vp, vp]
     lib.capdec_beam_search.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
     lib.capdec_sample.argtypes = [vp, i32, i32, ctypes.c_uint64, i32, vp, vp, vp, vp]
+    lib.capdec_score.argtypes = [vp, vp, i32, i32, vp, vp]
     lib.capdec_launch_count.argtypes = [vp]
     lib.capdec_launch_count.restype = i64
     lib.capdec_test_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
@@ -267,6 +268,23 @@ class CaptionDecoder:
                                                     self.stream.cuda_stream), "capdec_beam_search")
             torch.cuda.current_stream(self.device).wait_stream(self.stream)
         return (tokens, scores, lengths, alphas) if return_alphas else (tokens, scores, lengths)
+
+    def score(self, tokens, n_per_image: int = 1):
+        """Teacher-forced log-probs of given words: tokens [B*n, T] int (no <sta>, the layout ``sample`` returns) ->
+        logprobs [B*n, T] fp32 CUDA tensor, log p(word t | image, <sta>, words < t)."""
+        torch = _torch()
+        tokens = tokens.to(self.device, torch.int32).contiguous()
+        M, T = tokens.shape
+        if M != self.B * n_per_image:
+            raise ValueError(f"tokens has {M} rows, the prepared batch has {self.B} images x {n_per_image}")
+        logprobs = torch.empty((M, T), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            self._check(self.lib.capdec_score(self._h, tokens.data_ptr(), n_per_image, T, logprobs.data_ptr(),
+                                              self.stream.cuda_stream), "capdec_score")
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        self._keep_tokens = tokens
+        return logprobs
 
     def sample(self, mode: int, n_per_image: int = 1, seed: int = 0, max_seq: int = 20, return_alphas: bool = False):
         """-> tokens [B*n,max_seq] int32, logprobs [B*n,max_seq] fp32 (CUDA tensors) [, alphas [B*n,max_seq,R] fp32]."""

@@ -697,6 +697,8 @@ struct StepCtx {
     uint32_t seed = 0;
     int use_noise = 0;
     bool first_from_c0 = false;
+    const int* forced = nullptr;  // teacher-forced words [row * forced_ld + step] (capdec_score) or null
+    int forced_ld = 0;
     float* alphas = nullptr;  // where this step's attention maps go ([row * alpha_stride + region]) or null
     size_t alpha_stride = 0;
 };
@@ -712,6 +714,8 @@ int run_logits(capdec_handle* h, const Act16& a, const StepCtx& c, cudaStream_t 
     e.seed = c.seed;
     e.step = c.t - 1;
     e.use_noise = c.use_noise;
+    e.forced = c.forced;
+    e.forced_ld = c.forced_ld;
     return launch_gemm(h, c.logits_epi, c.ktop, ma, a.lo, mb, h->W_pred.lo, c.M, h->V, h->H, e, st);
 }
 
@@ -1515,6 +1519,9 @@ static int enqueue_beam_search(capdec_handle* h, int32_t beam, int32_t max_seq, 
     return CAPDEC_OK;
 }
 
+static int sample_impl(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t seed, int32_t max_seq, int32_t* tokens,
+                       float* logprobs, float* alphas, const int32_t* forced, cudaStream_t st);
+
 int capdec_sample(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t seed, int32_t max_seq, int32_t* tokens,
                   float* logprobs, float* alphas, void* stream) {
     if (!h) return CAPDEC_ERR_INVALID;
@@ -1523,11 +1530,25 @@ int capdec_sample(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t 
         return fail(h, CAPDEC_ERR_INVALID, "sample: n_per_image / max_seq out of range or null tokens");
     if (mode != CAPDEC_SAMPLE_GREEDY && mode != CAPDEC_SAMPLE_MULTINOMIAL) return fail(h, CAPDEC_ERR_INVALID, "unknown sample mode");
     if (alphas && h->cfg.arch == CAPDEC_ARCH_NIC) return fail(h, CAPDEC_ERR_INVALID, "NIC has no attention maps; pass alphas = NULL");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(h, cudaSetDevice(h->cfg.device));
+    return sample_impl(h, mode, n_per_image, seed, max_seq, tokens, logprobs, alphas, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int capdec_score(capdec_handle* h, const int32_t* tokens, int32_t n_per_image, int32_t max_seq, float* logprobs, void* stream) {
+    if (!h) return CAPDEC_ERR_INVALID;
+    if (!h->prepared) return fail(h, CAPDEC_ERR_STATE, "capdec_score before capdec_prepare");
+    if (n_per_image <= 0 || n_per_image > h->Kmax || max_seq <= 0 || max_seq > h->Tmax || !tokens || !logprobs)
+        return fail(h, CAPDEC_ERR_INVALID, "score: n_per_image / max_seq out of range or null tokens / logprobs");
+    CK(h, cudaSetDevice(h->cfg.device));
+    return sample_impl(h, CAPDEC_SAMPLE_GREEDY, n_per_image, 0, max_seq, nullptr, logprobs, nullptr, tokens,
+                       static_cast<cudaStream_t>(stream));
+}
+
+static int sample_impl(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t seed, int32_t max_seq, int32_t* tokens,
+                       float* logprobs, float* alphas, const int32_t* forced, cudaStream_t st) {
     const int B = h->B, n = n_per_image, M = B * n;
     CKS(h, reset_state(h, M, st));
-    CK(h, cudaMemsetAsync(tokens, 0, static_cast<size_t>(M) * max_seq * sizeof(int32_t), st));
+    if (tokens) CK(h, cudaMemsetAsync(tokens, 0, static_cast<size_t>(M) * max_seq * sizeof(int32_t), st));
     if (logprobs) CK(h, cudaMemsetAsync(logprobs, 0, static_cast<size_t>(M) * max_seq * sizeof(float), st));
     SampleState s{};
     s.B = B, s.n = n, s.V = h->V, s.T = max_seq;
@@ -1546,6 +1567,8 @@ int capdec_sample(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t 
     c.M = M, c.K = n, c.logits_epi = EPI_SAMPLE, c.ktop = 1;
     c.seed = static_cast<uint32_t>(seed & 0xFFFFFFFFu);
     c.use_noise = s.multinomial;
+    c.forced = forced;
+    c.forced_ld = max_seq;
     const AdvOps ops = adv_ops(h, false);
     for (int t = 1; t <= max_seq; ++t) {
         c.t = t;

@@ -62,6 +62,8 @@ struct EpiParams {
     uint32_t seed;          // SAMPLE: counter-based Gumbel noise (0 noise when use_noise == 0)
     int step;
     int use_noise;
+    const int* forced;      // SAMPLE: teacher forcing -- the word of row r at this step is forced[r * forced_ld + step]
+    int forced_ld;          //   (capdec_score); null = draw / arg-max
 };
 
 struct GemmParams {
@@ -425,11 +427,12 @@ struct TopkState {
 // the plain argmax of ``sample``.  Also carries (max, sum-exp) for the log-prob of the drawn word.
 struct DrawState {
     float m, s, best, best_raw;
-    int best_i;
+    int best_i, forced;
     uint32_t rs;
     __device__ __forceinline__ void init(int row, const GemmParams& p) {
         m = -INFINITY, s = 0.f, best = -INFINITY, best_raw = 0.f, best_i = 0x7FFFFFFF;
         rs = gumbel_row_step_hash(p.epi.seed, static_cast<uint32_t>(row), static_cast<uint32_t>(p.epi.step));
+        forced = (p.epi.forced && row < p.M) ? __ldg(p.epi.forced + static_cast<size_t>(row) * p.epi.forced_ld + p.epi.step) : -1;
     }
     __device__ __forceinline__ void tile(uint32_t taddr, int n_base, int c0, int c1, const GemmParams& p) {
 #pragma unroll 1
@@ -439,7 +442,14 @@ struct DrawState {
             float v[32];
             tmem_ld_32x32(taddr + c * 32, v);
             const float cmax = logits_chunk_stats(v, n0, p.N, p.epi.bias, m, s);
-            if (p.epi.use_noise) {
+            if (p.epi.forced) {  // the given word "wins": its raw logit is what the log-prob needs
+                const int f = forced - n0;
+                if (f >= 0 && f < 32) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (i == f) best = 3.0e38f, best_i = forced, best_raw = v[i];
+                }
+            } else if (p.epi.use_noise) {
 #pragma unroll 4
                 for (int i = 0; i < 32; ++i) {
                     if (n0 + i < p.N) {

@@ -1828,7 +1828,7 @@ __global__ void __launch_bounds__(128) sample_step_kernel(const float* __restric
                     if (unf) atomicAdd(s.live_count + t, 1);
                 }
             } else {
-                s.tokens[static_cast<size_t>(row) * s.T + t] = word;
+                if (s.tokens) s.tokens[static_cast<size_t>(row) * s.T + t] = word;
                 if (s.logprobs) s.logprobs[static_cast<size_t>(row) * s.T + t] = braw - lse;
             }
             s.tok[row] = word;

@@ -234,6 +234,16 @@ class B200Captioner:
         return tokens.long(), logprobs
 
 
+    # not part of the reference's captioner surface: forward values of its teacher-forced ``forward`` for a rollout
+    def score(self, visual_inputs, tokens, n_per_image: int = 1):
+        """log p(word t | image, previous words) of given rollouts: tokens (B*n_per_image, T) as ``sampler_rl`` returns
+        them -> (B*n_per_image, T) float.  What ``decoder.forward`` + log_softmax + gather give in the reference
+        (BUTD_Model.py:97-151); lets a training loop re-score sequences sampled by the fused rollout."""
+        feats, mask = self._features(visual_inputs)
+        self._prepare(feats, mask)
+        return self.decoder.score(tokens, n_per_image)
+
+
 def ids_to_caption(ids: Sequence[int], ix2word) -> str:
     """Engine.py:288-297: words until '<end>', skipping '<sta>'."""
     words: List[str] = []

@@ -408,3 +408,42 @@ def test_bottom_up_needs_refiner_weights():
     with pytest.raises(RuntimeError, match="img_feats_porjection"):
         dec.prepare_bottom_up(torch.zeros(2, meta["R"], 2048).cuda())
     dec.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# teacher-forced scoring (capdec_score): the reference decoder's ``forward`` on given captions
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["butd_tiny_k3", "nic_tiny_k3", "aoa_tiny_k3_masked", "butd_full_k3", "nic_full_k3", "aoa_full_k3"])
+def test_score_matches_reference_forward(name):
+    """Sum of capdec_score over the reference's own beam-search caption == the reference's teacher-forced sequence
+    log-prob (golden ``scores``, produced by its ``forward``), within 1e-3 in the fp32-grade mode; per-step values against
+    the oracle's teacher-forced log-probs."""
+    meta, gold = load_case(name)
+    dec, sd, feats, mask = _make(meta, "f16x3")
+    B, T = meta["B"], meta["T"]
+    words = torch.from_numpy(gold["tokens"][:, 1:].astype(np.int32)).cuda()          # drop <sta>
+    lp = dec.score(words, 1).cpu().numpy()
+    n_words = gold["lengths"] - 1
+    valid = np.arange(T)[None, :] < n_words[:, None]
+    total = (lp * valid).sum(1)
+    assert np.allclose(total, gold["scores"], atol=1e-3, rtol=1e-5), np.abs(total - gold["scores"]).max()
+    o = _oracle(meta, sd, feats, mask)
+    words_np = gold["tokens"][:, 1:].astype(np.int64)[:, None, :]  # (B, 1, T): word t is scored, then fed at step t+1
+    ref = orc.teacher_forced_logprobs(o, words_np, words_np)[:, 0]
+    assert np.abs(lp - ref)[valid].max() < 1e-3
+    dec.close()
+
+
+@pytest.mark.parametrize("name", ["butd_full_k3", "aoa_tiny_k3"])
+def test_score_reproduces_rollout_logprobs(name):
+    """Scoring a greedy rollout returns the log-probs the rollout itself reported (same kernels, forced word = arg-max)."""
+    meta, _ = load_case(name)
+    dec, *_ = _make(meta, "f16", rows=2)
+    cd = _capdec()
+    tok, lp = dec.sample(cd.SAMPLE_GREEDY, 2, 0, meta["T"])
+    again = dec.score(tok, 2)
+    torch.cuda.synchronize()
+    assert torch.allclose(again, lp, atol=1e-5)
+    with pytest.raises(ValueError):
+        dec.score(tok[:3], 2)
+    dec.close()
