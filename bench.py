@@ -283,6 +283,25 @@ def run_gpu_arm(args, w):
         return tok
 
     step_device.calls = 0
+    reward = None
+    if scst:  # the SCST step's reward on the device too (CIDEr-D against synthetic references, Utils.py:319-367)
+        from simpleimagecaptionzoo_b200 import scst as scst_mod
+        ix2word, refs = synth.make_caption_corpus(B, dims["vocab_size"], seed=rank)
+        df, ref_len = scst_mod.document_frequency_from_corpus(refs)
+        reward = scst_mod.CiderDReward({wd: i for i, wd in enumerate(ix2word)}, df, ref_len, device=local)
+        gts, img_ids = dict(enumerate(refs)), list(range(B))
+        _rollout = step_device
+
+        def step_device():  # noqa: F811
+            dec.prepare(dev_feats)
+            greedy, _ = dec.sample(capdec.SAMPLE_GREEDY, 1, 0, T)
+            tok, _ = dec.sample(capdec.SAMPLE_MULTINOMIAL, K, _rollout.calls, T)
+            _rollout.calls += 1
+            step_device.rewards = reward(tok, greedy, gts, img_ids, n_per_image=K)
+            tok = tok.view(B, K * T)
+            if world > 1:
+                tok = engine.all_gather_captions(tok, n_total)
+            return tok
 
     def run_e2e(n_steps):
         """n_steps batches through the pipelined captioner API: every step's features start in pinned HOST memory and
@@ -291,9 +310,11 @@ def run_gpu_arm(args, w):
         if scst:  # the rollout API has no streaming form: H2D, both rollouts and the read-back run back to back
             for _ in range(n_steps):
                 vi = {key: host_feats}
-                cap.sampler(vi, max_len=T)
+                greedy = cap.sampler(vi, max_len=T)
                 seq, _ = cap.sampler_rl(vi, max_len=T, n_per_image=K)
+                rew = reward(seq, greedy, gts, img_ids, n_per_image=K)
                 last = seq.view(B, K * T).to(torch.int32).cpu().numpy()
+                rew[:, 0].cpu()
             return last
         for tok in cap.beam_search_stream(({key: host_feats} for _ in range(n_steps)), beam_size=K, max_seq=T):
             last = tok

@@ -141,6 +141,30 @@ int capdec_sample(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t 
  *   logprobs [B*n_per_image, max_seq] fp32 log p(word t | image, previous words) */
 int capdec_score(capdec_handle* h, const int32_t* tokens, int32_t n_per_image, int32_t max_seq, float* logprobs, void* stream);
 
+/* ---- CIDEr-D self-critical reward (the SCST step after the two rollouts) --------------------------------------------
+ * Replaces Utils.get_self_critical_reward (Utils.py:319-367) -> CiderD.compute_score (cider/pyciderevalcap/ciderD/
+ * ciderD.py:32-55) -> CiderScorer.compute_cider (ciderD_scorer.py:127-206, df mode "<dataset>-train") on word ids. */
+typedef struct capdec_cider capdec_cider;
+int capdec_cider_create(int32_t device, capdec_cider** out);
+void capdec_cider_destroy(capdec_cider* c);
+const char* capdec_cider_last_error(const capdec_cider* c);
+/* 64-bit key of an n-gram of k word ids (the host side hashes the document-frequency table with the same function). */
+uint64_t capdec_cider_ngram_key(const int32_t* ids, int32_t k);
+/* Document frequencies of the training corpus (the reference's cider/data/<dataset>-train.p: 'document_frequency',
+ * 'ref_len'): n entries, keys[i] = capdec_cider_ngram_key of the n-gram, df[i] = number of training images whose
+ * references contain it; log_ref_len = log(number of training images).  HOST arrays, copied. */
+int capdec_cider_set_df(capdec_cider* c, const uint64_t* keys, const float* df, int64_t n, double log_ref_len);
+/* rewards[b*n + i] = weight * (CIDEr-D(sample i of image b) - CIDEr-D(greedy rollout of image b)), DEVICE pointers:
+ *   gen        [B*n_per_image, max_seq] int32 as capdec_sample(MULTINOMIAL) stores them (<end> and after = 0)
+ *   greedy     [B, max_seq] int32 as capdec_sample(GREEDY) stores them (the caption ends before the first <end>)
+ *   ref_tokens [n_refs_total, ref_ld] int32 word ids of the reference captions (out-of-vocabulary words get ids >=
+ *              vocabulary size on the host side), ref_lens [n_refs_total] (<= 65), ref_offsets [B+1]: image b owns the
+ *              references [ref_offsets[b], ref_offsets[b+1])
+ *   sigma = 6 (ciderD.py:25); scores [B, n_per_image+1] (samples then greedy) or NULL. */
+int capdec_cider_reward(capdec_cider* c, const int32_t* gen, int32_t n_per_image, const int32_t* greedy, int32_t batch,
+                        int32_t max_seq, const int32_t* ref_tokens, const int32_t* ref_lens, const int32_t* ref_offsets,
+                        int32_t ref_ld, double sigma, double weight, float* rewards, float* scores, void* stream);
+
 /* Number of kernels the library launched on behalf of this handle since create (bench.py's gpu_launches). */
 int64_t capdec_launch_count(const capdec_handle* h);
 

@@ -651,3 +651,88 @@ def agreement(tokens_a, tokens_b, min_gap, tol=1e-4):
         ok = bool(np.any(g[:max(t, 1)] < tol))
         out.append("tie" if ok else "diff")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# CIDEr-D self-critical reward
+# ---------------------------------------------------------------------------------------------------
+
+def _precook(sentence: str, n: int = 4) -> dict:
+    """ciderD_scorer.py:17-33: n-gram (tuple of words) -> count, n-grams of length 1..n."""
+    words = sentence.split()
+    counts: dict = {}
+    for k in range(1, n + 1):
+        for i in range(len(words) - k + 1):
+            g = tuple(words[i:i + k])
+            counts[g] = counts.get(g, 0) + 1
+    return counts
+
+
+def ciderd_scores(hyps, refs, document_frequency: dict, ref_len: float, n: int = 4, sigma: float = 6.0) -> np.ndarray:
+    """CiderScorer.compute_cider (ciderD_scorer.py:127-206) with a precomputed document-frequency table (df mode
+    "<dataset>-train", :78-83): hyps[i] (a string) is scored against refs[i] (a list of strings).  float64, as the
+    reference."""
+    log_ref_len = np.log(float(ref_len))
+
+    def counts2vec(cnts):  # :128-153
+        vec = [dict() for _ in range(n)]
+        norm = [0.0] * n
+        length = 0
+        for g, tf in cnts.items():
+            df = np.log(max(1.0, document_frequency.get(g, 0.0)))
+            k = len(g) - 1
+            vec[k][g] = float(tf) * (log_ref_len - df)
+            norm[k] += vec[k][g] ** 2
+            if k == 1:
+                length += tf
+        return vec, [np.sqrt(x) for x in norm], length
+
+    def sim(vh, vr, nh, nr, lh, lr):  # :155-183
+        delta = float(lh - lr)
+        val = np.zeros(n)
+        for k in range(n):
+            for g in vh[k]:
+                val[k] += min(vh[k][g], vr[k].get(g, 0.0)) * vr[k].get(g, 0.0)
+            if nh[k] != 0 and nr[k] != 0:
+                val[k] /= nh[k] * nr[k]
+            val[k] *= np.e ** (-(delta ** 2) / (2 * sigma ** 2))
+        return val
+
+    out = []
+    for hyp, rs in zip(hyps, refs):  # :192-206
+        vec, norm, length = counts2vec(_precook(hyp, n))
+        score = np.zeros(n)
+        for r in rs:
+            vr, nr, lr = counts2vec(_precook(r, n))
+            score += sim(vec, vr, norm, nr, length, lr)
+        out.append(np.mean(score) / len(rs) * 10.0)
+    return np.array(out)
+
+
+def self_critical_reward(gen_result: np.ndarray, greedy_res: np.ndarray, ground_truth: dict, img_ids, ix2word,
+                         document_frequency: dict, ref_len: float, cider_weight: float = 1.0):
+    """Utils.get_self_critical_reward (Utils.py:319-367): sampled captions = words up to the last non-zero id (at least
+    one word), greedy captions = words before '<end>'; reward = CIDEr-D(sample) - CIDEr-D(greedy), repeated over the
+    time steps.  -> (rewards (B, max_len) float32, scores of [samples..., greedys...])."""
+    B = gen_result.shape[0]
+    hyps, refs = [], []
+    for b in range(B):
+        ids = gen_result[b]
+        end = 0
+        for e in range(len(ids) - 1, -1, -1):
+            end = e
+            if ids[e] != 0:
+                break
+        hyps.append(" ".join(ix2word[int(w)] for w in ids[:end + 1]))
+        refs.append(ground_truth[img_ids[b]])
+    for b in range(B):
+        words = []
+        for w in greedy_res[b]:
+            if ix2word[int(w)] == "<end>":
+                break
+            words.append(ix2word[int(w)])
+        hyps.append(" ".join(words))
+        refs.append(ground_truth[img_ids[b]])
+    scores = cider_weight * ciderd_scores(hyps, refs, document_frequency, ref_len)
+    diff = scores[:B] - scores[B:]
+    return np.repeat(diff[:, None], gen_result.shape[1], 1).astype(f32), scores

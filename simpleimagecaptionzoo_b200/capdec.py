@@ -25,6 +25,8 @@ SYMBOLS = (
     "capdec_finalize_weights", "capdec_prepare", "capdec_beam_search", "capdec_sample", "capdec_launch_count",
     "capdec_test_gemm", "capdec_profile", "capdec_profile_read", "capdec_test_gemm_time",
     "capdec_prepare_bottom_up", "capdec_get_refined", "capdec_score",
+    "capdec_cider_create", "capdec_cider_destroy", "capdec_cider_last_error", "capdec_cider_ngram_key", "capdec_cider_set_df",
+    "capdec_cider_reward",
 )
 CATEGORIES = ("gemm_lstm", "gemm_store", "gemm_glu", "gemm_logits", "attention", "bookkeeping", "other")
 
@@ -63,6 +65,15 @@ def load_library(path: str = LIB_PATH) -> ctypes.CDLL:
     lib.capdec_beam_search.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
     lib.capdec_sample.argtypes = [vp, i32, i32, ctypes.c_uint64, i32, vp, vp, vp, vp]
     lib.capdec_score.argtypes = [vp, vp, i32, i32, vp, vp]
+    lib.capdec_cider_create.argtypes = [i32, ctypes.POINTER(vp)]
+    lib.capdec_cider_destroy.argtypes = [vp]
+    lib.capdec_cider_destroy.restype = None
+    lib.capdec_cider_last_error.argtypes = [vp]
+    lib.capdec_cider_last_error.restype = ctypes.c_char_p
+    lib.capdec_cider_ngram_key.argtypes = [vp, i32]
+    lib.capdec_cider_ngram_key.restype = ctypes.c_uint64
+    lib.capdec_cider_set_df.argtypes = [vp, vp, vp, i64, ctypes.c_double]
+    lib.capdec_cider_reward.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp, i32, ctypes.c_double, ctypes.c_double, vp, vp, vp]
     lib.capdec_launch_count.argtypes = [vp]
     lib.capdec_launch_count.restype = i64
     lib.capdec_test_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]

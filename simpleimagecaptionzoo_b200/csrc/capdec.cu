@@ -14,6 +14,7 @@
 
 #include "../../include/capdec.h"
 #include "kernels.cuh"
+#include "cider.cuh"
 
 using namespace capdec;
 
@@ -1067,8 +1068,99 @@ int reset_state(capdec_handle* h, int M, cudaStream_t st) {
 
 }  // namespace
 
+struct capdec_cider {
+    int device = 0;
+    std::string err;
+    uint64_t* keys = nullptr;  // device open-addressing table
+    float* df = nullptr;
+    uint64_t slots = 0;
+    double log_ref_len = 0.0;
+};
+
 // ================================================================================================ C ABI
 extern "C" {
+
+// ------------------------------------------------------------------------------------------------ CIDEr-D reward
+uint64_t capdec_cider_ngram_key(const int32_t* ids, int32_t k) { return (ids && k > 0) ? cider_ngram_key(ids, k) : 0; }
+
+const char* capdec_cider_last_error(const capdec_cider* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int capdec_cider_create(int32_t device, capdec_cider** out) {
+    if (!out) return CAPDEC_ERR_INVALID;
+    *out = nullptr;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+        g_create_error = "capdec_cider needs an sm_100a (B200) device; there is no fallback path";
+        cudaGetLastError();
+        return CAPDEC_ERR_CUDA;
+    }
+    capdec_cider* c = new capdec_cider();
+    c->device = device;
+    *out = c;
+    return CAPDEC_OK;
+}
+
+void capdec_cider_destroy(capdec_cider* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaFree(c->keys);
+    cudaFree(c->df);
+    delete c;
+}
+
+int capdec_cider_set_df(capdec_cider* c, const uint64_t* keys, const float* df, int64_t n, double log_ref_len) {
+    if (!c || n < 0 || (n > 0 && (!keys || !df))) return CAPDEC_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    cudaFree(c->keys);
+    cudaFree(c->df);
+    c->keys = nullptr, c->df = nullptr, c->slots = 0;
+    c->log_ref_len = log_ref_len;
+    if (n == 0) return CAPDEC_OK;
+    uint64_t slots = 16;
+    while (slots < static_cast<uint64_t>(n) * 2) slots <<= 1;
+    std::vector<uint64_t> hk(slots, 0);
+    std::vector<float> hv(slots, 0.f);
+    for (int64_t i = 0; i < n; ++i) {
+        if (keys[i] == 0) {
+            c->err = "cider_set_df: key 0 is reserved";
+            return CAPDEC_ERR_INVALID;
+        }
+        uint64_t s = cider_mix64(keys[i]) & (slots - 1);
+        while (hk[s] != 0 && hk[s] != keys[i]) s = (s + 1) & (slots - 1);
+        hk[s] = keys[i];
+        hv[s] = df[i];
+    }
+    CK(c, cudaMalloc(reinterpret_cast<void**>(&c->keys), slots * sizeof(uint64_t)));
+    CK(c, cudaMalloc(reinterpret_cast<void**>(&c->df), slots * sizeof(float)));
+    CK(c, cudaMemcpy(c->keys, hk.data(), slots * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    CK(c, cudaMemcpy(c->df, hv.data(), slots * sizeof(float), cudaMemcpyHostToDevice));
+    c->slots = slots;
+    return CAPDEC_OK;
+}
+
+int capdec_cider_reward(capdec_cider* c, const int32_t* gen, int32_t n_per_image, const int32_t* greedy, int32_t batch,
+                        int32_t max_seq, const int32_t* ref_tokens, const int32_t* ref_lens, const int32_t* ref_offsets,
+                        int32_t ref_ld, double sigma, double weight, float* rewards, float* scores, void* stream) {
+    if (!c) return CAPDEC_ERR_INVALID;
+    if (!gen || !greedy || !ref_tokens || !ref_lens || !ref_offsets || !rewards || batch <= 0 || max_seq <= 0 || ref_ld <= 0 ||
+        n_per_image <= 0 || n_per_image > MAX_ROWS || sigma <= 0.0) {
+        c->err = "cider_reward: null pointer or size out of range (1 <= n_per_image <= 8)";
+        return CAPDEC_ERR_INVALID;
+    }
+    CK(c, cudaSetDevice(c->device));
+    const size_t smem = static_cast<size_t>(n_per_image + 1 + CIDER_REF_SLOTS) * sizeof(CiderVec);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CK(c, cudaFuncSetAttribute(cider_reward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>((CIDER_MAX_HYPS + CIDER_REF_SLOTS) * sizeof(CiderVec))));
+        attr_set = true;
+    }
+    CiderTable tab{c->keys, c->df, c->slots ? c->slots - 1 : 0, c->log_ref_len};
+    cider_reward_kernel<<<batch, 32 * (n_per_image + 1), smem, static_cast<cudaStream_t>(stream)>>>(
+        tab, gen, n_per_image, greedy, max_seq, ref_tokens, ref_lens, ref_offsets, ref_ld, sigma, weight, rewards, scores);
+    CK(c, cudaGetLastError());
+    return CAPDEC_OK;
+}
 
 int capdec_abi_version(void) { return CAPDEC_ABI_VERSION; }
 

@@ -167,6 +167,67 @@ def make_uniforms(batch: int, steps: int, seed: int = 0) -> np.ndarray:
     return _rng(5_000_003 + seed).random((batch, steps), dtype=np.float32)
 
 
+def make_caption_corpus(n_images: int = 60, vocab_size: int = 64, refs_per_image: int = 5, seed: int = 0):
+    """Synthetic tokenised caption corpus for the CIDEr-D reward tests: ``ix2word`` (ids 0-3 = <pad>,<sta>,<end>,<unk> as
+    PreProcess/Build_caption_vocab.py:37-40 assigns them) and, per image, ``refs_per_image`` (+0..2) reference strings of
+    5-16 Zipf-distributed words; ~3 % of the reference words are outside the vocabulary."""
+    rng = _rng(8_000_003 + seed)
+    ix2word = ["<pad>", "<sta>", "<end>", "<unk>"] + [f"w{i}" for i in range(4, vocab_size)]
+    p = 1.0 / np.arange(1, vocab_size - 3)
+    p /= p.sum()
+    refs = []
+    for _ in range(n_images):
+        topic = rng.choice(np.arange(4, vocab_size), size=6, p=p)  # words an image's captions tend to share
+        caps = []
+        for _ in range(refs_per_image + int(rng.integers(0, 3))):
+            L = int(rng.integers(5, 17))
+            ids = np.where(rng.random(L) < 0.5, rng.choice(topic, size=L), rng.choice(np.arange(4, vocab_size), size=L, p=p))
+            words = [ix2word[i] for i in ids]
+            for j in range(L):
+                if rng.random() < 0.03:
+                    words[j] = f"oov{int(rng.integers(0, 20))}"
+            caps.append(" ".join(words))
+        refs.append(caps)
+    return ix2word, refs
+
+
+def make_rollouts(ix2word, refs, img_index, n_per_image: int, max_len: int = 20, seed: int = 0):
+    """Synthetic SCST rollouts for images ``img_index`` of a corpus: ``gen`` (B*n, T) in ``sample_rl``'s storage (<end> and
+    everything after it = 0) and ``greedy`` (B, T) in ``sample``'s (an <end>=2 somewhere, words keep coming after it).
+    Rows are noisy copies of the image's references so that scores are non-trivial; a few rows hit the edge cases (empty
+    caption, full-length caption without <end>)."""
+    rng = _rng(9_000_003 + seed)
+    word2ix = {w: i for i, w in enumerate(ix2word)}
+    V, T = len(ix2word), max_len
+
+    def noisy(img):
+        ref = refs[img][int(rng.integers(0, len(refs[img])))].split()
+        ids = [word2ix.get(w, UNK) for w in ref][:int(rng.integers(1, T))]
+        return [int(rng.integers(4, V)) if rng.random() < 0.25 else i for i in ids]
+
+    B = len(img_index)
+    gen = np.zeros((B * n_per_image, T), np.int32)
+    greedy = np.zeros((B, T), np.int32)
+    for b, img in enumerate(img_index):
+        for j in range(n_per_image):
+            ids = noisy(img)
+            r = rng.random()
+            if r < 0.05:
+                ids = []                                  # <end> drawn first: stored as all zeros
+            elif r < 0.10:
+                ids = [int(x) for x in rng.integers(4, V, size=T)]  # never finished
+            gen[b * n_per_image + j, :len(ids)] = ids
+        ids = noisy(img)
+        if rng.random() < 0.05:
+            ids = []
+        row = [int(x) for x in rng.integers(4, V, size=T)]   # greedy keeps generating after <end> (BUTD_Model.py:153-189)
+        row[:len(ids)] = ids
+        if len(ids) < T and rng.random() < 0.9:
+            row[len(ids)] = END
+        greedy[b] = row
+    return gen, greedy
+
+
 # Named dimension sets ------------------------------------------------------------------------------------
 
 DIMS = {
