@@ -303,7 +303,7 @@ def run_gpu_arm(args, w):
                 tok = engine.all_gather_captions(tok, n_total)
             return tok
 
-    def run_e2e(n_steps):
+    def run_e2e(n_steps, host_feats=host_feats):
         """n_steps batches through the pipelined captioner API: every step's features start in pinned HOST memory and
         every step's captions end in host memory (H2D of step i+1 overlaps the decode of step i)."""
         last = None
@@ -365,6 +365,21 @@ def run_gpu_arm(args, w):
     e2e_value = n_total * args.steps / e2e_s
     h2d = host_feats.numel() * host_feats.element_size()
     d2h = tok_host.size * tok_host.itemsize // (world if world > 1 else 1)
+    # same end-to-end step with the host features in the packed fp16 shard format (feature_store.py):
+    # half the host->device bytes, no conversion pass; reported beside the reference-format (fp32) number, not instead of it
+    e2e_f16 = None
+    if raw_bu and args.math == "f16" and not scst:
+        host_f16 = host_feats.half().pin_memory()
+        run_e2e(3, host_f16)
+        barrier()
+        t0 = time.perf_counter()
+        run_e2e(args.steps, host_f16)
+        torch.cuda.synchronize()
+        f16_s = max_over_ranks(time.perf_counter() - t0)
+        if world > 1:
+            dist.barrier()
+        e2e_f16 = {"value": n_total * args.steps / f16_s, "unit": UNIT, "h2d_bytes_per_step": host_f16.numel() * 2,
+                   "ms_per_step": 1e3 * f16_s / args.steps, "host_format": "fp16 feature shard rows"}
 
     # ---- per-kernel timing (CUDA events on the launching stream) for the roofline object
     peaks = load_peaks()
@@ -413,6 +428,7 @@ def run_gpu_arm(args, w):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_s / args.steps},
+        "e2e_fp16_shard": e2e_f16,
         "gpu_launches": launches,
         "roofline": roofline,
         "kernels": kern,

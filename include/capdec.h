@@ -99,6 +99,13 @@ int capdec_finalize_weights(capdec_handle* h, void* stream);
  * feats (and mask) are DEVICE pointers and must stay valid until the following decode call has completed. */
 int capdec_prepare(capdec_handle* h, const float* feats, const float* mask, int32_t batch, int32_t regions, void* stream);
 
+/* capdec_prepare for features that arrive as dense fp16 rows [B,R,D] (uint16_t = IEEE binary16 bits) -- the packed feature
+ * shards of simpleimagecaptionzoo_b200/feature_store.py, which replace the reference's per-image zlib .npz files read
+ * one by one (Datasets.py:138-145; half the host->device bytes, no conversion pass).  BUTD: D = enc_dim.  AoA with the
+ * refiner loaded: D = enc_dim, runs what capdec_prepare_bottom_up runs.  fp16 math mode only (the library rounds fp32
+ * features to fp16 for its operands anyway: same captions as capdec_prepare on the same rounded values). */
+int capdec_prepare_f16(capdec_handle* h, const uint16_t* feats16, const float* mask, int32_t batch, int32_t regions, void* stream);
+
 /* AoADetection_Captioner / AoASpatial_Captioner from the bottom-up (or CNN grid) features: the encoder-side half the
  * reference runs in front of AoA_Decoder on every sampler call (AoA_Model.py:748-751, 598-601) --
  *   img_feats_porjection = Linear(enc_dim -> H) + ReLU under pack_wrapper (:650-655, 661-665: rows where mask == 0

@@ -24,7 +24,7 @@ SYMBOLS = (
     "capdec_abi_version", "capdec_create", "capdec_destroy", "capdec_last_error", "capdec_load_weight",
     "capdec_finalize_weights", "capdec_prepare", "capdec_beam_search", "capdec_sample", "capdec_launch_count",
     "capdec_test_gemm", "capdec_profile", "capdec_profile_read", "capdec_test_gemm_time",
-    "capdec_prepare_bottom_up", "capdec_get_refined", "capdec_score",
+    "capdec_prepare_bottom_up", "capdec_get_refined", "capdec_score", "capdec_prepare_f16",
     "capdec_cider_create", "capdec_cider_destroy", "capdec_cider_last_error", "capdec_cider_ngram_key", "capdec_cider_set_df",
     "capdec_cider_reward",
 )
@@ -61,6 +61,7 @@ def load_library(path: str = LIB_PATH) -> ctypes.CDLL:
     lib.capdec_finalize_weights.argtypes = [vp, vp]
     lib.capdec_prepare.argtypes = [vp, vp, vp, i32, i32, vp]
     lib.capdec_prepare_bottom_up.argtypes = [vp, vp, vp, i32, i32, vp]
+    lib.capdec_prepare_f16.argtypes = [vp, vp, vp, i32, i32, vp]
     lib.capdec_get_refined.argtypes = [vp, vp, vp]
     lib.capdec_beam_search.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
     lib.capdec_sample.argtypes = [vp, i32, i32, ctypes.c_uint64, i32, vp, vp, vp, vp]
@@ -220,15 +221,20 @@ class CaptionDecoder:
     def prepare(self, feats, mask=None):
         """feats: CUDA fp32 [B,R,D] (BUTD), [B,R,H] refined (AoA) or [B,E] (NIC); mask: [B,R] float or None."""
         torch = _torch()
-        feats = feats.to(self.device, torch.float32).contiguous()
+        f16 = feats.dtype == torch.float16 and feats.dim() == 3  # packed fp16 feature shards (feature_store.py)
+        feats = feats.to(self.device, torch.float16 if f16 else torch.float32).contiguous()
         if mask is not None:
             mask = mask.to(self.device, torch.float32).contiguous()
         B = feats.shape[0]
         R = feats.shape[1] if feats.dim() == 3 else 0
         with torch.cuda.device(self.device):
             self.stream.wait_stream(torch.cuda.current_stream(self.device))
-            self._check(self.lib.capdec_prepare(self._h, feats.data_ptr(), None if mask is None else mask.data_ptr(), B, R,
-                                                self.stream.cuda_stream), "capdec_prepare")
+            if f16:
+                self._check(self.lib.capdec_prepare_f16(self._h, feats.data_ptr(), None if mask is None else mask.data_ptr(), B, R,
+                                                        self.stream.cuda_stream), "capdec_prepare_f16")
+            else:
+                self._check(self.lib.capdec_prepare(self._h, feats.data_ptr(), None if mask is None else mask.data_ptr(), B, R,
+                                                    self.stream.cuda_stream), "capdec_prepare")
             torch.cuda.current_stream(self.device).wait_stream(self.stream)
         self._keep = (feats, mask)  # the library reads them during decode
         self.B, self.R = B, R
@@ -239,6 +245,8 @@ class CaptionDecoder:
         torch = _torch()
         if not self.has_refiner:
             raise RuntimeError("prepare_bottom_up needs the checkpoint's img_feats_porjection.* / aoa_refine.* entries")
+        if bu_feats.dtype == torch.float16:  # packed fp16 shard rows: same path, no conversion pass
+            return self.prepare(bu_feats, mask)
         bu_feats = bu_feats.to(self.device, torch.float32).contiguous()
         if mask is not None:
             mask = mask.to(self.device, torch.float32).contiguous()

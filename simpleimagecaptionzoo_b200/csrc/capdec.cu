@@ -635,14 +635,18 @@ int launch_refine_att(capdec_handle* h, int B, int R, const float* mask, cudaStr
 }
 
 // bu_feats [B,R,D] fp32 (+ prefix mask [B,R]) -> h->refined [B*R, H] fp32
-int run_refiner(capdec_handle* h, const float* bu, const float* mask, int B, int R, cudaStream_t st) {
+int run_refiner(capdec_handle* h, const float* bu, const float* mask, int B, int R, cudaStream_t st, const __half* bu_f16 = nullptr) {
     const int H = h->H, D = h->D;
     const size_t BR = static_cast<size_t>(B) * R;
     const int N = static_cast<int>(BR);
     CUtensorMap ma, mb;
-    cvt_f16_kernel<<<grid_for(BR * D / 4), 256, 0, st>>>(bu, BR, D, h->bu16.p, h->bu16.ld, h->bu16.lo, 0);
-    CK(h, cudaGetLastError());
-    h->launches++;
+    if (bu_f16) {  // packed fp16 shard rows are the GEMM operand as they are
+        CK(h, cudaMemcpyAsync(h->bu16.p, bu_f16, BR * D * sizeof(__half), cudaMemcpyDeviceToDevice, st));
+    } else {
+        cvt_f16_kernel<<<grid_for(BR * D / 4), 256, 0, st>>>(bu, BR, D, h->bu16.p, h->bu16.ld, h->bu16.lo, 0);
+        CK(h, cudaGetLastError());
+        h->launches++;
+    }
     {  // x = relu(W_p bu + b_p), zeros in the padded rows (pack_wrapper, AoA_Model.py:650-655)
         CKS(h, map_a(h, &ma, h->bu16));
         CKS(h, map_b(h, &mb, h->W_proj));
@@ -1372,7 +1376,32 @@ int capdec_finalize_weights(capdec_handle* h, void* stream) {
     return CAPDEC_OK;
 }
 
-static int prepare_impl(capdec_handle* h, const float* feats, const float* mask, int32_t batch, int32_t regions, cudaStream_t st);
+// feats16 != null: the features arrive as dense fp16 rows (packed feature shards) instead of fp32
+static int prepare_impl(capdec_handle* h, const float* feats, const float* mask, int32_t batch, int32_t regions, cudaStream_t st,
+                        const __half* feats16 = nullptr);
+
+int capdec_prepare_f16(capdec_handle* h, const uint16_t* feats16, const float* mask, int32_t batch, int32_t regions, void* stream) {
+    if (!h) return CAPDEC_ERR_INVALID;
+    if (!h->weights_ready) return fail(h, CAPDEC_ERR_STATE, "capdec_prepare_f16 before capdec_finalize_weights");
+    if (!feats16 || batch <= 0 || batch > h->Bmax) return fail(h, CAPDEC_ERR_INVALID, "prepare_f16: batch out of range or null feats");
+    if (h->split) return fail(h, CAPDEC_ERR_INVALID, "prepare_f16: the fp32-grade math mode (f16x3) needs fp32 features");
+    if (h->cfg.arch == CAPDEC_ARCH_NIC) return fail(h, CAPDEC_ERR_INVALID, "prepare_f16: NIC takes its (B, E) image embedding in fp32");
+    if (regions <= 0 || regions > h->Rmax) return fail(h, CAPDEC_ERR_INVALID, "prepare_f16: regions out of range");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(h, cudaSetDevice(h->cfg.device));
+    const __half* f16 = reinterpret_cast<const __half*>(feats16);
+    if (h->cfg.arch == CAPDEC_ARCH_AOA && h->refiner_ready) {  // fp16 bottom-up features -> projection + refiner
+        h->prepared = false;
+        const float* m = nullptr;
+        if (mask) {
+            CK(h, cudaMemcpyAsync(h->mask_buf, mask, static_cast<size_t>(batch) * regions * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            m = h->mask_buf;
+        }
+        CKS(h, run_refiner(h, nullptr, m, batch, regions, st, f16));
+        return prepare_impl(h, h->refined, m, batch, regions, st);
+    }
+    return prepare_impl(h, nullptr, mask, batch, regions, st, f16);
+}
 
 int capdec_prepare(capdec_handle* h, const float* feats, const float* mask, int32_t batch, int32_t regions, void* stream) {
     if (!h) return CAPDEC_ERR_INVALID;
@@ -1413,7 +1442,8 @@ int capdec_get_refined(capdec_handle* h, float* dst, void* stream) {
     return CAPDEC_OK;
 }
 
-static int prepare_impl(capdec_handle* h, const float* feats, const float* mask, int32_t batch, int32_t regions, cudaStream_t st) {
+static int prepare_impl(capdec_handle* h, const float* feats, const float* mask, int32_t batch, int32_t regions, cudaStream_t st,
+                        const __half* feats16) {
     const int H = h->H, E = h->E;
     h->prepared = false;
     CUtensorMap ma, mb;
@@ -1439,11 +1469,15 @@ static int prepare_impl(capdec_handle* h, const float* feats, const float* mask,
         if (h->cfg.arch == CAPDEC_ARCH_BUTD) {
             const int A = h->A, D = h->D;
             if (mask) return fail(h, CAPDEC_ERR_INVALID, "BUTD takes no region mask");
-            cvt_f16_kernel<<<grid_for(BR * D / 4), 256, 0, st>>>(feats, BR, D, h->feats16.p, h->feats16.ld, h->feats16.lo, 0);
+            // one pass: fp16 operand rows (padded for the attention kernel's bulk copies) + the mean over the regions
+            if (feats16)
+                butd_ingest_kernel<__half><<<batch, 256, 0, st>>>(feats16, regions, D, h->feats16.p, h->feats16.ld, h->feats16.lo,
+                                                                  h->mean16.p, h->mean16.ld, h->mean16.lo);
+            else
+                butd_ingest_kernel<float><<<batch, 256, 0, st>>>(feats, regions, D, h->feats16.p, h->feats16.ld, h->feats16.lo,
+                                                                 h->mean16.p, h->mean16.ld, h->mean16.lo);
             CK(h, cudaGetLastError());
-            region_mean_kernel<<<batch, 256, 0, st>>>(feats, nullptr, regions, D, nullptr, h->mean16.p, h->mean16.ld, h->mean16.lo);
-            CK(h, cudaGetLastError());
-            h->launches += 2;
+            h->launches += 1;
             {  // enc_att(feats): once per image instead of once per step and beam (BUTD_Model.py:57)
                 CKS(h, map_a(h, &ma, h->feats16));
                 CKS(h, map_b(h, &mb, h->W_aux1));
@@ -1470,7 +1504,8 @@ static int prepare_impl(capdec_handle* h, const float* feats, const float* mask,
         } else {
             cvt_f16_kernel<<<grid_for(BR * H / 4), 256, 0, st>>>(feats, BR, H, h->feats16.p, h->feats16.ld, h->feats16.lo, 0);
             CK(h, cudaGetLastError());
-            region_mean_kernel<<<batch, 256, 0, st>>>(feats, mask, regions, H, h->mean32, nullptr, 0, 0);
+            if (feats16) return fail(h, CAPDEC_ERR_INVALID, "prepare_f16: AoA refined features are taken in fp32 (fp16 applies to bu_feats)");
+            region_mean_kernel<float><<<batch, 256, 0, st>>>(feats, H, mask, regions, H, h->mean32, nullptr, 0, 0);
             CK(h, cudaGetLastError());
             h->launches += 2;
             CKS(h, map_a(h, &ma, h->feats16));

@@ -109,10 +109,12 @@ __global__ void cvt_f16_kernel(const float* __restrict__ src, size_t rows, int c
 }
 
 // mean over regions (optionally masked: sum(f*m)/sum(m), AoA_Model.py:422-425); writes fp32 and/or fp16 operand.
-__global__ void region_mean_kernel(const float* __restrict__ feats, const float* __restrict__ mask, int R, int C,
+// T = float (the reference's feature format) or __half (packed fp16 feature shards, rows of ld elements).
+template <typename T>
+__global__ void region_mean_kernel(const T* __restrict__ feats, int ld, const float* __restrict__ mask, int R, int C,
                                    float* __restrict__ out32, __half* __restrict__ out16, int ld16, int lo16) {
     const int b = blockIdx.x;
-    const float* f = feats + static_cast<size_t>(b) * R * C;
+    const T* f = feats + static_cast<size_t>(b) * R * ld;
     float msum = static_cast<float>(R);
     if (mask) {
         msum = 0.f;
@@ -121,7 +123,7 @@ __global__ void region_mean_kernel(const float* __restrict__ feats, const float*
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float acc = 0.f;
         for (int r = 0; r < R; ++r) {
-            const float x = f[static_cast<size_t>(r) * C + c];
+            const float x = static_cast<float>(f[static_cast<size_t>(r) * ld + c]);
             acc += mask ? x * mask[static_cast<size_t>(b) * R + r] : x;
         }
         const float m = acc / msum;
@@ -132,6 +134,45 @@ __global__ void region_mean_kernel(const float* __restrict__ feats, const float*
             out16[static_cast<size_t>(b) * ld16 + c] = hi;
             if (lo16 > 0) out16[static_cast<size_t>(b) * ld16 + lo16 + c] = lo;
         }
+    }
+}
+
+// BUTD ingest of one image per CTA in ONE pass over its features [R, D]: convert / copy into the row-padded fp16 operand
+// layout (hi | lo in the split mode) and accumulate the mean over the regions (BUTD_Model.py:251) as the fp16 operand of
+// the hoisted gate term.  T = float (reference format) or __half (packed feature shards).  D % 8 == 0.
+template <typename T>
+__global__ void __launch_bounds__(256) butd_ingest_kernel(const T* __restrict__ feats, int R, int D, __half* __restrict__ dst,
+                                                          int dst_ld, int dst_lo, __half* __restrict__ mean16, int mean_ld,
+                                                          int mean_lo) {
+    const int b = blockIdx.x;
+    const T* src = feats + static_cast<size_t>(b) * R * D;
+    __half* out = dst + static_cast<size_t>(b) * R * dst_ld;
+    const float rf = static_cast<float>(R);
+    for (int c = threadIdx.x * 8; c < D; c += blockDim.x * 8) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int r = 0; r < R; ++r) {
+            float x[8];
+            if constexpr (sizeof(T) == 4) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(src + static_cast<size_t>(r) * D + c));
+                const float4 d = __ldg(reinterpret_cast<const float4*>(src + static_cast<size_t>(r) * D + c) + 1);
+                x[0] = a.x, x[1] = a.y, x[2] = a.z, x[3] = a.w, x[4] = d.x, x[5] = d.y, x[6] = d.z, x[7] = d.w;
+                store_h16x8(out + static_cast<size_t>(r) * dst_ld + c, dst_lo, x);
+            } else {
+                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * D + c));
+                *reinterpret_cast<uint4*>(out + static_cast<size_t>(r) * dst_ld + c) = raw;
+                const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = __half22float2(h2[i]);
+                    x[2 * i] = f.x, x[2 * i + 1] = f.y;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += x[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = acc[i] / rf;
+        store_h16x8(mean16 + static_cast<size_t>(b) * mean_ld + c, mean_lo, acc);
     }
 }
 

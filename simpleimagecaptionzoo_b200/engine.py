@@ -157,6 +157,8 @@ class B200Captioner:
                 slot["mask"] = None if mask is None else mask.to(self.device, non_blocking=True)
                 slot["ready"] = torch.cuda.Event()
                 slot["ready"].record(copy)
+                if isinstance(visual_inputs, dict) and callable(visual_inputs.get("_on_copied")):
+                    visual_inputs["_on_copied"](slot["ready"])  # the producer may reuse its host buffer after this event
             return slot
 
         it = iter(batches)
