@@ -766,11 +766,11 @@ int launch_butd_att_stream_t(capdec_handle* h, const StepCtx& c, const T* enc, c
     return CAPDEC_OK;
 }
 
-template <int KR, int CTAS>
+template <int KR, int CTAS, bool FULL>
 int launch_butd_att_mma_t(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
     using C = AttMmaCfg<KR, CTAS>;
     static bool attr_set = false;
-    auto kern = butd_attention_mma_kernel<KR, CTAS>;
+    auto kern = butd_attention_mma_kernel<KR, CTAS, FULL>;
     const size_t smem = att_mma_smem_bytes(KR, C::STAGES, h->R, h->A, h->enc16.ld, h->feats16.ld);
     if (!attr_set) {
         CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -788,13 +788,18 @@ int launch_butd_att_mma_t(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
     h->launches++;
     return CAPDEC_OK;
 }
+template <int KR, int CTAS>
+int launch_butd_att_mma_d(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
+    if (h->A == 1024 && h->D == 2048) return launch_butd_att_mma_t<KR, CTAS, true>(h, c, st);
+    return launch_butd_att_mma_t<KR, CTAS, false>(h, c, st);
+}
 template <int KR>
 int launch_butd_att_mma(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
     // two CTAs per SM (3-stage rings) when the per-CTA state is small enough, else one CTA with a deep ring
     if (KR <= 3 && h->att_variant != 2 &&
         2 * (att_mma_smem_bytes(KR, AttMmaCfg<KR, 2>::STAGES, h->R, h->A, h->enc16.ld, h->feats16.ld) + 1024) <= 228 * 1024)
-        return launch_butd_att_mma_t<KR, 2>(h, c, st);
-    return launch_butd_att_mma_t<KR, 1>(h, c, st);
+        return launch_butd_att_mma_d<KR, 2>(h, c, st);
+    return launch_butd_att_mma_d<KR, 1>(h, c, st);
 }
 
 // fp16 mode reads the fp16 copies (projected features written by the projection GEMM, raw features converted for

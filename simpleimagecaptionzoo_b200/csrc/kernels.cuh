@@ -628,6 +628,7 @@ __host__ __device__ inline AttMmaShape att_mma_shape(int R, int ld_enc, int ld_f
     s.rp = (R + 15) / 16 * 16;
     return s;
 }
+constexpr int ATT_CG = 3;  // 16-row score chunks accumulated in registers between two cross-warp reductions (R <= 48: one)
 template <int KR, int CTAS> struct AttMmaCfg {
     static constexpr int CTAS_PER_SM = CTAS;
     static constexpr int STAGES = CTAS == 2 ? 3 : (KR <= 5 ? 6 : 5);
@@ -636,13 +637,15 @@ template <int KR, int CTAS> struct AttMmaCfg {
 __host__ __device__ inline size_t att_mma_smem_bytes(int KR, int stages, int R, int A, int ld_enc, int ld_feats) {
     const AttMmaShape s = att_mma_shape(R, ld_enc, ld_feats);
     return static_cast<size_t>(stages) * s.stage_bytes + 2 * stages * 8 + static_cast<size_t>(KR) * (A + 8) * 2 +
-           static_cast<size_t>(KR) * s.rp * 4 + 2 * 8 * KR * 16 * 4 + 8 * (s.rp + 8) * 2 + static_cast<size_t>(A) * 2 + 128;
+           static_cast<size_t>(KR) * s.rp * 4 + 8 * KR * ATT_CG * 16 * 4 + 8 * (s.rp + 8) * 2 + static_cast<size_t>(A) * 2 + 128;
 }
 
+// relu(x + d) on two fp16 lanes in ONE instruction: fma.rn.relu(x, 1, d) -- the product by 1 is exact, so the result is
+// the correctly rounded sum, clamped at 0 (HFMA2.RELU instead of HADD2 + HMNMX2)
 __device__ __forceinline__ uint32_t relu_add_h2(uint32_t x, uint32_t d) {
-    const __half2 r = __hmax2(__hadd2(*reinterpret_cast<const __half2*>(&x), *reinterpret_cast<const __half2*>(&d)),
-                              __float2half2_rn(0.f));
-    return *reinterpret_cast<const uint32_t*>(&r);
+    uint32_t r;
+    asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0x3C003C00u), "r"(d));
+    return r;
 }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     const __half2 r = __floats2half2_rn(a, b);
@@ -662,7 +665,9 @@ __device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
     }
 }
 
-template <int KR, int CTAS>
+// FULL: A == 1024 and D == 2048 (the reference's dims): every warp owns 8 score tiles and 16 context tiles, known at
+// compile time (no per-tile predicates).
+template <int KR, int CTAS, bool FULL>
 __global__ void __launch_bounds__(288, CTAS)
 butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __half* __restrict__ feats16, int ld_feats,
                           size_t total_rows, const float* __restrict__ dec_ctx, const float* __restrict__ w_aff, float b_aff, int B,
@@ -675,8 +680,8 @@ butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * sh.stage_bytes);
     __half* s_dec16 = reinterpret_cast<__half*>(bars + 2 * STAGES);          // [KR][A+8]
     float* s_e = reinterpret_cast<float*>(s_dec16 + KR * (A + 8));           // [KR][rp]
-    float* s_part = s_e + KR * sh.rp;                                        // [2][8][KR][16]
-    __half* s_alpha = reinterpret_cast<__half*>(s_part + 2 * 8 * KR * 16);   // [8][rp+8]
+    float* s_part = s_e + KR * sh.rp;                                        // [8 warps][KR][ATT_CG*16]
+    __half* s_alpha = reinterpret_cast<__half*>(s_part + 8 * KR * ATT_CG * 16);  // [8][rp+8]
     __half* s_w16 = s_alpha + 8 * (sh.rp + 8);                               // [A]
     const uint32_t full_bar = smem_u32(bars), empty_bar = smem_u32(bars + STAGES);
     const uint32_t ring = smem_u32(smem);
@@ -706,9 +711,12 @@ butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __
             for (int img = blockIdx.x; img < B; img += gridDim.x) {
                 for (int c = 0; c < n_chunks1 + n_chunks3; ++c) {
                     const bool p1 = c < n_chunks1;
-                    const size_t row0 = static_cast<size_t>(img) * R + (p1 ? c * 16 : (c - n_chunks1) * 8);
+                    const int r0 = p1 ? c * 16 : (c - n_chunks1) * 8;
+                    const size_t row0 = static_cast<size_t>(img) * R + r0;
+                    // only the image's own rows: the last chunk of a phase is short (R = 36: 16 + 16 + 4 and 4 x 8 + 4 rows);
+                    // the rest of its slot keeps finite fp16 values of an earlier chunk, which get alpha = 0 / are ignored
                     size_t nr = p1 ? 16 : 8;
-                    if (row0 + nr > total_rows) nr = total_rows - row0;  // never read past the last prepared row
+                    if (r0 + static_cast<int>(nr) > R) nr = R - r0;
                     const uint32_t bytes = static_cast<uint32_t>(nr) * (p1 ? sh.row1 : sh.row3);
                     const __half* src = p1 ? enc16 + row0 * ld_enc : feats16 + row0 * ld_feats;
                     mbar_wait_lean(empty_bar + 8 * stage, phase ^ 1);
@@ -727,8 +735,8 @@ butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __
     const uint32_t wmask = g == 0 ? 0xFFFFFFFFu : 0u;  // B fragment of the w-dot: w in output column 0 only
     // loop-invariant per-thread shared addresses (bytes).  Warp cw owns column tiles cw, cw+8, ... (phase 1) and the
     // 16 d-tiles [16cw, 16cw+16) (phase 3); tile j of a warp is a compile-time offset from these bases.
-    const int nj1 = max(0, min(8, ((A >> 4) - cw + 7) >> 3));           // valid phase-1 tiles of this warp
-    const int nj3 = max(0, min(16, (D >> 4) - cw * 16));                // valid phase-3 tiles of this warp
+    const int nj1 = FULL ? 8 : max(0, min(8, ((A >> 4) - cw + 7) >> 3));   // valid phase-1 tiles of this warp
+    const int nj3 = FULL ? 16 : max(0, min(16, (D >> 4) - cw * 16));      // valid phase-3 tiles of this warp
     const uint32_t w_addr = smem_u32(s_w16) + (cw * 16 + 2 * t) * 2;    // + 256*j (+16 for the upper 8 columns)
     const uint32_t dec_addr = smem_u32(s_dec16) + (cw * 16 + 2 * t) * 2;  // + k*(A+8)*2 + 256*j (+16)
     const uint32_t dec_pitch = (A + 8) * 2;
@@ -748,7 +756,6 @@ butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __
     load_dec(blockIdx.x);
     int stage = 0;
     uint32_t phase = 0;
-    int flip = 0;
     for (int img = blockIdx.x; img < B; img += gridDim.x) {
         if (dec_ok) {
 #pragma unroll
@@ -760,55 +767,75 @@ butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __
             }
         }
         named_bar_sync(1, 256);
-        // ---------------- phase 1: scores
-        for (int c = 0; c < n_chunks1; ++c) {
-            float acc[KR][4];
+        // ---------------- phase 1: scores.  Each warp sums its 8 column tiles of up to ATT_CG row chunks in registers;
+        // the 8 warps' partial sums meet in shared memory once per chunk group (once per image for R <= 48)
+        const bool one_group = n_chunks1 <= ATT_CG;
+        for (int c0 = 0; c0 < n_chunks1; c0 += ATT_CG) {
+            float acc[ATT_CG][KR][4];
 #pragma unroll
-            for (int k = 0; k < KR; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f;
-            mbar_wait_lean(full_bar + 8 * stage, phase);
-            const uint32_t base1 = ring + stage * sh.stage_bytes + ld1_off;
+            for (int cc = 0; cc < ATT_CG; ++cc)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (j < nj1) {
-                    uint32_t x[4];
-                    ldmatrix_x4(x, base1 + 256 * j);
-                    const uint32_t wb0 = lds_b32(w_addr + 256 * j) & wmask;
-                    const uint32_t wb1 = lds_b32(w_addr + 256 * j + 16) & wmask;
+                for (int k = 0; k < KR; ++k) acc[cc][k][0] = acc[cc][k][1] = acc[cc][k][2] = acc[cc][k][3] = 0.f;
 #pragma unroll
-                    for (int k = 0; k < KR; ++k) {
-                        const uint32_t dlo = lds_b32(dec_addr + k * dec_pitch + 256 * j);
-                        const uint32_t dhi = lds_b32(dec_addr + k * dec_pitch + 256 * j + 16);
-                        mma_m16n8k16_f16(acc[k], relu_add_h2(x[0], dlo), relu_add_h2(x[1], dlo), relu_add_h2(x[2], dhi),
-                                         relu_add_h2(x[3], dhi), wb0, wb1);
+            for (int cc = 0; cc < ATT_CG; ++cc) {
+                if (c0 + cc < n_chunks1) {
+                    mbar_wait_lean(full_bar + 8 * stage, phase);
+                    const uint32_t base1 = ring + stage * sh.stage_bytes + ld1_off;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (FULL || j < nj1) {
+                            uint32_t x[4];
+                            ldmatrix_x4(x, base1 + 256 * j);
+                            const uint32_t wb0 = lds_b32(w_addr + 256 * j) & wmask;
+                            const uint32_t wb1 = lds_b32(w_addr + 256 * j + 16) & wmask;
+#pragma unroll
+                            for (int k = 0; k < KR; ++k) {
+                                const uint32_t dlo = lds_b32(dec_addr + k * dec_pitch + 256 * j);
+                                const uint32_t dhi = lds_b32(dec_addr + k * dec_pitch + 256 * j + 16);
+                                mma_m16n8k16_f16(acc[cc][k], relu_add_h2(x[0], dlo), relu_add_h2(x[1], dlo), relu_add_h2(x[2], dhi),
+                                                 relu_add_h2(x[3], dhi), wb0, wb1);
+                            }
+                        }
                     }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty_bar + 8 * stage);
+                    if (++stage == STAGES) stage = 0, phase ^= 1;
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty_bar + 8 * stage);
-            if (++stage == STAGES) stage = 0, phase ^= 1;
-            float* part = s_part + flip * 8 * KR * 16;
-            flip ^= 1;
             if (t == 0) {
 #pragma unroll
-                for (int k = 0; k < KR; ++k) {
-                    part[(cw * KR + k) * 16 + g] = acc[k][0];
-                    part[(cw * KR + k) * 16 + g + 8] = acc[k][2];
-                }
-            }
-            named_bar_sync(1, 256);
-            if (tid < KR * 16) {
-                const int k = tid >> 4, i = tid & 15;
-                float sum = 0.f;
+                for (int cc = 0; cc < ATT_CG; ++cc)
 #pragma unroll
-                for (int w8 = 0; w8 < 8; ++w8) sum += part[(w8 * KR + k) * 16 + i];
-                const int r = c * 16 + i;
-                if (r < R && k < K) s_e[k * sh.rp + r] = sum + b_aff;
+                    for (int k = 0; k < KR; ++k) {
+                        s_part[(cw * KR + k) * (ATT_CG * 16) + cc * 16 + g] = acc[cc][k][0];
+                        s_part[(cw * KR + k) * (ATT_CG * 16) + cc * 16 + g + 8] = acc[cc][k][2];
+                    }
+            }
+            if (c0 == 0) load_dec(img + gridDim.x);
+            named_bar_sync(1, 256);
+            if (!one_group) {  // long region lists: fold this group's partial sums into s_e, then reuse the buffer
+                for (int i = tid; i < KR * ATT_CG * 16; i += 256) {
+                    const int k = i / (ATT_CG * 16), q = i - k * (ATT_CG * 16);
+                    float sum = 0.f;
+#pragma unroll
+                    for (int w8 = 0; w8 < 8; ++w8) sum += s_part[(w8 * KR + k) * (ATT_CG * 16) + q];
+                    const int r = c0 * 16 + q;
+                    if (r < R && k < K) s_e[k * sh.rp + r] = sum + b_aff;
+                }
+                named_bar_sync(1, 256);
             }
         }
-        load_dec(img + gridDim.x);
-        named_bar_sync(1, 256);
         // ---------------- phase 2: softmax over regions -> fp16 alpha rows (B operand of phase 3)
         for (int k = cw; k < K; k += 8) {
+            if (one_group) {  // the reduction over the 8 warps' partial sums is folded into the softmax warp's loads
+                for (int r = lane; r < R; r += 32) {
+                    float sum = 0.f;
+#pragma unroll
+                    for (int w8 = 0; w8 < 8; ++w8) sum += s_part[(w8 * KR + k) * (ATT_CG * 16) + r];
+                    s_e[k * sh.rp + r] = sum + b_aff;
+                }
+                __syncwarp();
+            }
             float m = -INFINITY;
             for (int r = lane; r < R; r += 32) m = fmaxf(m, s_e[k * sh.rp + r]);
             m = warp_max(m);
@@ -837,7 +864,7 @@ butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __
             const uint32_t base3 = ring + stage * sh.stage_bytes + ld3_off;
 #pragma unroll
             for (int jp = 0; jp < 8; ++jp) {
-                if (2 * jp < nj3) {
+                if (FULL || 2 * jp < nj3) {
                     uint32_t m4[4];
                     ldmatrix_x4_trans(m4, base3 + 64 * jp);
                     mma_m16n8k8_f16(acc3[2 * jp], m4[0], m4[1], b0);
@@ -855,7 +882,7 @@ butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __
             const bool b0ok = 2 * t < K, b1ok = 2 * t + 1 < K;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                if (j < nj3) {
+                if (FULL || j < nj3) {
                     if (b0ok) {
                         o0[16 * j] = __float2half_rn(acc3[j][0]);
                         o0[16 * j + 8] = __float2half_rn(acc3[j][2]);
@@ -1366,9 +1393,11 @@ aoa_attention_mma_kernel(const __half* __restrict__ k16, const __half* __restric
             for (int img = blockIdx.x; img < B; img += gridDim.x) {
                 for (int c = 0; c < 2 * n_chunks; ++c) {
                     const bool kpart = c < n_chunks;
-                    const size_t row0 = static_cast<size_t>(img) * R + (kpart ? c : c - n_chunks) * 16;
-                    size_t nr = 16;
-                    if (row0 + nr > total_rows) nr = total_rows - row0;
+                    const int r0 = (kpart ? c : c - n_chunks) * 16;
+                    const size_t row0 = static_cast<size_t>(img) * R + r0;
+                    // only the image's own rows (R = 36: 16 + 16 + 4); the rest of a short chunk's slot keeps finite fp16
+                    // values of an earlier chunk: their scores are never read and their probabilities are zero
+                    const size_t nr = r0 + 16 > R ? R - r0 : 16;
                     const uint32_t bytes = static_cast<uint32_t>(nr) * row_bytes;
                     mbar_wait_lean(empty_bar + 8 * stage, phase ^ 1);
                     mbar_arrive_expect_tx(full_bar + 8 * stage, bytes);
