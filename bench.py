@@ -25,8 +25,18 @@ import time
 if "reference" in sys.argv:
     for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[_v] = str(os.cpu_count())
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):
+    os.environ["NCCL_DEBUG"] = "NONE"  # both VERSION and WARN make NCCL printf its version banner to stdout
+
+# The contract is ONE JSON line on stdout.  Native libraries (NCCL, cuDNN, ...) printf to file descriptor 1 whatever Python's
+# sys.stdout is, so fd 1 is pointed at stderr for the whole run and the JSON line is written to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 import numpy as np  # noqa: E402
 
@@ -216,7 +226,7 @@ def run_reference_arm(args, w):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -447,7 +457,7 @@ def run_gpu_arm(args, w):
         line["parity_sample"] = {"images": n_cpu, "exact": sum(v == "exact" for v in verdict),
                                  "tie_justified": sum(v == "tie" for v in verdict), "diff": sum(v == "diff" for v in verdict)}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
