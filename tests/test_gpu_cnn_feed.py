@@ -67,3 +67,26 @@ def test_nic_captioner_on_raw_images():
     streamed = list(cap.beam_search_stream(({"img_tensors": images.pin_memory()} for _ in range(3)), beam_size=3))
     for s in streamed:
         assert np.array_equal(s, tok2.cpu().numpy())
+
+
+def test_aoa_spatial_from_images_runs_the_native_refiner():
+    """AoASpatial: images -> CNN grid (feed) -> img_feats_porjection + aoa_refine + decoder inside the library; refined
+    features equal the oracle's refiner applied to the feed's own grid."""
+    from oracle import capdec_oracle as orc
+    from simpleimagecaptionzoo_b200 import cnn_feed, engine
+    dims = synth.DIMS["AOA"]
+    sd = synth.make_state_dict("AOA", seed=0, **dims)
+    sd.update(synth.make_refiner_state_dict(hidden_dim=dims["hidden_dim"], enc_dim=2048, seed=0))
+    sd.update(cnn_feed.make_encoder_state_dict(seed=0))
+    settings = dict(model_type="AoASpatial", embed_dim=dims["embed_dim"], hidden_dim=dims["hidden_dim"], enc_img_size=7)
+    cap = engine.B200Captioner("AoASpatial", settings, dims["vocab_size"], sd, max_batch=4, max_rows=3, max_seq=20)
+    feed = cnn_feed.attach(cap, sd)
+    assert cap.native_refiner
+    images = torch.randn(4, 3, 224, 224, generator=torch.Generator().manual_seed(9))
+    tok = cap.beam_search_sampler({"img_tensors": images}, beam_size=3)
+    assert tok.shape == (4, 21)
+    grid = feed({"img_tensors": images})
+    assert grid.shape == (4, 49, 2048)
+    got = cap.decoder.refined_features().cpu().numpy()
+    ref = orc.aoa_project_refine({k: v for k, v in sd.items() if isinstance(v, np.ndarray)}, grid.cpu().numpy(), None, num_heads=8)
+    assert np.abs(got - ref).max() < 6e-2

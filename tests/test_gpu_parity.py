@@ -447,3 +447,52 @@ def test_score_reproduces_rollout_logprobs(name):
     with pytest.raises(ValueError):
         dec.score(tok[:3], 2)
     dec.close()
+
+
+@pytest.mark.parametrize("R,masked", [(10, True), (49, False), (64, True), (100, True), (196, False)])
+@pytest.mark.parametrize("math", ["f16", "f16x3"])
+def test_refiner_region_counts(R, masked, math):
+    """Every key-tile instantiation of the refiner's self-attention (R <= 48 / 64 / 112 / 208 keys; the generic kernel in
+    the fp32-grade mode) at BASELINE dims against the oracle: 7x7 and 14x14 CNN grids (AoASpatial), adaptive bottom-up
+    features with up to 100 boxes and a prefix mask."""
+    from simpleimagecaptionzoo_b200 import synth
+    capdec = _capdec()
+    dims = synth.DIMS["AOA"]
+    sd = synth.make_state_dict("AOA", seed=2, **dims)
+    sd.update(synth.make_refiner_state_dict(hidden_dim=dims["hidden_dim"], enc_dim=2048, seed=2))
+    B = 3
+    bu = synth.make_region_feats(B, R, 2048, 11)
+    mask = synth.make_region_mask(B, R, max(1, R // 3), 11) if masked else None
+    if mask is not None:
+        bu = bu * mask[:, :, None]
+    dec = capdec.CaptionDecoder("AOA", sd, hidden_dim=dims["hidden_dim"], embed_dim=dims["embed_dim"], vocab_size=dims["vocab_size"],
+                                enc_dim=2048, num_heads=dims["num_heads"], max_batch=B, max_regions=R, max_rows=3, max_seq=20, math=math)
+    dec.prepare_bottom_up(torch.from_numpy(bu).cuda(), None if mask is None else torch.from_numpy(mask).cuda())
+    got = dec.refined_features().cpu().numpy()
+    ref = orc.aoa_project_refine(sd, bu, mask, num_heads=dims["num_heads"])
+    valid = np.ones((B, R), bool) if mask is None else mask.astype(bool)
+    err = np.abs(got - ref)[valid].max()
+    assert err < REFINED_BOUND[math], err
+    tok, _, _ = dec.beam_search(3, 20)  # the decoder consumes the refined features of any region count
+    assert tok.shape == (B, 21)
+    dec.close()
+
+
+def test_fp16_bottom_up_features_with_mask():
+    """capdec_prepare_f16 on the AoA encoder side with a prefix mask == the fp32 entry point on the same rounded values."""
+    meta, _ = load_case("aoaref_full_k3_masked")
+    capdec = _capdec()
+    sd, bu, mask = rebuild_refiner(meta)
+    d = meta["dims"]
+    dec = capdec.CaptionDecoder("AOA", sd, hidden_dim=d["hidden_dim"], embed_dim=d["embed_dim"], vocab_size=d["vocab_size"],
+                                enc_dim=2048, num_heads=d["num_heads"], max_batch=meta["B"], max_regions=meta["R"], max_rows=3, max_seq=20)
+    f16 = torch.from_numpy(bu).half().cuda()
+    m = torch.from_numpy(mask).cuda()
+    dec.prepare_bottom_up(f16, m)
+    a = dec.refined_features().clone()
+    ta, _, _ = dec.beam_search(3, 20)
+    dec.prepare_bottom_up(f16.float(), m)
+    b = dec.refined_features()
+    tb, _, _ = dec.beam_search(3, 20)
+    assert torch.equal(a, b) and torch.equal(ta, tb)
+    dec.close()
