@@ -34,11 +34,16 @@ def main():
     ap.add_argument("--max-seq", type=int, default=20)
     ap.add_argument("--oracle-sample", type=int, default=48)
     ap.add_argument("--chunk", type=int, default=1000)
+    ap.add_argument("--bottom-up", action="store_true",
+                    help="AOA: start from 36x2048 bottom-up features (img_feats_porjection + aoa_refine + decoder in the library)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "agreement.json"))
     args = ap.parse_args()
 
     dims = synth.DIMS[args.arch]
     sd = synth.make_state_dict(args.arch, seed=0, **dims)
+    bottom_up = args.bottom_up and args.arch == "AOA"
+    if bottom_up:
+        sd.update(synth.make_refiner_state_dict(hidden_dim=dims["hidden_dim"], enc_dim=2048, seed=0))
     K, T, R = args.beam, args.max_seq, args.regions
     kw = dict(hidden_dim=dims["hidden_dim"], embed_dim=dims["embed_dim"], vocab_size=dims["vocab_size"],
               atten_dim=dims.get("atten_dim", 0), enc_dim=dims.get("enc_dim", 2048), num_heads=dims.get("num_heads", 8),
@@ -48,8 +53,8 @@ def main():
     o = orc.make_decoder(args.arch, sd)
 
     def feats_for(lo, n):
-        if args.arch == "BUTD":
-            return synth.make_region_feats(n, R, dims["enc_dim"], 7000 + lo)
+        if args.arch == "BUTD" or bottom_up:
+            return synth.make_region_feats(n, R, dims.get("enc_dim", 2048), 7000 + lo)
         if args.arch == "NIC":
             return synth.make_image_embed(n, dims["embed_dim"], 7000 + lo)
         return synth.make_refined_feats(n, R, dims["hidden_dim"], 7000 + lo)
@@ -63,9 +68,9 @@ def main():
         n = min(args.chunk, args.images - lo)
         f = feats_for(lo, n)
         ft = torch.from_numpy(f).cuda()
-        fast.prepare(ft)
+        (fast.prepare_bottom_up if bottom_up else fast.prepare)(ft)
         tf, sf, _ = fast.beam_search(K, T)
-        exact.prepare(ft)
+        (exact.prepare_bottom_up if bottom_up else exact.prepare)(ft)
         tx, sx, _ = exact.beam_search(K, T)
         torch.cuda.synchronize()
         tf, tx, sf, sx = tf.cpu().numpy(), tx.cpu().numpy(), sf.cpu().numpy(), sx.cpu().numpy()
@@ -75,7 +80,7 @@ def main():
         bad = np.nonzero(~same)[0]
         sample = rng.choice(np.nonzero(same)[0], size=min(args.oracle_sample * n // args.images + 1, int(same.sum())), replace=False)
         for i in list(bad) + list(sample):
-            o.prepare(f[i:i + 1])
+            o.prepare(orc.aoa_project_refine(sd, f[i:i + 1]) if bottom_up else f[i:i + 1])
             res = orc.beam_search_batched(o, K, T)
             vx = orc.agreement(tx[i:i + 1], res.tokens, res.min_gap, tol=1e-4)[0]
             n_x3_checked += 1
@@ -93,7 +98,7 @@ def main():
               f"  ({time.time() - t0:.0f}s)", flush=True)
     score_err = np.concatenate(score_err)
     out = {
-        "arch": args.arch, "images": args.images, "beam": K, "max_seq": T, "regions": R, "vocab": dims["vocab_size"],
+        "arch": args.arch, "from_bottom_up_features": bottom_up, "images": args.images, "beam": K, "max_seq": T, "regions": R, "vocab": dims["vocab_size"],
         "f16_vs_reference": {"exact": n_same, "tie_justified": n_tie, "diff": n_diff,
                              "exact_or_tie_frac": (n_same + n_tie) / args.images, "exact_frac": n_same / args.images},
         "f16x3_vs_oracle": {"checked": n_x3_checked, "exact": int(n_x3_exact), "tie_justified": int(n_x3_tie),
