@@ -102,6 +102,7 @@ struct capdec_handle {
     int* seqs[2] = {nullptr, nullptr};
     float *cum = nullptr, *best_score = nullptr;
     // CUDA graph of one whole beam-search decode (all steps), replayed while the shapes / buffers stay the same
+    bool use_pdl = false;    // CAPDEC_PDL=1: programmatic dependent launch inside the decode loop (measured neutral)
     bool use_graphs = true;  // CAPDEC_NO_GRAPH=1 disables
     cudaGraphExec_t graph_exec = nullptr;
     struct GraphKey {
@@ -170,6 +171,25 @@ void prof_end(capdec_handle* h, cudaStream_t st) {
     cudaEventRecord(h->recs.back().b, st);
 }
 
+// Launch a decode-loop kernel with programmatic dependent launch: its blocks may be scheduled, and run their set-up, while
+// the previous kernel of the stream drains (every such kernel calls griddep_wait() before it reads what a predecessor
+// wrote).  Not while per-launch timing is on (the event records between launches would hide the overlap anyway).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(const capdec_handle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                       Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (h->use_pdl && !h->prof) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 template <typename T>
 int dalloc(capdec_handle* h, T** out, size_t n, bool zero = true) {
     void* p = nullptr;
@@ -232,7 +252,7 @@ int launch_gemm_t(capdec_handle* h, const CUtensorMap& ma, const CUtensorMap& mb
     const int cat = EPI == EPI_LSTM ? CAPDEC_CAT_GEMM_LSTM : EPI == EPI_STORE ? CAPDEC_CAT_GEMM_STORE
                   : EPI == EPI_GLU ? CAPDEC_CAT_GEMM_GLU : CAPDEC_CAT_GEMM_LOGITS;
     prof_begin(h, cat, 2.0 * p.M * p.N * (static_cast<double>(p.k_blocks) * BLOCK_K), st);
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, pg);
+    CK(h, launch_pdl(h, kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, ma, mb, pg));
     prof_end(h, st);
     CK(h, cudaGetLastError());
     h->launches++;
@@ -255,7 +275,7 @@ int launch_gemm2_t(capdec_handle* h, const CUtensorMap& ma, const CUtensorMap& m
     const int cat = EPI == EPI_LSTM ? CAPDEC_CAT_GEMM_LSTM : EPI == EPI_STORE ? CAPDEC_CAT_GEMM_STORE
                   : EPI == EPI_GLU ? CAPDEC_CAT_GEMM_GLU : CAPDEC_CAT_GEMM_LOGITS;
     prof_begin(h, cat, 2.0 * p.M * p.N * (static_cast<double>(p.k_blocks) * BLOCK_K), st);
-    kern<<<2 * pairs, GEMM_THREADS, GemmCfg2::SMEM_BYTES, st>>>(ma, mb, pg);
+    CK(h, launch_pdl(h, kern, dim3(2 * pairs), dim3(GEMM_THREADS), GemmCfg2::SMEM_BYTES, st, ma, mb, pg));
     prof_end(h, st);
     CK(h, cudaGetLastError());
     h->launches++;
@@ -500,9 +520,10 @@ int finalize_aoa(capdec_handle* h, cudaStream_t st) {
 int launch_layernorm(capdec_handle* h, const float* x, int M, const float* gain, const float* bias, __half* q16, int ld16, int lo16,
                      float* out32, cudaStream_t st) {
     prof_begin(h, CAPDEC_CAT_OTHER, 0.0, st);
-    if (h->H == 1024) aoa_layernorm_vec_kernel<8><<<(M + 7) / 8, 256, 0, st>>>(x, M, gain, bias, 1e-6f, q16, ld16, lo16, out32);
-    else if (h->H == 512) aoa_layernorm_vec_kernel<4><<<(M + 7) / 8, 256, 0, st>>>(x, M, gain, bias, 1e-6f, q16, ld16, lo16, out32);
-    else aoa_layernorm_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, M, h->H, gain, bias, 1e-6f, q16, ld16, lo16, out32);
+    const dim3 grid((M + 7) / 8), block(256);
+    if (h->H == 1024) CK(h, launch_pdl(h, aoa_layernorm_vec_kernel<8>, grid, block, 0, st, x, M, gain, bias, 1e-6f, q16, ld16, lo16, out32));
+    else if (h->H == 512) CK(h, launch_pdl(h, aoa_layernorm_vec_kernel<4>, grid, block, 0, st, x, M, gain, bias, 1e-6f, q16, ld16, lo16, out32));
+    else CK(h, launch_pdl(h, aoa_layernorm_kernel, grid, block, 0, st, x, M, h->H, gain, bias, 1e-6f, q16, ld16, lo16, out32));
     prof_end(h, st);
     CK(h, cudaGetLastError());
     h->launches++;
@@ -780,9 +801,9 @@ int launch_butd_att_mma_t(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
     const int cap = h->num_sms * C::CTAS_PER_SM;
     const int grid = h->B < cap ? h->B : cap;
     prof_begin(h, CAPDEC_CAT_ATTENTION, 0.0, st);
-    kern<<<grid, C::THREADS, smem, st>>>(h->enc16.p, h->enc16.ld, h->feats16.p, h->feats16.ld, static_cast<size_t>(h->B) * h->R,
-                                         h->dec_ctx, h->w_aff, h->b_aff, h->B, h->R, h->A, h->D, c.K, h->XB.p, h->XB.ld, c.alphas,
-                                         c.alpha_stride);
+    CK(h, launch_pdl(h, kern, dim3(grid), dim3(C::THREADS), smem, st, h->enc16.p, h->enc16.ld, h->feats16.p, h->feats16.ld,
+                     static_cast<size_t>(h->B) * h->R, h->dec_ctx, h->w_aff, h->b_aff, h->B, h->R, h->A, h->D, c.K, h->XB.p, h->XB.ld,
+                     c.alphas, c.alpha_stride));
     prof_end(h, st);
     CK(h, cudaGetLastError());
     h->launches++;
@@ -837,8 +858,8 @@ int launch_aoa_att_mma(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
     }
     const int grid = h->B < h->num_sms ? h->B : h->num_sms;
     prof_begin(h, CAPDEC_CAT_ATTENTION, 0.0, st);
-    kern<<<grid, 288, smem, st>>>(h->k16.p, h->v16.p, h->k16.ld, static_cast<size_t>(h->B) * h->R, h->q16.p, h->q16.ld, h->mask, h->B,
-                                  h->R, h->H, h->NH, c.K, stages, h->XB.p, h->XB.ld, c.alphas, c.alpha_stride);
+    CK(h, launch_pdl(h, kern, dim3(grid), dim3(288), smem, st, h->k16.p, h->v16.p, h->k16.ld, static_cast<size_t>(h->B) * h->R,
+                     h->q16.p, h->q16.ld, h->mask, h->B, h->R, h->H, h->NH, c.K, stages, h->XB.p, h->XB.ld, c.alphas, c.alpha_stride));
     prof_end(h, st);
     CK(h, cudaGetLastError());
     h->launches++;
@@ -1217,6 +1238,8 @@ static int create_impl(capdec_handle* h) {
         h->pair_gemm = !(g1 && g1[0] == '1');
         const char* ng = getenv("CAPDEC_NO_GRAPH");
         h->use_graphs = !(ng && ng[0] == '1');
+        const char* np = getenv("CAPDEC_PDL");
+        h->use_pdl = np && np[0] == '1';
         const char* v = getenv("CAPDEC_ATT_VARIANT");
         h->att_variant = v ? atoi(v) : 0;
     }
@@ -1636,11 +1659,11 @@ static int enqueue_beam_search(capdec_handle* h, int32_t beam, int32_t max_seq, 
         s.seqs_in = h->seqs[(t + 1) & 1];
         s.seqs_out = h->seqs[t & 1];
         prof_begin(h, CAPDEC_CAT_BOOKKEEPING, 0.0, st);
-        if (K <= 1) beam_step_kernel<4, 1><<<B, 128, 0, st>>>(h->part, n_slots, s, t, ops);
-        else if (K <= 3) beam_step_kernel<4, 3><<<B, 128, 0, st>>>(h->part, n_slots, s, t, ops);
-        else if (K <= 4) beam_step_kernel<4, 5><<<B, 128, 0, st>>>(h->part, n_slots, s, t, ops);
-        else if (K <= 5) beam_step_kernel<8, 5><<<B, 128, 0, st>>>(h->part, n_slots, s, t, ops);
-        else beam_step_kernel<8, 8><<<B, 128, 0, st>>>(h->part, n_slots, s, t, ops);
+        if (K <= 1) CK(h, launch_pdl(h, beam_step_kernel<4, 1>, dim3(B), dim3(128), 0, st, h->part, n_slots, s, t, ops));
+        else if (K <= 3) CK(h, launch_pdl(h, beam_step_kernel<4, 3>, dim3(B), dim3(128), 0, st, h->part, n_slots, s, t, ops));
+        else if (K <= 4) CK(h, launch_pdl(h, beam_step_kernel<4, 5>, dim3(B), dim3(128), 0, st, h->part, n_slots, s, t, ops));
+        else if (K <= 5) CK(h, launch_pdl(h, beam_step_kernel<8, 5>, dim3(B), dim3(128), 0, st, h->part, n_slots, s, t, ops));
+        else CK(h, launch_pdl(h, beam_step_kernel<8, 8>, dim3(B), dim3(128), 0, st, h->part, n_slots, s, t, ops));
         prof_end(h, st);
         CK(h, cudaGetLastError());
         h->launches++;
@@ -1710,10 +1733,10 @@ static int sample_impl(capdec_handle* h, int32_t mode, int32_t n_per_image, uint
         c.alpha_stride = static_cast<size_t>(max_seq) * h->R;
         CKS(h, run_step(h, c, st));
         prof_begin(h, CAPDEC_CAT_BOOKKEEPING, 0.0, st);
-        if (n <= 1) sample_step_kernel<1><<<B, 128, 0, st>>>(h->part, n_slots, s, t - 1, ops);
-        else if (n <= 3) sample_step_kernel<3><<<B, 128, 0, st>>>(h->part, n_slots, s, t - 1, ops);
-        else if (n <= 5) sample_step_kernel<5><<<B, 128, 0, st>>>(h->part, n_slots, s, t - 1, ops);
-        else sample_step_kernel<8><<<B, 128, 0, st>>>(h->part, n_slots, s, t - 1, ops);
+        if (n <= 1) CK(h, launch_pdl(h, sample_step_kernel<1>, dim3(B), dim3(128), 0, st, h->part, n_slots, s, t - 1, ops));
+        else if (n <= 3) CK(h, launch_pdl(h, sample_step_kernel<3>, dim3(B), dim3(128), 0, st, h->part, n_slots, s, t - 1, ops));
+        else if (n <= 5) CK(h, launch_pdl(h, sample_step_kernel<5>, dim3(B), dim3(128), 0, st, h->part, n_slots, s, t - 1, ops));
+        else CK(h, launch_pdl(h, sample_step_kernel<8>, dim3(B), dim3(128), 0, st, h->part, n_slots, s, t - 1, ops));
         prof_end(h, st);
         CK(h, cudaGetLastError());
         h->launches++;

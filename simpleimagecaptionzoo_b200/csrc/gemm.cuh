@@ -563,6 +563,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_launch();  // set-up done: the next kernel of the stream may be scheduled behind this one ...
+    griddep_wait();    // ... and this one touches its operands only once its predecessors have finished
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -735,6 +737,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     cluster_sync_all();  // barrier inits and TMEM allocation of BOTH CTAs are visible before any remote signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_launch();  // set-up done: the next kernel of the stream may be scheduled behind this one ...
+    griddep_wait();    // ... and this one touches its operands only once its predecessors have finished
 
     if (warp == 0) {
         // ===================== TMA producer (each CTA loads its A rows and its half of B) =====================

@@ -273,6 +273,8 @@ __global__ void __launch_bounds__(256) butd_attention_kernel(const T* __restrict
                                                              float* __restrict__ alphas_out, size_t alpha_stride) {
     using C = AttCfg<KR>;
     constexpr int GR = C::GR, NV = C::NV, NP = C::NP, LB = C::LB;
+    griddep_launch();
+    griddep_wait();  // the inputs come from earlier kernels of the stream
     extern __shared__ float sm[];
     float* s_e = sm;                    // [KR][R] scores, then alphas
     float* s_red = s_e + KR * R;        // [2][8 warps][NP]
@@ -420,6 +422,8 @@ __global__ void __launch_bounds__(288, AttStreamCfg<KR, T>::CTAS_PER_SM)
 butd_attention_stream_kernel(const T* __restrict__ enc_ctx, const T* __restrict__ feats, const float* __restrict__ dec_ctx,
                              const float* __restrict__ w_aff, float b_aff, int B, int R, int A, int D, int K,
                              __half* __restrict__ ctx16, int ld16, int lo16, float* __restrict__ alphas_out, size_t alpha_stride) {
+    griddep_launch();
+    griddep_wait();  // the inputs come from earlier kernels of the stream
     using C = AttStreamCfg<KR, T>;
     constexpr int GR = C::GR, NV = C::NV, NP = C::NP, RC3 = C::RC3, STAGES = C::STAGES;
     extern __shared__ uint8_t att_smem_raw[];
@@ -702,6 +706,8 @@ butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __
     }
     fence_proxy_async_smem();  // the zero fill above (generic proxy) is ordered before the bulk copies (async proxy)
     __syncthreads();
+    griddep_launch();
+    griddep_wait();  // dec_ctx (and, on the first step, the projected features) come from earlier kernels of the stream
 
     if (warp == 0) {
         // ===================== producer: ONE contiguous bulk copy per chunk (16 / 8 padded rows) =====================
@@ -904,6 +910,8 @@ butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __
 __global__ void aoa_layernorm_kernel(const float* __restrict__ h, int M, int H, const float* __restrict__ gain,
                                      const float* __restrict__ bias, float eps, __half* __restrict__ q16, int ld16, int lo16,
                                      float* __restrict__ out32 = nullptr) {
+    griddep_launch();
+    griddep_wait();  // the inputs come from earlier kernels of the stream
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -935,6 +943,8 @@ template <int NV4>
 __global__ void __launch_bounds__(256) aoa_layernorm_vec_kernel(const float* __restrict__ h, int M, const float* __restrict__ gain,
                                                                 const float* __restrict__ bias, float eps, __half* __restrict__ q16,
                                                                 int ld16, int lo16, float* __restrict__ out32) {
+    griddep_launch();
+    griddep_wait();  // the inputs come from earlier kernels of the stream
     constexpr int H = 128 * NV4;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -1216,6 +1226,8 @@ __global__ void __launch_bounds__(256) aoa_attention_kernel(const float* __restr
                                                             const float* __restrict__ mask, int R, int H, int nh, int K,
                                                             __half* __restrict__ x16, int ld16, int lo16,
                                                             float* __restrict__ alphas_out, size_t alpha_stride) {
+    griddep_launch();
+    griddep_wait();  // the inputs come from earlier kernels of the stream
     extern __shared__ float sm[];
     float* s_q = sm;               // [KR][H]
     float* s_p = s_q + KR * H;     // [KR][nh][R]
@@ -1385,6 +1397,8 @@ aoa_attention_mma_kernel(const __half* __restrict__ k16, const __half* __restric
     }
     fence_proxy_async_smem();
     __syncthreads();
+    griddep_launch();
+    griddep_wait();  // q16 comes from the preceding projection GEMM
 
     if (warp == 0) {
         if (lane == 0) {  // producer: K chunks then V chunks of every image, one contiguous copy each
@@ -1677,6 +1691,8 @@ __global__ void beam_init_kernel(BeamState s, AdvOps ops, int parent_is_img) {
 template <int KTOP, int KR>
 __global__ void __launch_bounds__(128) beam_step_kernel(const float* __restrict__ part, int n_tiles, BeamState s, int t,
                                                         AdvOps ops) {
+    griddep_launch();
+    griddep_wait();  // the inputs come from earlier kernels of the stream
     constexpr int PS = topk_part_stride(KTOP);
     __shared__ float c_val[MAX_ROWS][MAX_ROWS];
     __shared__ int c_idx[MAX_ROWS][MAX_ROWS];
@@ -1855,6 +1871,8 @@ __global__ void sample_init_kernel(SampleState s, AdvOps ops, int parent_is_img)
 template <int KR>
 __global__ void __launch_bounds__(128) sample_step_kernel(const float* __restrict__ part, int n_tiles, SampleState s, int t,
                                                           AdvOps ops) {
+    griddep_launch();
+    griddep_wait();  // the inputs come from earlier kernels of the stream
     __shared__ int s_tok[MAX_ROWS], s_prow[MAX_ROWS];
     const int img = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

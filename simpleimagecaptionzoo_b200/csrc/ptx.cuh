@@ -83,6 +83,14 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc
                  "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// -- block scheduling, barrier / TMEM set-up, prologue -- while its predecessor in the stream is still draining.
+// griddep_launch() lets the NEXT kernel's blocks be scheduled as soon as every block of this one has passed it;
+// griddep_wait() blocks until all prerequisite grids have completed and their memory is visible: it precedes the first
+// access to anything an earlier kernel of the stream wrote (and is a no-op in a normally launched kernel).
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // 16-byte asynchronous copy global -> shared (per thread), grouped and awaited by the issuing thread.
 __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(gsrc)) : "memory");
