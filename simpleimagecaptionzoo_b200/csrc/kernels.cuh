@@ -1689,7 +1689,7 @@ __global__ void beam_init_kernel(BeamState s, AdvOps ops, int parent_is_img) {
 //   step 1 looks at row 0 only; selected <end> candidates complete (running best, strict '>' = first max) and
 //   shrink the beam; survivors keep their sorted order; states follow their parent.
 template <int KTOP, int KR>
-__global__ void __launch_bounds__(128) beam_step_kernel(const float* __restrict__ part, int n_tiles, BeamState s, int t,
+__global__ void __launch_bounds__(128, KR <= 3 ? 12 : 8) beam_step_kernel(const float* __restrict__ part, int n_tiles, BeamState s, int t,
                                                         AdvOps ops) {
     griddep_launch();
     griddep_wait();  // the inputs come from earlier kernels of the stream
@@ -1697,6 +1697,7 @@ __global__ void __launch_bounds__(128) beam_step_kernel(const float* __restrict_
     __shared__ float c_val[MAX_ROWS][MAX_ROWS];
     __shared__ int c_idx[MAX_ROWS][MAX_ROWS];
     __shared__ int s_parent[MAX_ROWS], s_tok[MAX_ROWS];
+    __shared__ int s_n_new, s_best_src;
     const int img = blockIdx.x;
     const int K = s.K, L = s.T + 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1749,13 +1750,13 @@ __global__ void __launch_bounds__(128) beam_step_kernel(const float* __restrict_
     __syncthreads();
 
     if (threadIdx.x == 0) {
-        // global top-nl over rows x K candidates, ordered by (score desc, flat index asc)
+        // global top-nl over rows x K candidates, ordered by (score desc, flat index asc).  This thread only DECIDES
+        // (survivors, their parents, the best completed hypothesis); the token histories are copied by the whole CTA below.
         int taken[MAX_ROWS];  // how many candidates of each row are consumed (rows are sorted already)
         for (int r = 0; r < K; ++r) taken[r] = 0;
         int n_new = 0;
+        int best_src = -1;  // slot whose history + <end> became the best completed hypothesis in this step
         float best = s.best_score[img];
-        const int* sin = s.seqs_in + static_cast<size_t>(img) * K * L;
-        int* sout = s.seqs_out + static_cast<size_t>(img) * K * L;
         for (int j = 0; j < nl; ++j) {
             float bv = -INFINITY;
             int br = -1;
@@ -1771,16 +1772,9 @@ __global__ void __launch_bounds__(128) beam_step_kernel(const float* __restrict_
             if (word == TOK_END) {
                 if (bv > best) {  // strict: first maximum wins (BUTD_Model.py:307)
                     best = bv;
-                    int* bs = s.best_seq + static_cast<size_t>(img) * L;
-                    for (int i = 0; i < t; ++i) bs[i] = sin[br * L + i];
-                    bs[t] = TOK_END;
-                    for (int i = t + 1; i < L; ++i) bs[i] = TOK_PAD;
-                    s.best_len[img] = t + 1;
-                    if (s.best_pslot) s.best_pslot[img] = br;
+                    best_src = br;
                 }
             } else {
-                for (int i = 0; i < t; ++i) sout[n_new * L + i] = sin[br * L + i];
-                sout[n_new * L + t] = word;
                 s_parent[n_new] = img * K + br;  // absolute parent row
                 s_tok[n_new] = word;
                 s.cum[img * K + n_new] = bv;
@@ -1789,6 +1783,12 @@ __global__ void __launch_bounds__(128) beam_step_kernel(const float* __restrict_
         }
         s.best_score[img] = best;
         s.n_live[img] = n_new;
+        if (best_src >= 0) {
+            s.best_len[img] = t + 1;
+            if (s.best_pslot) s.best_pslot[img] = best_src;
+        }
+        s_n_new = n_new;
+        s_best_src = best_src;
         for (int q = n_new; q < K; ++q) {
             s_parent[q] = img * K;
             s_tok[q] = TOK_PAD;
@@ -1796,6 +1796,21 @@ __global__ void __launch_bounds__(128) beam_step_kernel(const float* __restrict_
         }
     }
     __syncthreads();
+    {  // token histories: survivor q = history of its parent slot + its word; best completed = history + <end> + <pad>...
+        const int* sin = s.seqs_in + static_cast<size_t>(img) * K * L;
+        int* sout = s.seqs_out + static_cast<size_t>(img) * K * L;
+        const int n_new = s_n_new;
+        for (int i = threadIdx.x; i < n_new * L; i += blockDim.x) {
+            const int q = i / L, p = i - q * L;
+            if (p < t) sout[i] = sin[(s_parent[q] - img * K) * L + p];
+            else if (p == t) sout[i] = s_tok[q];
+        }
+        if (s_best_src >= 0) {
+            int* bs = s.best_seq + static_cast<size_t>(img) * L;
+            for (int p = threadIdx.x; p < L; p += blockDim.x)
+                bs[p] = p < t ? sin[s_best_src * L + p] : (p == t ? TOK_END : TOK_PAD);
+        }
+    }
     if (threadIdx.x < K) {
         s.parent[img * K + threadIdx.x] = s_parent[threadIdx.x];
         s.tok[img * K + threadIdx.x] = s_tok[threadIdx.x];
