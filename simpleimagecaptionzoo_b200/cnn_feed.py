@@ -58,12 +58,56 @@ def make_encoder_state_dict(embed_dim: Optional[int] = None, seed: int = 0, resi
     return sd
 
 
+def _fold(conv, bn, dtype, device):
+    """conv + eval-mode BatchNorm -> (weight, bias) of ONE convolution, folded in fp64: w' = w * g / sqrt(var + eps),
+    b' = beta - mean * g / sqrt(var + eps).  Weight in channels-last memory format for the NHWC tensor-core kernels."""
+    torch = _torch()
+    w = conv.weight.detach().double()
+    scale = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+    b = bn.bias.detach().double() - bn.running_mean.detach().double() * scale
+    w = (w * scale[:, None, None, None]).to(device=device, dtype=dtype).contiguous(memory_format=torch.channels_last)
+    return w, b.to(device=device, dtype=dtype), tuple(conv.stride), tuple(conv.padding)
+
+
+class FusedResNetTrunk:
+    """The reference's ``feature_extractor`` (ResNet-101 trunk, eval mode) as 105 fused cuDNN calls instead of ~350
+    kernels: every BatchNorm is folded into its convolution, every conv + bias + ReLU is one ``cudnn_convolution_relu`` and
+    every bottleneck's last conv + bias + residual add + ReLU one ``cudnn_convolution_add_relu`` (cuDNN's fused epilogues:
+    the activation tensor is written once per convolution instead of three times)."""
+
+    def __init__(self, fx, dtype, device):
+        conv1, bn1, _, _, l1, l2, l3, l4 = list(fx.children())
+        self.stem = _fold(conv1, bn1, dtype, device)
+        self.blocks = []
+        for layer in (l1, l2, l3, l4):
+            for blk in layer.children():
+                down = _fold(blk.downsample[0], blk.downsample[1], dtype, device) if blk.downsample is not None else None
+                self.blocks.append((_fold(blk.conv1, blk.bn1, dtype, device), _fold(blk.conv2, blk.bn2, dtype, device),
+                                    _fold(blk.conv3, blk.bn3, dtype, device), down))
+
+    def __call__(self, x):
+        torch = _torch()
+        F = torch.nn.functional
+        one = (1, 1)
+
+        def conv_relu(t, p):
+            return torch.cudnn_convolution_relu(t, p[0], p[1], p[2], p[3], one, 1)
+
+        x = conv_relu(x, self.stem)
+        x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+        for c1, c2, c3, down in self.blocks:
+            identity = x if down is None else F.conv2d(x, down[0], down[1], down[2], down[3])
+            out = conv_relu(conv_relu(x, c1), c2)
+            x = torch.cudnn_convolution_add_relu(out, c3[0], identity, 1.0, c3[1], c3[2], c3[3], one, 1)
+        return x
+
+
 class CnnFeed:
     """``feature_fn`` for :class:`engine.B200Captioner`: ``visual_inputs['img_tensors']`` (B,3,224,224) fp32, host
     (ideally pinned) or device -> the decoder's input as a CUDA fp32 tensor."""
 
     def __init__(self, model_type: str, state_dict: Mapping[str, object], *, enc_img_size: int = 7, device: int = 0,
-                 dtype: str = "fp16", use_graph: bool = True):
+                 dtype: str = "fp16", use_graph: bool = True, fuse: bool = True):
         torch = _torch()
         if not torch.cuda.is_available():
             raise RuntimeError("CnnFeed needs a CUDA device; there is no CPU path")
@@ -79,7 +123,21 @@ class CnnFeed:
         sub = {k[len(prefix):]: (torch.as_tensor(v) if not torch.is_tensor(v) else v) for k, v in state_dict.items()
                if k.startswith(prefix)}
         fx.load_state_dict(sub, strict=True)
-        self.fx = fx.eval().to(self.device, self.dtype).to(memory_format=torch.channels_last)
+        fx = fx.eval()
+        self.trunk = None
+        if fuse:  # folded-BN, fused-epilogue cuDNN calls; checked once against the module forward, else the modules are kept
+            try:
+                trunk = FusedResNetTrunk(fx, self.dtype, self.device)
+                probe = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(0)).to(self.device, self.dtype)
+                probe = probe.contiguous(memory_format=torch.channels_last)
+                with torch.no_grad():
+                    got = trunk(probe).float()
+                    ref = fx.to(self.device)(probe.float())
+                if torch.isfinite(got).all() and ((got - ref).norm() / ref.norm()).item() < 2e-2:
+                    self.trunk = trunk
+            except Exception:  # noqa: BLE001  (a cuDNN build without the fused conv-bias-relu engines)
+                self.trunk = None
+        self.fx = fx.to(self.device, self.dtype).to(memory_format=torch.channels_last)
         for p in self.fx.parameters():
             p.requires_grad_(False)
         self.W = self.b = None
@@ -89,12 +147,14 @@ class CnnFeed:
             self.W = (v * (g / v.norm(dim=1, keepdim=True))).float().to(self.device)
             self.b = torch.as_tensor(state_dict["encoder.img_embedding.bias"]).float().to(self.device)
         self._graphs = {}
-        self.stream = torch.cuda.Stream(self.device)
+        self._turn = {}
+        self.stream = torch.cuda.Stream(self.device)       # capture stream
+        self.copy_stream = torch.cuda.Stream(self.device)  # host -> device copies of the next batch
 
     # ------------------------------------------------------------------ forward
     def _forward(self, x):
         torch = _torch()
-        f = self.fx(x)  # (B, 2048, h, w) channels-last
+        f = self.trunk(x) if self.trunk is not None else self.fx(x)  # (B, 2048, h, w) channels-last
         if self.model_type == "NIC":
             pooled = f.float().mean(dim=(2, 3))  # resnet.avgpool + view (NIC_Model.py:34-35), accumulated in fp32
             return torch.addmm(self.b, pooled, self.W.t())  # img_embedding (:36)
@@ -102,6 +162,23 @@ class CnnFeed:
             f = torch.nn.functional.adaptive_avg_pool2d(f.float(), (self.grid, self.grid))
         # (B, 2048, s, s) -> (B, s*s, 2048): channels-last storage already is that layout, so this is a view + cast
         return f.permute(0, 2, 3, 1).reshape(f.shape[0], -1, f.shape[1]).float().contiguous()
+
+    def _capture(self, key, images):
+        """One replayable instance of the forward for this input shape: static input / output buffers + CUDA graph."""
+        torch = _torch()
+        cur = torch.cuda.current_stream(self.device)
+        static_in = torch.empty(key, dtype=torch.float32, device=self.device)
+        static_in.copy_(images, non_blocking=True)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            for _ in range(2):  # warm-up outside capture (cuDNN algorithm selection, workspace allocation)
+                self._forward(static_in.to(self.dtype).contiguous(memory_format=torch.channels_last))
+        cur.wait_stream(self.stream)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=self.stream):
+            static_out = self._forward(static_in.to(self.dtype).contiguous(memory_format=torch.channels_last))
+        return dict(graph=graph, static_in=static_in, static_out=static_out, free=None)
 
     def __call__(self, visual_inputs):
         torch = _torch()
@@ -114,25 +191,30 @@ class CnnFeed:
             if not self.use_graph:
                 x = images.to(self.device, non_blocking=True).to(self.dtype).contiguous(memory_format=torch.channels_last)
                 return self._forward(x)
-            slot = self._graphs.get(key)
-            if slot is None:
-                static_in = torch.empty(key, dtype=torch.float32, device=self.device)
-                static_in.copy_(images, non_blocking=True)
-                self.stream.wait_stream(cur)
-                with torch.cuda.stream(self.stream):
-                    for _ in range(2):  # warm-up outside capture (cuDNN algorithm selection, workspace allocation)
-                        self._forward(static_in.to(self.dtype).contiguous(memory_format=torch.channels_last))
-                cur.wait_stream(self.stream)
-                torch.cuda.synchronize(self.device)
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, stream=self.stream):
-                    static_out = self._forward(static_in.to(self.dtype).contiguous(memory_format=torch.channels_last))
-                slot = self._graphs[key] = (graph, static_in, static_out)
-            graph, static_in, static_out = slot
-            static_in.copy_(images, non_blocking=True)
-            graph.replay()
+            # two instances per shape, used in turn: the host -> device copy of batch i+1 (copy stream) overlaps the
+            # convolutions of batch i (caller's stream)
+            slots = self._graphs.setdefault(key, [])
+            turn = self._turn.get(key, 0)
+            self._turn[key] = turn + 1
+            if len(slots) < 2:
+                slots.append(self._capture(key, images))
+            slot = slots[turn % len(slots)] if len(slots) == 2 else slots[-1]
+            if images.is_cuda:
+                slot["static_in"].copy_(images, non_blocking=True)
+            else:
+                with torch.cuda.stream(self.copy_stream):
+                    if slot["free"] is not None:
+                        self.copy_stream.wait_event(slot["free"])  # the replay that last read this buffer has finished
+                    slot["static_in"].copy_(images, non_blocking=True)
+                    ready = torch.cuda.Event()
+                    ready.record(self.copy_stream)
+                cur.wait_event(ready)
+            slot["graph"].replay()
             # a pipelined caller stages batch i+1 before batch i is decoded: hand out a copy, not the graph's own buffer
-            return static_out.clone()
+            out = slot["static_out"].clone()
+            slot["free"] = torch.cuda.Event()
+            slot["free"].record(cur)
+            return out
 
 
 def attach(captioner, state_dict, **kw):

@@ -90,3 +90,16 @@ def test_aoa_spatial_from_images_runs_the_native_refiner():
     got = cap.decoder.refined_features().cpu().numpy()
     ref = orc.aoa_project_refine({k: v for k, v in sd.items() if isinstance(v, np.ndarray)}, grid.cpu().numpy(), None, num_heads=8)
     assert np.abs(got - ref).max() < 6e-2
+
+
+def test_fused_trunk_is_used_and_matches_modules():
+    """The folded-BN / fused-epilogue trunk is what runs (the constructor's self-check accepted it) and agrees with the
+    plain module forward of the same weights."""
+    from simpleimagecaptionzoo_b200 import cnn_feed
+    sd = cnn_feed.make_encoder_state_dict(embed_dim=512, seed=2)
+    images = torch.randn(4, 3, 224, 224, generator=torch.Generator().manual_seed(1))
+    fused = cnn_feed.CnnFeed("NIC", sd)
+    plain = cnn_feed.CnnFeed("NIC", sd, fuse=False)
+    assert fused.trunk is not None and plain.trunk is None
+    a, b = fused({"img_tensors": images}), plain({"img_tensors": images})
+    assert ((a - b).norm() / b.norm()).item() < REL_L2_BOUND
