@@ -317,9 +317,8 @@ def run_gpu_arm(args, w):
         """n_steps batches through the pipelined captioner API: every step's features start in pinned HOST memory and
         every step's captions end in host memory (H2D of step i+1 overlaps the decode of step i)."""
         last = None
-        if scst:  # the rollout API has no streaming form: H2D, both rollouts and the read-back run back to back
-            for _ in range(n_steps):
-                vi = {key: host_feats}
+        if scst:  # the SCST step forward: prefetched H2D, greedy + multinomial rollouts, CIDEr-D reward, read-back
+            for vi in cap.prefetch_to_device(({key: host_feats} for _ in range(n_steps))):
                 greedy = cap.sampler(vi, max_len=T)
                 seq, _ = cap.sampler_rl(vi, max_len=T, n_per_image=K)
                 rew = reward(seq, greedy, gts, img_ids, n_per_image=K)

@@ -194,6 +194,55 @@ class B200Captioner:
             e.synchronize()
             yield h.numpy()
 
+    def prefetch_to_device(self, batches):
+        """Generator over ``visual_inputs`` dicts whose host tensors (ideally pinned) are replaced by device tensors, the copy
+        of batch i+1 running on a copy stream while the caller works on batch i -- what an SCST training loop needs around
+        its two rollouts (``Engine.SCST_training_epoch`` moves every batch synchronously, Engine.py:254-255).  The device
+        buffers are two alternating slots: use a batch before asking for the one after the next."""
+        torch = _torch()
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._slots = [dict(buf=None, mask=None, free=None, ready=None) for _ in range(2)]
+        copy = self._copy_stream
+        bufs, free = [dict(), dict()], [None, None]
+
+        def stage(i, vi):
+            out = dict(vi)
+            with torch.cuda.stream(copy):
+                if free[i % 2] is not None:
+                    copy.wait_event(free[i % 2])
+                for k, v in vi.items():
+                    if isinstance(v, np.ndarray) and v.dtype.kind == "f":
+                        v = torch.from_numpy(v)
+                    if torch.is_tensor(v) and not v.is_cuda:
+                        b = bufs[i % 2].get(k)
+                        if b is None or b.shape != v.shape or b.dtype != v.dtype:
+                            b = bufs[i % 2][k] = torch.empty(v.shape, dtype=v.dtype, device=self.device)
+                        b.copy_(v, non_blocking=True)
+                        out[k] = b
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            return out, ev
+
+        it = iter(batches)
+        try:
+            nxt = stage(0, next(it))
+        except StopIteration:
+            return
+        i = 0
+        while nxt is not None:
+            cur, ev = nxt
+            try:
+                nxt = stage(i + 1, next(it))
+            except StopIteration:
+                nxt = None
+            main.wait_event(ev)
+            yield cur
+            free[i % 2] = torch.cuda.Event()
+            free[i % 2].record(main)  # everything the caller enqueued on this batch precedes the slot's next overwrite
+            i += 1
+
     def sampler(self, visual_inputs, max_len: int = 20):
         feats, mask = self._features(visual_inputs)
         self._prepare(feats, mask)

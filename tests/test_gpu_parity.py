@@ -496,3 +496,20 @@ def test_fp16_bottom_up_features_with_mask():
     tb, _, _ = dec.beam_search(3, 20)
     assert torch.equal(a, b) and torch.equal(ta, tb)
     dec.close()
+
+
+def test_prefetch_to_device_pipeline():
+    """B200Captioner.prefetch_to_device hands out device copies of host batches in order, two alternating slots."""
+    from simpleimagecaptionzoo_b200 import engine, synth
+    dims = synth.TINY_DIMS["BUTD"]
+    sd = synth.make_state_dict("BUTD", seed=0, **dims)
+    settings = dict(model_type="BUTDDetection", embed_dim=dims["embed_dim"], hidden_dim=dims["hidden_dim"], atten_dim=dims["atten_dim"])
+    cap = engine.B200Captioner("BUTDDetection", settings, dims["vocab_size"], sd, max_batch=8, max_regions=6, max_rows=3,
+                               enc_dim=dims["enc_dim"])
+    host = [torch.from_numpy(synth.make_region_feats(8, 6, dims["enc_dim"], s)).pin_memory() for s in range(5)]
+    direct = [cap.sampler({"bu_feats": h}, max_len=10).cpu() for h in host]
+    got = []
+    for vi in cap.prefetch_to_device({"bu_feats": h, "bu_masks": None} for h in host):
+        assert vi["bu_feats"].is_cuda
+        got.append(cap.sampler(vi, max_len=10).cpu())
+    assert len(got) == 5 and all(torch.equal(a, b) for a, b in zip(got, direct))
