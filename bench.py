@@ -472,7 +472,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="images per GPU")
     ap.add_argument("--max-seq", type=int, default=20)
     ap.add_argument("--math", default="f16", choices=["f16", "f16x3"])
-    ap.add_argument("--cpu-images", type=int, default=8)
+    ap.add_argument("--cpu-images", type=int, default=64, help="images of the same batch the CPU port decodes (about 10 s)")
     ap.add_argument("--ref-images", type=int, default=4, help="images per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -18,7 +18,7 @@ def test_build_produces_library_with_all_symbols():
     from simpleimagecaptionzoo_b200 import capdec
     lib = ctypes.CDLL(capdec.LIB_PATH)
     header = open(os.path.join(ROOT, "include", "capdec.h")).read()
-    declared = sorted(set(re.findall(r"\b(capdec_[a-z_]+)\s*\(", header)))
+    declared = sorted(set(re.findall(r"\b(capdec_[a-z0-9_]+)\s*\(", header)))
     assert declared, "no declarations found in include/capdec.h"
     for sym in declared:
         assert hasattr(lib, sym), f"libcapdec.so does not export {sym}"
@@ -127,3 +127,15 @@ def test_bottom_up_collate_matches_reference_shapes():
     assert out["bu_feats"].shape == (3, 36, 8)
     assert out["bu_masks"].sum(1).tolist() == [10, 36, 20]
     assert float(out["bu_feats"][0, 10:].abs().sum()) == 0.0
+
+
+def test_side_modules_fail_loudly_without_gpu():
+    """The reward scorer and the CNN feed have no CPU path either."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a GPU")
+    from simpleimagecaptionzoo_b200 import cnn_feed, scst
+    with pytest.raises(RuntimeError, match="no CPU"):
+        scst.CiderDReward({"a": 4}, {("a",): 1.0}, 10)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        cnn_feed.CnnFeed("NIC", {})
