@@ -129,7 +129,7 @@ struct capdec_handle {
         const float *ln_gain = nullptr, *ln_bias = nullptr;
     };
     std::vector<RefineLayer> refine;
-    bool refiner_ready = false;
+    bool refiner_ready = false, refiner_allocated = false;
     Act16 W_proj, bu16, XR, qkv16;  // projection weight [H, D]; fp16 bottom-up features; [att | LN(x)] operand; Q|K|V (fp16 mode)
     float *b_proj = nullptr, *qkv32 = nullptr, *xres = nullptr, *refined = nullptr;
     const float *rfinal_gain = nullptr, *rfinal_bias = nullptr;
@@ -538,7 +538,8 @@ int finalize_refiner(capdec_handle* h, cudaStream_t st) {
     const int H = h->H, D = h->D;
     if (D <= 0 || D % 64) return fail(h, CAPDEC_ERR_INVALID, "AoA refiner needs enc_dim (bottom-up feature width) as a multiple of 64");
     const Raw *w, *b, *gn, *bs;
-    const bool first = h->refine.empty();
+    const bool first = !h->refiner_allocated;  // a failed first attempt (missing entry) frees nothing and is not repeated
+    if (first && !h->refine.empty()) return fail(h, CAPDEC_ERR_STATE, "an earlier finalize of the AoA refiner failed; create a new handle");
     if (first) {
         CKS(h, alloc_act(h, &h->W_proj, H, D));
         CKS(h, dalloc(h, &h->b_proj, H));
@@ -592,6 +593,7 @@ int finalize_refiner(capdec_handle* h, cudaStream_t st) {
         else CKS(h, alloc_act(h, &h->qkv16, static_cast<int>(BR), 3 * H));
         CKS(h, dalloc(h, &h->xres, BR * H));
         CKS(h, dalloc(h, &h->refined, BR * H));
+        h->refiner_allocated = true;
     }
     h->refiner_ready = true;
     return CAPDEC_OK;
@@ -1530,9 +1532,10 @@ static int prepare_impl(capdec_handle* h, const float* feats, const float* mask,
                 CKS(h, launch_gemm(h, EPI_STORE, 1, ma, h->mean16.lo, mb, h->W_aux3.lo, batch, 4 * H, D, e, st));
             }
         } else {
+            if (feats16 || !feats)
+                return fail(h, CAPDEC_ERR_INVALID, "prepare_f16: AoA refined features are taken in fp32 (fp16 applies to bu_feats)");
             cvt_f16_kernel<<<grid_for(BR * H / 4), 256, 0, st>>>(feats, BR, H, h->feats16.p, h->feats16.ld, h->feats16.lo, 0);
             CK(h, cudaGetLastError());
-            if (feats16) return fail(h, CAPDEC_ERR_INVALID, "prepare_f16: AoA refined features are taken in fp32 (fp16 applies to bu_feats)");
             region_mean_kernel<float><<<batch, 256, 0, st>>>(feats, H, mask, regions, H, h->mean32, nullptr, 0, 0);
             CK(h, cudaGetLastError());
             h->launches += 2;

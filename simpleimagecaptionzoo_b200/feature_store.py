@@ -6,7 +6,7 @@ them one by one (Datasets.py:138-145); ``*_Eng.modify_visual_inputs`` then pads 
 device (BUTD_Engine.py:36-45).  At >10^5 captions/s that loader is the wall, and the fp32 host->device copy (453 MB per
 1536 images) is what bounds this repo's end-to-end number.  A shard here is ONE flat file:
 
-    [ 4096-byte JSON header | image_ids int64[N] | lengths int32[N] | bboxes fp32[N,R,4] (optional) | feats fp16[N,R,D] ]
+    [ 4096-byte JSON header | feats fp16[N,R,D] | image_ids int64[N] | lengths int32[N] | bboxes fp32[N,R,4] (optional) ]
 
 memory-mapped, features stored as the fp16 values the decoder's tensor-core operands use anyway, rows zero-padded to R
 regions with the true count in ``lengths`` (adaptive bottom-up features -> ``bu_masks``).  ``batches()`` fills a small ring
@@ -33,11 +33,16 @@ def _align(n: int, a: int = 64) -> int:
 
 
 class FeatureShardWriter:
-    """``with FeatureShardWriter(path, regions=36, dim=2048) as w: w.append(image_id, feat[, bbox])``."""
+    """``with FeatureShardWriter(path, regions=36, dim=2048) as w: w.append(image_id, feat[, bbox])``.  Feature rows are
+    streamed to the file as they arrive (a COCO-sized shard is ~18 GB); the small per-image index follows the feature block
+    when the writer is closed and the header records where everything is."""
 
     def __init__(self, path: str, regions: int, dim: int = 2048, with_bboxes: bool = False):
         self.path, self.R, self.D, self.with_bboxes = path, regions, dim, with_bboxes
-        self._ids, self._lens, self._feats, self._boxes = [], [], [], []
+        self._ids, self._lens, self._boxes = [], [], []
+        self._f = open(path, "wb")
+        self._f.write(b" " * HEADER_BYTES)
+        self._closed = False
 
     def append(self, image_id: int, feat: np.ndarray, bbox: Optional[np.ndarray] = None):
         feat = np.asarray(feat)
@@ -49,9 +54,9 @@ class FeatureShardWriter:
             row[:n] = feat  # fp32 -> fp16, round to nearest even: the rounding the decoder applies to its operands
         if not np.isfinite(row).all():
             raise ValueError(f"feature of image {image_id} leaves the fp16 range")
+        self._f.write(row.tobytes())
         self._ids.append(int(image_id))
         self._lens.append(n)
-        self._feats.append(row)
         if self.with_bboxes:
             b = np.zeros((self.R, 4), np.float32)
             if bbox is not None:
@@ -59,27 +64,28 @@ class FeatureShardWriter:
             self._boxes.append(b)
 
     def close(self):
+        if self._closed:
+            return
+        self._closed = True
         N = len(self._ids)
-        off_ids = HEADER_BYTES
+        off_feats = HEADER_BYTES
+        off_ids = _align(off_feats + 2 * N * self.R * self.D)
         off_lens = _align(off_ids + 8 * N)
         off_box = _align(off_lens + 4 * N)
-        off_feats = _align(off_box + (16 * N * self.R if self.with_bboxes else 0))
         header = dict(magic=MAGIC, version=1, n=N, regions=self.R, dim=self.D, dtype="float16", with_bboxes=self.with_bboxes,
                       off_ids=off_ids, off_lens=off_lens, off_bboxes=off_box, off_feats=off_feats)
         blob = json.dumps(header).encode()
         assert len(blob) < HEADER_BYTES
-        with open(self.path, "wb") as f:
-            f.write(blob.ljust(HEADER_BYTES, b" "))
-            f.seek(off_ids)
-            f.write(np.asarray(self._ids, np.int64).tobytes())
-            f.seek(off_lens)
-            f.write(np.asarray(self._lens, np.int32).tobytes())
-            if self.with_bboxes:
-                f.seek(off_box)
-                f.write(np.stack(self._boxes).tobytes() if N else b"")
-            f.seek(off_feats)
-            for row in self._feats:
-                f.write(row.tobytes())
+        f = self._f
+        f.seek(off_ids)
+        f.write(np.asarray(self._ids, np.int64).tobytes())
+        f.seek(off_lens)
+        f.write(np.asarray(self._lens, np.int32).tobytes())
+        f.seek(off_box)
+        f.write(np.stack(self._boxes).tobytes() if (self.with_bboxes and N) else b"\0")
+        f.seek(0)
+        f.write(blob.ljust(HEADER_BYTES, b" "))
+        f.close()
 
     def __enter__(self):
         return self
@@ -87,6 +93,8 @@ class FeatureShardWriter:
     def __exit__(self, *exc):
         if exc[0] is None:
             self.close()
+        else:
+            self._f.close()
 
 
 def convert_npz_directory(npz_paths: Iterable[Tuple[int, str]], shard_path: str, regions: int, dim: int = 2048):
@@ -112,7 +120,7 @@ class FeatureShard:
         self.bboxes = (np.memmap(path, np.float32, "r", header["off_bboxes"], (self.N, self.R, 4))
                        if header["with_bboxes"] else None)
         self.feats = np.memmap(path, np.float16, "r", header["off_feats"], (self.N, self.R, self.D))
-        expect = header["off_feats"] + 2 * self.N * self.R * self.D
+        expect = max(header["off_feats"] + 2 * self.N * self.R * self.D, header["off_lens"] + 4 * self.N)
         if os.path.getsize(path) < expect:
             raise ValueError(f"{path} is truncated: {os.path.getsize(path)} < {expect} bytes")
 

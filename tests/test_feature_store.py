@@ -130,3 +130,18 @@ def test_shard_streams_through_the_captioner(tmp_path):
     assert np.array_equal(np.concatenate(order), np.arange(N)) and got.shape == (N, 21)
     ref = cap.beam_search_sampler({"bu_feats": torch.from_numpy(feats[:16]).half().float()}, beam_size=3).cpu().numpy()
     assert np.array_equal(got[:16], ref)
+
+
+@pytest.mark.gpu
+def test_fp16_refined_features_are_rejected_cleanly():
+    """AoA without the refiner entries: fp16 input has no meaning (the decoder takes refined features in fp32)."""
+    torch = pytest.importorskip("torch")
+    from simpleimagecaptionzoo_b200 import capdec
+    dims = synth.TINY_DIMS["AOA"]
+    dec = capdec.CaptionDecoder("AOA", synth.make_state_dict("AOA", seed=0, **dims), max_batch=4, max_regions=6, **dims)
+    with pytest.raises(RuntimeError, match="fp32"):
+        dec.prepare(torch.zeros(4, 6, dims["hidden_dim"], dtype=torch.float16).cuda())
+    dec.prepare(torch.zeros(4, 6, dims["hidden_dim"]).cuda())  # the handle is still usable
+    tok, _, _ = dec.beam_search(3, 5)
+    assert tok.shape == (4, 6)
+    dec.close()
