@@ -260,7 +260,7 @@ def run_gpu_arm(args, w):
     if not raw_bu:  # CNN encoder (or a synthetic stand-in for the refined features): the decoder's input is the input
         feature_fn = lambda vi: vi["feats"]  # noqa: E731
     cap = engine.B200Captioner(w["model_type"], settings, dims["vocab_size"], sd, feature_fn=feature_fn, max_batch=B,
-                               max_regions=max(R, 1), max_rows=K, max_seq=T, math=args.math, device=local,
+                               max_regions=max(R, 1), max_rows=K + 1 if w.get("scst") else K, max_seq=T, math=args.math, device=local,
                                enc_dim=dims.get("enc_dim", 2048), num_heads=dims.get("num_heads", 8))
     dec = cap.decoder
     key = "bu_feats" if raw_bu else "feats"
@@ -304,8 +304,7 @@ def run_gpu_arm(args, w):
 
         def step_device():  # noqa: F811
             dec.prepare(dev_feats)
-            greedy, _ = dec.sample(capdec.SAMPLE_GREEDY, 1, 0, T)
-            tok, _ = dec.sample(capdec.SAMPLE_MULTINOMIAL, K, _rollout.calls, T)
+            tok, _, greedy = dec.scst_rollout(K, _rollout.calls, T)  # both rollouts of the step in one pass
             _rollout.calls += 1
             step_device.rewards = reward(tok, greedy, gts, img_ids, n_per_image=K)
             tok = tok.view(B, K * T)
@@ -319,8 +318,7 @@ def run_gpu_arm(args, w):
         last = None
         if scst:  # the SCST step forward: prefetched H2D, greedy + multinomial rollouts, CIDEr-D reward, read-back
             for vi in cap.prefetch_to_device(({key: host_feats} for _ in range(n_steps))):
-                greedy = cap.sampler(vi, max_len=T)
-                seq, _ = cap.sampler_rl(vi, max_len=T, n_per_image=K)
+                greedy, seq, _ = cap.scst_rollouts(vi, max_len=T, n_per_image=K)
                 rew = reward(seq, greedy, gts, img_ids, n_per_image=K)
                 last = seq.view(B, K * T).to(torch.int32).cpu().numpy()
                 rew[:, 0].cpu()

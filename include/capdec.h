@@ -140,6 +140,15 @@ int capdec_beam_search(capdec_handle* h, int32_t beam, int32_t max_seq, int32_t*
 int capdec_sample(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t seed, int32_t max_seq, int32_t* tokens,
                   float* logprobs, float* alphas, void* stream);
 
+/* The two rollouts of an SCST step (Engine.SCST_training_epoch, Engine.py:258-262: model.sampler then model.sampler_rl on
+ * the same batch) in ONE pass over the prepared batch: n_per_image multinomial rows + one greedy row per image share every
+ * GEMM / attention launch (the image's features are read once per step for all of them).  Row for row the outputs equal
+ * capdec_sample(MULTINOMIAL, n_per_image, seed) and capdec_sample(GREEDY, 1): the sampled rows keep their noise streams.
+ *   sample_tokens [B*n_per_image, max_seq] int32, sample_logprobs [B*n_per_image, max_seq] fp32 (may be NULL),
+ *   greedy_tokens [B, max_seq] int32.  Needs n_per_image + 1 <= cfg.max_rows. */
+int capdec_scst_rollout(capdec_handle* h, int32_t n_per_image, uint64_t seed, int32_t max_seq, int32_t* sample_tokens,
+                        float* sample_logprobs, int32_t* greedy_tokens, void* stream);
+
 /* Teacher-forced scoring of given word sequences for the prepared batch: what the reference's decoder ``forward`` computes
  * for given captions (BUTD_Model.py:97-151, NIC_Model.py:58-98, AoA_Model.py:229-293) followed by log_softmax + gather --
  * the ``seqLogprobs`` of an arbitrary rollout (Utils.py:290-317 RewardCriterion's input), forward values only.

@@ -24,7 +24,7 @@ SYMBOLS = (
     "capdec_abi_version", "capdec_create", "capdec_destroy", "capdec_last_error", "capdec_load_weight",
     "capdec_finalize_weights", "capdec_prepare", "capdec_beam_search", "capdec_sample", "capdec_launch_count",
     "capdec_test_gemm", "capdec_profile", "capdec_profile_read", "capdec_test_gemm_time",
-    "capdec_prepare_bottom_up", "capdec_get_refined", "capdec_score", "capdec_prepare_f16",
+    "capdec_prepare_bottom_up", "capdec_get_refined", "capdec_score", "capdec_prepare_f16", "capdec_scst_rollout",
     "capdec_cider_create", "capdec_cider_destroy", "capdec_cider_last_error", "capdec_cider_ngram_key", "capdec_cider_set_df",
     "capdec_cider_reward",
 )
@@ -66,6 +66,7 @@ def load_library(path: str = LIB_PATH) -> ctypes.CDLL:
     lib.capdec_beam_search.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
     lib.capdec_sample.argtypes = [vp, i32, i32, ctypes.c_uint64, i32, vp, vp, vp, vp]
     lib.capdec_score.argtypes = [vp, vp, i32, i32, vp, vp]
+    lib.capdec_scst_rollout.argtypes = [vp, i32, ctypes.c_uint64, i32, vp, vp, vp, vp]
     lib.capdec_cider_create.argtypes = [i32, ctypes.POINTER(vp)]
     lib.capdec_cider_destroy.argtypes = [vp]
     lib.capdec_cider_destroy.restype = None
@@ -287,6 +288,21 @@ class CaptionDecoder:
                                                     self.stream.cuda_stream), "capdec_beam_search")
             torch.cuda.current_stream(self.device).wait_stream(self.stream)
         return (tokens, scores, lengths, alphas) if return_alphas else (tokens, scores, lengths)
+
+    def scst_rollout(self, n_per_image: int = 1, seed: int = 0, max_seq: int = 20):
+        """Both rollouts of an SCST step in one pass -> (sample tokens [B*n,T] int32, sample logprobs [B*n,T] fp32, greedy
+        tokens [B,T] int32); row for row what ``sample(MULTINOMIAL, n, seed)`` and ``sample(GREEDY, 1)`` return."""
+        torch = _torch()
+        M = self.B * n_per_image
+        tokens = torch.empty((M, max_seq), dtype=torch.int32, device=self.device)
+        logprobs = torch.empty((M, max_seq), dtype=torch.float32, device=self.device)
+        greedy = torch.empty((self.B, max_seq), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            self._check(self.lib.capdec_scst_rollout(self._h, n_per_image, seed, max_seq, tokens.data_ptr(), logprobs.data_ptr(),
+                                                     greedy.data_ptr(), self.stream.cuda_stream), "capdec_scst_rollout")
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        return tokens, logprobs, greedy
 
     def score(self, tokens, n_per_image: int = 1):
         """Teacher-forced log-probs of given words: tokens [B*n, T] int (no <sta>, the layout ``sample`` returns) ->

@@ -724,6 +724,7 @@ struct StepCtx {
     int ktop = 4;
     uint32_t seed = 0;
     int use_noise = 0;
+    int scst_n = 0;  // > 0: rows = scst_n sampled + 1 greedy rollout per image
     bool first_from_c0 = false;
     const int* forced = nullptr;  // teacher-forced words [row * forced_ld + step] (capdec_score) or null
     int forced_ld = 0;
@@ -742,6 +743,7 @@ int run_logits(capdec_handle* h, const Act16& a, const StepCtx& c, cudaStream_t 
     e.seed = c.seed;
     e.step = c.t - 1;
     e.use_noise = c.use_noise;
+    e.scst_n = c.scst_n;
     e.forced = c.forced;
     e.forced_ld = c.forced_ld;
     return launch_gemm(h, c.logits_epi, c.ktop, ma, a.lo, mb, h->W_pred.lo, c.M, h->V, h->H, e, st);
@@ -1678,7 +1680,7 @@ static int enqueue_beam_search(capdec_handle* h, int32_t beam, int32_t max_seq, 
 }
 
 static int sample_impl(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t seed, int32_t max_seq, int32_t* tokens,
-                       float* logprobs, float* alphas, const int32_t* forced, cudaStream_t st);
+                       float* logprobs, float* alphas, const int32_t* forced, cudaStream_t st, int32_t* greedy_tokens = nullptr);
 
 int capdec_sample(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t seed, int32_t max_seq, int32_t* tokens,
                   float* logprobs, float* alphas, void* stream) {
@@ -1692,6 +1694,17 @@ int capdec_sample(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t 
     return sample_impl(h, mode, n_per_image, seed, max_seq, tokens, logprobs, alphas, nullptr, static_cast<cudaStream_t>(stream));
 }
 
+int capdec_scst_rollout(capdec_handle* h, int32_t n_per_image, uint64_t seed, int32_t max_seq, int32_t* sample_tokens,
+                        float* sample_logprobs, int32_t* greedy_tokens, void* stream) {
+    if (!h) return CAPDEC_ERR_INVALID;
+    if (!h->prepared) return fail(h, CAPDEC_ERR_STATE, "capdec_scst_rollout before capdec_prepare");
+    if (n_per_image <= 0 || n_per_image + 1 > h->Kmax || max_seq <= 0 || max_seq > h->Tmax || !sample_tokens || !greedy_tokens)
+        return fail(h, CAPDEC_ERR_INVALID, "scst_rollout: n_per_image + 1 must be <= max_rows; null outputs or max_seq out of range");
+    CK(h, cudaSetDevice(h->cfg.device));
+    return sample_impl(h, CAPDEC_SAMPLE_MULTINOMIAL, n_per_image + 1, seed, max_seq, sample_tokens, sample_logprobs, nullptr, nullptr,
+                       static_cast<cudaStream_t>(stream), greedy_tokens);
+}
+
 int capdec_score(capdec_handle* h, const int32_t* tokens, int32_t n_per_image, int32_t max_seq, float* logprobs, void* stream) {
     if (!h) return CAPDEC_ERR_INVALID;
     if (!h->prepared) return fail(h, CAPDEC_ERR_STATE, "capdec_score before capdec_prepare");
@@ -1702,17 +1715,22 @@ int capdec_score(capdec_handle* h, const int32_t* tokens, int32_t n_per_image, i
                        static_cast<cudaStream_t>(stream));
 }
 
+// greedy_tokens != null: the SCST pair of rollouts in one pass -- n_per_image rows per image of which the LAST is the greedy
+// rollout (written to greedy_tokens [B, T]); tokens / logprobs then hold the n_per_image - 1 sampled rows per image.
 static int sample_impl(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t seed, int32_t max_seq, int32_t* tokens,
-                       float* logprobs, float* alphas, const int32_t* forced, cudaStream_t st) {
+                       float* logprobs, float* alphas, const int32_t* forced, cudaStream_t st, int32_t* greedy_tokens) {
     const int B = h->B, n = n_per_image, M = B * n;
+    const int M_out = greedy_tokens ? B * (n - 1) : M;
     CKS(h, reset_state(h, M, st));
-    if (tokens) CK(h, cudaMemsetAsync(tokens, 0, static_cast<size_t>(M) * max_seq * sizeof(int32_t), st));
-    if (logprobs) CK(h, cudaMemsetAsync(logprobs, 0, static_cast<size_t>(M) * max_seq * sizeof(float), st));
+    if (tokens) CK(h, cudaMemsetAsync(tokens, 0, static_cast<size_t>(M_out) * max_seq * sizeof(int32_t), st));
+    if (logprobs) CK(h, cudaMemsetAsync(logprobs, 0, static_cast<size_t>(M_out) * max_seq * sizeof(float), st));
     SampleState s{};
     s.B = B, s.n = n, s.V = h->V, s.T = max_seq;
     s.tok = h->tok, s.unfinished = h->unfinished, s.live_count = h->live_count, s.parent = h->parent;
     s.tokens = tokens, s.logprobs = logprobs;
     s.multinomial = mode == CAPDEC_SAMPLE_MULTINOMIAL;
+    s.scst = greedy_tokens != nullptr;
+    s.greedy_tokens = greedy_tokens;
     const bool nic = h->cfg.arch == CAPDEC_ARCH_NIC;
     if (n <= 1) sample_init_kernel<1><<<B, 128, 0, st>>>(s, adv_ops(h, true), nic ? 1 : 0);
     else if (n <= 3) sample_init_kernel<3><<<B, 128, 0, st>>>(s, adv_ops(h, true), nic ? 1 : 0);
@@ -1725,6 +1743,7 @@ static int sample_impl(capdec_handle* h, int32_t mode, int32_t n_per_image, uint
     c.M = M, c.K = n, c.logits_epi = EPI_SAMPLE, c.ktop = 1;
     c.seed = static_cast<uint32_t>(seed & 0xFFFFFFFFu);
     c.use_noise = s.multinomial;
+    c.scst_n = greedy_tokens ? n - 1 : 0;
     c.forced = forced;
     c.forced_ld = max_seq;
     const AdvOps ops = adv_ops(h, false);

@@ -62,6 +62,8 @@ struct EpiParams {
     uint32_t seed;          // SAMPLE: counter-based Gumbel noise (0 noise when use_noise == 0)
     int step;
     int use_noise;
+    int scst_n;             // SAMPLE, > 0: rows come in groups of scst_n sampled rollouts + ONE greedy rollout per image (the
+                            //   two rollouts of an SCST step in one pass); sample rows keep the noise stream of row img*scst_n+j
     const int* forced;      // SAMPLE: teacher forcing -- the word of row r at this step is forced[r * forced_ld + step]
     int forced_ld;          //   (capdec_score); null = draw / arg-max
 };
@@ -116,14 +118,26 @@ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
 // logit GEMM's epilogue).  lg2.approx has ~2^-22 ABSOLUTE error, which is useless for -log(u) when u -> 1 (exactly the
 // draws that win the arg-max), so that range uses the series of -log(1 - t), t = 1 - u (exact by Sterbenz):
 // |g - exact| <= ~1e-5 everywhere, far below the 1e-3 tie tolerance of the sampling parity tests.
-__device__ __forceinline__ float gumbel_from_hash(uint32_t row_step_hash, uint32_t v) {
-    const uint32_t x = fmix32(row_step_hash ^ (v * 0xC2B2AE3Du));
+__device__ __forceinline__ uint32_t gumbel_bits(uint32_t row_step_hash, uint32_t v) {
+    return fmix32(row_step_hash ^ (v * 0xC2B2AE3Du));
+}
+__device__ __forceinline__ float gumbel_from_bits(uint32_t x) {
     const float u = (static_cast<float>(x >> 8) + 0.5f) * 5.9604644775390625e-08f;  // 2^-24
     const float t = 1.0f - u;
     const float e_series = t * fmaf(t, fmaf(t, fmaf(t, 0.25f, 0.33333334f), 0.5f), 1.0f);  // -log(1-t), t < 2^-6: rel err < 1e-8
     const float e_lg2 = -LN2 * __log2f(u);
     const float e = t < 0.015625f ? e_series : e_lg2;                                       // E = -log(u) ~ Exp(1)
     return -LN2 * __log2f(e);
+}
+__device__ __forceinline__ float gumbel_from_hash(uint32_t row_step_hash, uint32_t v) {
+    return gumbel_from_bits(gumbel_bits(row_step_hash, v));
+}
+// Smallest 24-bit uniform (x >> 8) whose noise can exceed tau:  g > tau  <=>  u > exp(-exp(-tau)).  Conservative by two
+// units (and by the caller's margin on tau), so that no possible winner is ever skipped; tau = -inf gives 0 (all pass).
+__device__ __forceinline__ uint32_t gumbel_pass_threshold(float tau) {
+    const float U = __expf(-__expf(-tau));
+    const int thr = static_cast<int>(U * 16777216.0f) - 2;
+    return thr > 0 ? static_cast<uint32_t>(thr) : 0u;
 }
 __device__ __forceinline__ uint32_t gumbel_row_step_hash(uint32_t seed, uint32_t row, uint32_t t) {
     uint32_t h = fmix32(seed ^ (row * 0x9E3779B1u));
@@ -429,9 +443,17 @@ struct DrawState {
     float m, s, best, best_raw;
     int best_i, forced;
     uint32_t rs;
+    bool noisy;
     __device__ __forceinline__ void init(int row, const GemmParams& p) {
         m = -INFINITY, s = 0.f, best = -INFINITY, best_raw = 0.f, best_i = 0x7FFFFFFF;
-        rs = gumbel_row_step_hash(p.epi.seed, static_cast<uint32_t>(row), static_cast<uint32_t>(p.epi.step));
+        noisy = p.epi.use_noise != 0;
+        int noise_row = row;
+        if (p.epi.scst_n > 0) {
+            const int img = row / (p.epi.scst_n + 1), j = row - img * (p.epi.scst_n + 1);
+            noisy = noisy && j < p.epi.scst_n;  // the last row of an image's group is its greedy rollout
+            noise_row = img * p.epi.scst_n + j;
+        }
+        rs = gumbel_row_step_hash(p.epi.seed, static_cast<uint32_t>(noise_row), static_cast<uint32_t>(p.epi.step));
         forced = (p.epi.forced && row < p.M) ? __ldg(p.epi.forced + static_cast<size_t>(row) * p.epi.forced_ld + p.epi.step) : -1;
     }
     __device__ __forceinline__ void tile(uint32_t taddr, int n_base, int c0, int c1, const GemmParams& p) {
@@ -449,11 +471,18 @@ struct DrawState {
                     for (int i = 0; i < 32; ++i)
                         if (i == f) best = 3.0e38f, best_i = forced, best_raw = v[i];
                 }
-            } else if (p.epi.use_noise) {
-#pragma unroll 4
+            } else if (noisy) {
+                // A column wins only if logit + noise > best, i.e. only with noise above best - (largest logit of the
+                // chunk).  Whether a column's noise can exceed that bound is decided on the 24 hash bits alone (an integer
+                // compare); the two logarithms are evaluated for the few columns that pass (~1e-3 of a uniform vocabulary
+                // once the running best has settled, none of a trained model's low-probability words).  Exact: the columns
+                // skipped could not have won, the others are evaluated as before and in the same order.
+                const uint32_t thr = gumbel_pass_threshold(best - cmax - 1e-3f);
+#pragma unroll 8
                 for (int i = 0; i < 32; ++i) {
-                    if (n0 + i < p.N) {
-                        const float pv = v[i] + gumbel_from_hash(rs, static_cast<uint32_t>(n0 + i));
+                    const uint32_t x = gumbel_bits(rs, static_cast<uint32_t>(n0 + i));
+                    if ((x >> 8) >= thr && n0 + i < p.N) {
+                        const float pv = v[i] + gumbel_from_bits(x);
                         if (pv > best) best = pv, best_i = n0 + i, best_raw = v[i];
                     }
                 }

@@ -1862,6 +1862,8 @@ struct SampleState {
     int* tokens;       // [B*n, T] output
     float* logprobs;   // [B*n, T] output or null
     int multinomial;
+    int scst;          // 1: n = n_samples + 1 rows per image, the last one a greedy rollout (no <end> handling)
+    int* greedy_tokens;  // scst: [B, T] output of the greedy rows; tokens / logprobs then hold [B*(n-1), T] sample rows
 };
 
 template <int KR>
@@ -1920,16 +1922,20 @@ __global__ void __launch_bounds__(128) sample_step_kernel(const float* __restric
         }
         if (lane == 0) {
             int word = bi;
-            if (s.multinomial) {
+            const bool greedy_row = s.scst && r == s.n - 1;
+            const int out_row = s.scst ? img * (s.n - 1) + r : row;  // sample rows are stored densely without the greedy ones
+            if (s.multinomial && !greedy_row) {
                 int unf = s.unfinished[row];
                 unf = unf && (word != TOK_END);
                 word = unf ? word : 0;
                 s.unfinished[row] = unf;
                 if (!stopped) {
-                    s.tokens[static_cast<size_t>(row) * s.T + t] = word;
-                    if (s.logprobs) s.logprobs[static_cast<size_t>(row) * s.T + t] = braw - lse;
+                    s.tokens[static_cast<size_t>(out_row) * s.T + t] = word;
+                    if (s.logprobs) s.logprobs[static_cast<size_t>(out_row) * s.T + t] = braw - lse;
                     if (unf) atomicAdd(s.live_count + t, 1);
                 }
+            } else if (greedy_row) {
+                s.greedy_tokens[static_cast<size_t>(img) * s.T + t] = word;
             } else {
                 if (s.tokens) s.tokens[static_cast<size_t>(row) * s.T + t] = word;
                 if (s.logprobs) s.logprobs[static_cast<size_t>(row) * s.T + t] = braw - lse;

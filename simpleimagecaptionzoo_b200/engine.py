@@ -285,6 +285,18 @@ class B200Captioner:
         return tokens.long(), logprobs
 
 
+    def scst_rollouts(self, visual_inputs, max_len: int = 20, n_per_image: int = 1, seed: Optional[int] = None):
+        """``greedy_res = sampler(...)`` and ``seq_gen, seqLogprobs = sampler_rl(...)`` of one SCST step
+        (Engine.py:258-262) in ONE pass over the batch -> (greedy (B,T) long, seq (B*n,T) long, logprobs (B*n,T) float);
+        row for row the same values as the two separate calls."""
+        feats, mask = self._features(visual_inputs)
+        self._prepare(feats, mask)
+        if seed is None:
+            seed = self._seed + self._calls
+            self._calls += 1
+        tokens, logprobs, greedy = self.decoder.scst_rollout(n_per_image, seed, max_len)
+        return greedy.long(), tokens.long(), logprobs
+
     # not part of the reference's captioner surface: forward values of its teacher-forced ``forward`` for a rollout
     def score(self, visual_inputs, tokens, n_per_image: int = 1):
         """log p(word t | image, previous words) of given rollouts: tokens (B*n_per_image, T) as ``sampler_rl`` returns

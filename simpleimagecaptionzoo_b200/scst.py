@@ -184,7 +184,8 @@ class CiderDReward:
         if greedy.shape[1] != T:
             raise ValueError("gen_result and greedy_res must have the same max_len")
         tok, lens, offs = self.encode_refs(ground_truth, img_ids)
-        d_tok, d_lens, d_offs = (torch.from_numpy(a).to(self.device, non_blocking=True) for a in (tok, lens, offs))
+        # pinned staging: the upload is asynchronous and does not drain the stream the rollouts were enqueued on
+        d_tok, d_lens, d_offs = (torch.from_numpy(a).pin_memory().to(self.device, non_blocking=True) for a in (tok, lens, offs))
         rewards = torch.empty((B * n,), dtype=torch.float32, device=self.device)
         scores = torch.empty((B, n + 1), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):

@@ -513,3 +513,25 @@ def test_prefetch_to_device_pipeline():
         assert vi["bu_feats"].is_cuda
         got.append(cap.sampler(vi, max_len=10).cpu())
     assert len(got) == 5 and all(torch.equal(a, b) for a, b in zip(got, direct))
+
+
+@pytest.mark.parametrize("name", ["butd_tiny_k3", "nic_tiny_k3", "aoa_tiny_k3_masked", "butd_full_k3"])
+def test_scst_rollout_equals_separate_rollouts(name):
+    """capdec_scst_rollout (n samples + 1 greedy row per image in one pass) == capdec_sample(MULTINOMIAL, n) and
+    capdec_sample(GREEDY, 1) row for row: the sampled rows keep their (seed, row, step) noise streams, so the golden
+    sampling vectors of the reference hold for it too."""
+    meta, gold = load_case(name)
+    n = meta["n_samples"]
+    dec, *_ = _make(meta, "f16x3", rows=n + 1)
+    cd = _capdec()
+    seq, lp = dec.sample(cd.SAMPLE_MULTINOMIAL, n, meta["sample_seed"], meta["T"])
+    greedy, _ = dec.sample(cd.SAMPLE_GREEDY, 1, 0, meta["T"])
+    seq2, lp2, greedy2 = dec.scst_rollout(n, meta["sample_seed"], meta["T"])
+    torch.cuda.synchronize()
+    assert torch.equal(seq, seq2) and torch.equal(greedy, greedy2)
+    assert torch.allclose(lp, lp2, atol=1e-6)
+    same = (seq2.cpu().numpy().reshape(meta["B"], n, meta["T"]) == gold["sample_seq"]).all(-1)
+    assert same.mean() >= 0.9
+    with pytest.raises(RuntimeError, match="max_rows"):
+        dec.scst_rollout(n + 1, 0, meta["T"])
+    dec.close()
