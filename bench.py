@@ -184,6 +184,19 @@ def time_reference_form(w, sd, feats, beam, max_seq):
     if w.get("refiner"):  # AoA_Model.py:748-751: projection + refiner run on every sampler call
         feats = orc.aoa_project_refine(sd, feats, None)
     dec.prepare(feats)
+    if w.get("scst"):  # the SCST step forward as the reference runs it (Engine.py:258-263): greedy, 1..n samples, CIDEr-D
+        n_img = feats.shape[0]
+        if "cider" not in _ORACLE_CACHE:
+            from simpleimagecaptionzoo_b200 import scst as scst_mod
+            ix2word, refs = synth.make_caption_corpus(64, synth.DIMS[w["arch"]]["vocab_size"], seed=0)
+            _ORACLE_CACHE["cider"] = (ix2word, refs) + scst_mod.document_frequency_from_corpus(refs)
+        ix2word, refs, df, ref_len = _ORACLE_CACHE["cider"]
+        greedy, _, _ = orc.greedy_sample(dec, max_seq)
+        seq, _, _ = orc.multinomial_sample(dec, max_seq, beam, 0)
+        ids = [i % len(refs) for i in range(n_img) for _ in range(beam)]
+        orc.self_critical_reward(seq.reshape(n_img * beam, max_seq), np.repeat(greedy, beam, axis=0), dict(enumerate(refs)), ids,
+                                 ix2word, df, ref_len)
+        return time.perf_counter() - t0, None
     res = orc.beam_search_reference_form(dec, beam, max_seq)
     return time.perf_counter() - t0, res
 
