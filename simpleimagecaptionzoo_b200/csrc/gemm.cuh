@@ -153,6 +153,36 @@ __device__ __forceinline__ void store_h16x8(__half* dst, int lo_off, const float
     if (lo_off > 0) *reinterpret_cast<uint4*>(dst + lo_off) = *reinterpret_cast<const uint4*>(lo);
 }
 
+// 32-byte stores (STG.256): one instruction writes a whole 32-byte L2 sector, where two 16-byte stores leave it partially
+// written in between.  dst must be 32-byte aligned.
+__device__ __forceinline__ void st_global_f32x8(float* dst, const float (&x)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(__float_as_uint(x[0])), "r"(__float_as_uint(x[1])),
+                 "r"(__float_as_uint(x[2])), "r"(__float_as_uint(x[3])), "r"(__float_as_uint(x[4])), "r"(__float_as_uint(x[5])),
+                 "r"(__float_as_uint(x[6])), "r"(__float_as_uint(x[7]))
+                 : "memory");
+}
+__device__ __forceinline__ bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
+// 16 fp16 values (hi, and lo at +lo_off in the split mode) with one 32-byte store each when dst allows it
+__device__ __forceinline__ void store_h16x16(__half* dst, int lo_off, const float (&h)[16]) {
+    __align__(16) __half hi[16];
+    __align__(16) __half lo[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) split_f16(h[u], hi[u], lo[u]);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(hi);
+    if (aligned32(dst)) {
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]),
+                     "r"(w[5]), "r"(w[6]), "r"(w[7])
+                     : "memory");
+    } else {
+        reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(hi)[0];
+        reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(hi)[1];
+    }
+    if (lo_off > 0) {
+        reinterpret_cast<uint4*>(dst + lo_off)[0] = reinterpret_cast<const uint4*>(lo)[0];
+        reinterpret_cast<uint4*>(dst + lo_off)[1] = reinterpret_cast<const uint4*>(lo)[1];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ epilogues
 // Each epilogue thread owns ONE output row (TMEM lane) and walks its share of the tile's columns -- chunks
 // [c0, c1) of 32 columns -- so row-wise statistics (softmax max / sum, top-k) need no cross-thread traffic.
@@ -193,7 +223,13 @@ __device__ __forceinline__ void epi_store(uint32_t taddr, int row, int n_base, i
         }
         if (e.out32) {
             float* o = e.out32 + static_cast<size_t>(row) * e.ld32 + n0;
-            if (vec_ok) {
+            if (vec_ok && n0 + 32 <= p.N && aligned32(o)) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    const float x[8] = {v[i], v[i + 1], v[i + 2], v[i + 3], v[i + 4], v[i + 5], v[i + 6], v[i + 7]};
+                    st_global_f32x8(o + i, x);
+                }
+            } else if (vec_ok) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4)
                     if (n0 + i < p.N) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -205,13 +241,23 @@ __device__ __forceinline__ void epi_store(uint32_t taddr, int row, int n_base, i
         }
         if (e.out16) {
             __half* o = e.out16 + static_cast<size_t>(row) * e.ld16 + n0;
+            if (n0 + 32 <= p.N) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-                if (n0 + i < p.N) {
-                    float h[8];
+                for (int i = 0; i < 32; i += 16) {
+                    float h[16];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) h[u] = v[i + u];
-                    store_h16x8(o + i, e.lo16, h);
+                    for (int u = 0; u < 16; ++u) h[u] = v[i + u];
+                    store_h16x16(o + i, e.lo16, h);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    if (n0 + i < p.N) {
+                        float h[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) h[u] = v[i + u];
+                        store_h16x8(o + i, e.lo16, h);
+                    }
                 }
             }
         }
@@ -233,6 +279,22 @@ __device__ __forceinline__ void epi_lstm(uint32_t taddr, int row, int n_base, in
     }
     const float* cin = e.c_in ? e.c_in + static_cast<size_t>(prow) * e.ldc : nullptr;
     const float* gat = (e.gather && row_ok) ? e.gather + static_cast<size_t>(__ldg(e.gather_idx + row)) * e.gather_ld : nullptr;
+    // The additive terms of chunk c+1 (bias / hoisted per-image row, and the gathered embedding-gate row -- a random row
+    // of a 155 MB table, i.e. an L2 or HBM access) are requested while chunk c is being computed: one chunk of load
+    // latency is exposed per tile instead of four.
+    float4 na[8], ng[8];
+    auto request = [&](int c) {
+        const int n0 = n_base + c * 32;
+        if (row_ok && c < c1 && n0 < p.N) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) na[i] = __ldg(reinterpret_cast<const float4*>(add + n0) + i);
+            if (gat) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) ng[i] = __ldg(reinterpret_cast<const float4*>(gat + n0) + i);
+            }
+        }
+    };
+    request(c0);
 #pragma unroll 1
     for (int c = c0; c < c1; ++c) {
         const int n0 = n_base + c * 32;
@@ -242,19 +304,16 @@ __device__ __forceinline__ void epi_lstm(uint32_t taddr, int row, int n_base, in
         float4 cp0 = make_float4(0.f, 0.f, 0.f, 0.f), cp1 = cp0;
         if (row_ok) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) ad[i] = __ldg(reinterpret_cast<const float4*>(add + n0) + i);
-            if (gat) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float4 q = __ldg(reinterpret_cast<const float4*>(gat + n0) + i);
-                    ad[i].x += q.x, ad[i].y += q.y, ad[i].z += q.z, ad[i].w += q.w;
-                }
+            for (int i = 0; i < 8; ++i) {
+                ad[i] = na[i];
+                if (gat) ad[i].x += ng[i].x, ad[i].y += ng[i].y, ad[i].z += ng[i].z, ad[i].w += ng[i].w;
             }
             if (cin) {
                 cp0 = *reinterpret_cast<const float4*>(cin + j0);
                 cp1 = *reinterpret_cast<const float4*>(cin + j0 + 4);
             }
         }
+        request(c + 1);
         float v[32];
         tmem_ld_32x32(taddr + c * 32, v);
         if (!row_ok) continue;
@@ -267,13 +326,21 @@ __device__ __forceinline__ void epi_lstm(uint32_t taddr, int row, int n_base, in
             hn[u] = sigmoidf_acc(go) * tanhf_acc(cn[u]);
         }
         float* co = e.c_out + static_cast<size_t>(row) * e.ldc + j0;
-        *reinterpret_cast<float4*>(co) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-        *reinterpret_cast<float4*>(co + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+        if (aligned32(co)) {
+            st_global_f32x8(co, cn);
+        } else {
+            *reinterpret_cast<float4*>(co) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+            *reinterpret_cast<float4*>(co + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+        }
         store_h16x8(e.out16 + static_cast<size_t>(row) * e.ld16 + j0, e.lo16, hn);
         if (e.h32) {
             float* ho = e.h32 + static_cast<size_t>(row) * e.ldh32 + j0;
-            *reinterpret_cast<float4*>(ho) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-            *reinterpret_cast<float4*>(ho + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+            if (aligned32(ho)) {
+                st_global_f32x8(ho, hn);
+            } else {
+                *reinterpret_cast<float4*>(ho) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                *reinterpret_cast<float4*>(ho + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+            }
         }
     }
 }
@@ -334,19 +401,18 @@ __device__ __forceinline__ void epi_glu(uint32_t taddr, int row, int n_base, int
         }
         if (e.out32) {
             float* o = e.out32 + static_cast<size_t>(row) * e.ld32 + j0;
+            if (aligned32(o)) {
 #pragma unroll
-            for (int u = 0; u < 16; u += 4) *reinterpret_cast<float4*>(o + u) = make_float4(y[u], y[u + 1], y[u + 2], y[u + 3]);
-        }
-        if (e.out16) {
-            __half* o = e.out16 + static_cast<size_t>(row) * e.ld16 + j0;
+                for (int u = 0; u < 16; u += 8) {
+                    const float x[8] = {y[u], y[u + 1], y[u + 2], y[u + 3], y[u + 4], y[u + 5], y[u + 6], y[u + 7]};
+                    st_global_f32x8(o + u, x);
+                }
+            } else {
 #pragma unroll
-            for (int u = 0; u < 16; u += 8) {
-                float h[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) h[q] = y[u + q];
-                store_h16x8(o + u, e.lo16, h);
+                for (int u = 0; u < 16; u += 4) *reinterpret_cast<float4*>(o + u) = make_float4(y[u], y[u + 1], y[u + 2], y[u + 3]);
             }
         }
+        if (e.out16) store_h16x16(e.out16 + static_cast<size_t>(row) * e.ld16 + j0, e.lo16, y);
     }
 }
 
