@@ -13,7 +13,8 @@ from typing import Mapping, Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcapdec.so")
+# CAPDEC_LIB selects another build of the same library (A/B timing of two kernel versions on one GPU box)
+LIB_PATH = os.environ.get("CAPDEC_LIB") or os.path.join(_HERE, "libcapdec.so")
 
 ARCH = {"NIC": 0, "BUTD": 1, "AOA": 2}
 MATH = {"f16": 0, "f16x3": 1}

@@ -183,6 +183,15 @@ __device__ __forceinline__ void store_h16x16(__half* dst, int lo_off, const floa
     }
 }
 
+// pre[8] holds the chunk's 32 bias values when the chunk is full (requested one chunk ahead by the caller, so that their
+// L1 / L2 latency overlaps the previous chunk's arithmetic); the vocabulary's tail chunk loads its own.
+__device__ __forceinline__ void request_bias32(float4 (&pre)[8], const float* __restrict__ bias, int n0, int N) {
+    if (n0 + 32 <= N) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pre[i] = __ldg(reinterpret_cast<const float4*>(bias + n0) + i);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ epilogues
 // Each epilogue thread owns ONE output row (TMEM lane) and walks its share of the tile's columns -- chunks
 // [c0, c1) of 32 columns -- so row-wise statistics (softmax max / sum, top-k) need no cross-thread traffic.
@@ -193,20 +202,23 @@ __device__ __forceinline__ void epi_store(uint32_t taddr, int row, int n_base, i
     const bool row_ok = row < p.M;
     const bool vec_ok = (p.N & 3) == 0;
     const bool keep = !(e.row_keep && row_ok && __ldg(e.row_keep + row) == 0.f);
+    float4 nb[8];  // bias of the next chunk, requested one chunk ahead
+    if (e.bias && vec_ok && row_ok) request_bias32(nb, e.bias, n_base + c0 * 32, p.N);
 #pragma unroll 1
     for (int c = c0; c < c1; ++c) {
         const int n0 = n_base + c * 32;
         if (n0 >= p.N) break;  // warp-uniform
+        float4 cb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cb[i] = nb[i];
+        if (e.bias && vec_ok && row_ok && c + 1 < c1) request_bias32(nb, e.bias, n0 + 32, p.N);
         float v[32];
         tmem_ld_32x32(taddr + c * 32, v);
         if (!row_ok) continue;
         if (e.bias) {
             if (vec_ok && n0 + 32 <= p.N) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + i));
-                    v[i] += b.x, v[i + 1] += b.y, v[i + 2] += b.z, v[i + 3] += b.w;
-                }
+                for (int i = 0; i < 8; ++i) v[4 * i] += cb[i].x, v[4 * i + 1] += cb[i].y, v[4 * i + 2] += cb[i].z, v[4 * i + 3] += cb[i].w;
             } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
@@ -418,16 +430,17 @@ __device__ __forceinline__ void epi_glu(uint32_t taddr, int row, int n_base, int
 
 // One 32-column chunk of logits: add the bias, mask the padded vocabulary tail, fold into the running
 // (max, sum of exp(x - max)) pair.  exp via ex2.approx on log2e-prescaled arguments (one FFMA + one MUFU per element).
-__device__ __forceinline__ float logits_chunk_stats(float (&v)[32], int n0, int N, const float* __restrict__ bias, float& m,
-                                                    float& s) {
+__device__ __forceinline__ float logits_chunk_stats(float (&v)[32], int n0, int N, const float* __restrict__ bias,
+                                                    const float4 (&pre)[8], float& m, float& s) {
     float cmax = -INFINITY;
     if (n0 + 32 <= N) {
+        float c4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-            float b0 = __ldg(bias + n0 + i), b1 = __ldg(bias + n0 + i + 1), b2 = __ldg(bias + n0 + i + 2), b3 = __ldg(bias + n0 + i + 3);
-            v[i] += b0, v[i + 1] += b1, v[i + 2] += b2, v[i + 3] += b3;
-            cmax = fmaxf(cmax, fmaxf(fmaxf(v[i], v[i + 1]), fmaxf(v[i + 2], v[i + 3])));
+        for (int i = 0; i < 8; ++i) {
+            v[4 * i] += pre[i].x, v[4 * i + 1] += pre[i].y, v[4 * i + 2] += pre[i].z, v[4 * i + 3] += pre[i].w;
+            c4[i & 3] = fmaxf(c4[i & 3], fmaxf(fmaxf(v[4 * i], v[4 * i + 1]), fmaxf(v[4 * i + 2], v[4 * i + 3])));
         }
+        cmax = fmaxf(fmaxf(c4[0], c4[1]), fmaxf(c4[2], c4[3]));
     } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -441,10 +454,10 @@ __device__ __forceinline__ float logits_chunk_stats(float (&v)[32], int n0, int 
     }
     const float mn = fmaxf(m, cmax);
     const float mn2 = mn * LOG2E;
-    float acc = 0.f;
+    float a4[4] = {0.f, 0.f, 0.f, 0.f};  // four independent partial sums instead of one 32-long dependent chain
 #pragma unroll
-    for (int i = 0; i < 32; ++i) acc += exp2f(fmaf(v[i], LOG2E, -mn2));  // exp2(-inf) = 0 for the padded columns
-    s = s * exp2f(fmaf(m, LOG2E, -mn2)) + acc;
+    for (int i = 0; i < 32; ++i) a4[i & 3] += exp2f(fmaf(v[i], LOG2E, -mn2));  // exp2(-inf) = 0 for the padded columns
+    s = s * exp2f(fmaf(m, LOG2E, -mn2)) + ((a4[0] + a4[1]) + (a4[2] + a4[3]));
     m = mn;
     return cmax;
 }
@@ -464,13 +477,19 @@ struct TopkState {
         for (int q = 0; q < KTOP; ++q) tv[q] = -INFINITY, ti[q] = 0x7FFFFFFF;
     }
     __device__ __forceinline__ void tile(uint32_t taddr, int n_base, int c0, int c1, const GemmParams& p) {
+        float4 nb[8];
+        request_bias32(nb, p.epi.bias, n_base + c0 * 32, p.N);
 #pragma unroll 1
         for (int c = c0; c < c1; ++c) {
             const int n0 = n_base + c * 32;
             if (n0 >= p.N) break;
+            float4 cb[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cb[i] = nb[i];
+            if (c + 1 < c1) request_bias32(nb, p.epi.bias, n0 + 32, p.N);
             float v[32];
             tmem_ld_32x32(taddr + c * 32, v);
-            const float cmax = logits_chunk_stats(v, n0, p.N, p.epi.bias, m, s);
+            const float cmax = logits_chunk_stats(v, n0, p.N, p.epi.bias, cb, m, s);
             if (cmax > tv[KTOP - 1]) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
@@ -523,13 +542,19 @@ struct DrawState {
         forced = (p.epi.forced && row < p.M) ? __ldg(p.epi.forced + static_cast<size_t>(row) * p.epi.forced_ld + p.epi.step) : -1;
     }
     __device__ __forceinline__ void tile(uint32_t taddr, int n_base, int c0, int c1, const GemmParams& p) {
+        float4 nb[8];
+        request_bias32(nb, p.epi.bias, n_base + c0 * 32, p.N);
 #pragma unroll 1
         for (int c = c0; c < c1; ++c) {
             const int n0 = n_base + c * 32;
             if (n0 >= p.N) break;
+            float4 cb[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cb[i] = nb[i];
+            if (c + 1 < c1) request_bias32(nb, p.epi.bias, n0 + 32, p.N);
             float v[32];
             tmem_ld_32x32(taddr + c * 32, v);
-            const float cmax = logits_chunk_stats(v, n0, p.N, p.epi.bias, m, s);
+            const float cmax = logits_chunk_stats(v, n0, p.N, p.epi.bias, cb, m, s);
             if (p.epi.forced) {  // the given word "wins": its raw logit is what the log-prob needs
                 const int f = forced - n0;
                 if (f >= 0 && f < 32) {
