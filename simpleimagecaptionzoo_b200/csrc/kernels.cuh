@@ -714,6 +714,7 @@ butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            const uint64_t pol = l2_policy_evict_first();
             for (int img = blockIdx.x; img < B; img += gridDim.x) {
                 for (int c = 0; c < n_chunks1 + n_chunks3; ++c) {
                     const bool p1 = c < n_chunks1;
@@ -727,7 +728,7 @@ butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __
                     const __half* src = p1 ? enc16 + row0 * ld_enc : feats16 + row0 * ld_feats;
                     mbar_wait_lean(empty_bar + 8 * stage, phase ^ 1);
                     mbar_arrive_expect_tx(full_bar + 8 * stage, bytes);
-                    bulk_load_1d(ring + stage * sh.stage_bytes, src, bytes, full_bar + 8 * stage);
+                    bulk_load_1d_hint(ring + stage * sh.stage_bytes, src, bytes, full_bar + 8 * stage, pol);
                     if (++stage == STAGES) stage = 0, phase ^= 1;
                 }
             }
@@ -1404,6 +1405,7 @@ aoa_attention_mma_kernel(const __half* __restrict__ k16, const __half* __restric
         if (lane == 0) {  // producer: K chunks then V chunks of every image, one contiguous copy each
             int stage = 0;
             uint32_t phase = 0;
+            const uint64_t pol = l2_policy_evict_first();
             for (int img = blockIdx.x; img < B; img += gridDim.x) {
                 for (int c = 0; c < 2 * n_chunks; ++c) {
                     const bool kpart = c < n_chunks;
@@ -1415,7 +1417,7 @@ aoa_attention_mma_kernel(const __half* __restrict__ k16, const __half* __restric
                     const uint32_t bytes = static_cast<uint32_t>(nr) * row_bytes;
                     mbar_wait_lean(empty_bar + 8 * stage, phase ^ 1);
                     mbar_arrive_expect_tx(full_bar + 8 * stage, bytes);
-                    bulk_load_1d(ring + stage * stage_bytes, (kpart ? k16 : v16) + row0 * ld_kv, bytes, full_bar + 8 * stage);
+                    bulk_load_1d_hint(ring + stage * stage_bytes, (kpart ? k16 : v16) + row0 * ld_kv, bytes, full_bar + 8 * stage, pol);
                     if (++stage == stages) stage = 0, phase ^= 1;
                 }
             }
