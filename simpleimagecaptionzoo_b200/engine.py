@@ -392,6 +392,28 @@ class CaptionEngine:
         return result
 
 
+    def scst_forward_epoch(self, dataloader, reward, n_per_image: int = 1, max_len: int = 20):
+        """Forward half of ``Engine.SCST_training_epoch`` (Engine.py:251-272) with everything on the device: for every
+        ``(img_ids, img_tensors, img_gts, supp_info_datas)`` batch of the SCST dataloader yields
+        ``(img_ids, seq_gen (B*n,T) long, seqLogprobs (B*n,T) float, greedy_res (B,T) long, rewards (B*n,T) float)`` --
+        the inputs of ``RewardCriterion`` (Utils.py:290-317).  The host->device copy of batch i+1 overlaps the rollouts of
+        batch i, both rollouts run in one pass, ``reward`` is a :class:`scst.CiderDReward`.  The backward pass and the
+        optimiser step are the caller's (out of scope here)."""
+        meta = []
+
+        def inputs():
+            for img_ids, img_tensors, img_gts, supp_info_datas in dataloader:
+                meta.append((img_ids, img_gts))
+                yield self.modify_visual_inputs(img_tensors=img_tensors, supp_info_datas=supp_info_datas, device="cpu")
+
+        for vi in self.model.prefetch_to_device(inputs()):
+            img_ids, img_gts = meta.pop(0)
+            greedy, seq, logprobs = self.model.scst_rollouts(vi, max_len=max_len, n_per_image=n_per_image)
+            ids = [int(i) if not isinstance(i, (str, bytes)) else i for i in img_ids]
+            rewards = reward(seq, greedy, img_gts, ids, n_per_image=n_per_image)
+            yield img_ids, seq, logprobs, greedy, rewards
+
+
 class NIC_Eng(CaptionEngine):
     model_type = "NIC"
 

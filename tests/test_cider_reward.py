@@ -99,3 +99,40 @@ def test_device_reward_rejects_bad_input():
     with pytest.raises(ValueError, match="tokens"):
         scorer(gen, gen, {i: [" ".join(["w5"] * 70)] for i in range(4)}, [0, 1, 2, 3])
     scorer.close()
+
+
+@pytest.mark.gpu
+def test_engine_scst_forward_epoch():
+    """CaptionEngine.scst_forward_epoch: the forward half of an SCST epoch (prefetch, one-pass rollouts, device reward)
+    yields what RewardCriterion consumes, and its rewards equal the oracle's on the rollouts it produced."""
+    torch = pytest.importorskip("torch")
+    from simpleimagecaptionzoo_b200 import engine
+    dims = dict(synth.TINY_DIMS["BUTD"])
+    ix2word, refs = synth.make_caption_corpus(12, dims["vocab_size"], seed=4)
+    df, ref_len = scst.document_frequency_from_corpus(refs)
+    sd = synth.make_state_dict("BUTD", seed=1, chaotic=True, end_boost=1.0, **dims)
+
+    class Vocab:
+        def __init__(self, words):
+            self.ix2word = dict(enumerate(words))
+            self.word2ix = {w: i for i, w in enumerate(words)}
+
+        def __len__(self):
+            return len(self.ix2word)
+
+    settings = dict(model_type="BUTDDetection", embed_dim=dims["embed_dim"], hidden_dim=dims["hidden_dim"], atten_dim=dims["atten_dim"])
+    eng = engine.BUTDDetection_Eng(settings, "synthetic", Vocab(ix2word), state_dict=sd, max_batch=4, max_regions=6, max_rows=3,
+                                   max_seq=20, enc_dim=dims["enc_dim"])
+    feats = synth.make_region_feats(12, 6, dims["enc_dim"], 4)
+    gts = dict(enumerate(refs))
+    loader = [([4 * b + i for i in range(4)], None, gts, [{"bu_feat": feats[4 * b + i], "bu_bbox": None} for i in range(4)]) for b in range(3)]
+    reward = scst.CiderDReward(eng.caption_vocab.word2ix, df, ref_len)
+    seen = 0
+    for img_ids, seq, logprobs, greedy, rewards in eng.scst_forward_epoch(loader, reward, n_per_image=2, max_len=20):
+        assert seq.shape == (8, 20) and logprobs.shape == (8, 20) and greedy.shape == (4, 20) and rewards.shape == (8, 20)
+        ids_rep = [i for i in img_ids for _ in range(2)]
+        want, _ = orc.self_critical_reward(seq.cpu().numpy(), np.repeat(greedy.cpu().numpy(), 2, axis=0), gts, ids_rep, ix2word, df, ref_len)
+        assert np.abs(rewards.cpu().numpy() - want).max() < 1e-5
+        seen += len(img_ids)
+    assert seen == 12
+    reward.close()
