@@ -108,7 +108,7 @@ def test_beam_search_fp16_mode_tiny(name):
 
 def test_beam_search_fp16_mode_full_dims():
     """Single-pass fp16 operands at BASELINE dims: >= 90 % exact-or-tie-justified over all full-size golden images
-    (north_star's agreement target; tools/agreement.py measures it on thousands of images) and the stated bound on
+    (north_star's agreement target; tests/tools/agreement.py measures it on thousands of images) and the stated bound on
     the sequence log-prob."""
     verdicts, worst = [], 0.0
     for name in FULL:

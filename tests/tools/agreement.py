@@ -7,7 +7,7 @@ staged: (1) the fp32-grade CUDA mode (f16x3) is validated against the numpy orac
 image where the two CUDA modes disagree; (2) the fp16 mode is compared with f16x3 on all images; disagreements are
 classified with the oracle's top-(k+1) gaps (tie-justified if a gap < 1e-4 occurs at or before the first divergence).
 
-    python tools/agreement.py [--images 5000] [--arch BUTD] [--beam 3] [--out gpurun_out/agreement.json]
+    python tests/tools/agreement.py [--images 5000] [--arch BUTD] [--beam 3] [--out gpurun_out/agreement.json]
 """
 import argparse
 import json
@@ -18,7 +18,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 from oracle import capdec_oracle as orc  # noqa: E402

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Bring-up diagnostics for the GPU box: runs each check in isolation (own try/except) and prints a summary.
-Usage: python tools/gpu_check.py [gemm] [tiny] [full] [sample]   (default: all).  Output is also useful as a log
+Usage: python tests/tools/gpu_check.py [gemm] [tiny] [full] [sample]   (default: all).  Output is also useful as a log
 under gpurun_out/.  The numpy oracle is used here as the CHECKER only."""
 import os
 import sys
@@ -10,7 +10,7 @@ import traceback
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 from oracle import capdec_oracle as orc  # noqa: E402
