@@ -43,7 +43,8 @@ def _oracle(meta, sd, feats, mask):
 
 
 @pytest.mark.parametrize("math", ["f16", "f16x3"])
-@pytest.mark.parametrize("shape", [(128, 256, 64), (200, 300, 128), (48, 32, 192), (777, 1024, 1024), (3072, 512, 4096)])
+@pytest.mark.parametrize("shape", [(128, 256, 64), (200, 300, 128), (48, 32, 192), (777, 1024, 1024), (3072, 512, 4096),
+                                   (38500, 512, 128)])  # 151 row blocks: three groups of the grouped tile walk, the last one short
 def test_gemm_against_torch_fp64(shape, math):
     """The tcgen05 GEMM against a plain fp64 matmul of the same operands (fp16-rounded for the single-pass mode)."""
     capdec = _capdec()
