@@ -184,6 +184,11 @@ int capdec_cider_reward(capdec_cider* c, const int32_t* gen, int32_t n_per_image
 /* Number of kernels the library launched on behalf of this handle since create (bench.py's gpu_launches). */
 int64_t capdec_launch_count(const capdec_handle* h);
 
+/* Number of decode graphs captured so far.  Beam search and the rollouts replay a CUDA graph of their whole kernel
+ * sequence, cached per (kind, batch, regions, rows per image, max_seq, ...) -- up to 8 entries, least recently used
+ * replaced -- so a ragged last batch or alternating beam sizes capture once each. */
+int64_t capdec_graph_captures(const capdec_handle* h);
+
 /* Per-launch timing for bench.py's roofline line: while enabled, every kernel the handle launches is bracketed by
  * CUDA events on the launching stream.  capdec_profile_read waits for the recorded events and returns, per
  * category, the summed device time (ms), the algorithmic FLOPs of the GEMM launches (2*M*N*K, one pass) and the

@@ -27,7 +27,7 @@ SYMBOLS = (
     "capdec_test_gemm", "capdec_profile", "capdec_profile_read", "capdec_test_gemm_time",
     "capdec_prepare_bottom_up", "capdec_get_refined", "capdec_score", "capdec_prepare_f16", "capdec_scst_rollout",
     "capdec_cider_create", "capdec_cider_destroy", "capdec_cider_last_error", "capdec_cider_ngram_key", "capdec_cider_set_df",
-    "capdec_cider_reward",
+    "capdec_cider_reward", "capdec_graph_captures",
 )
 CATEGORIES = ("gemm_lstm", "gemm_store", "gemm_glu", "gemm_logits", "attention", "bookkeeping", "other")
 
@@ -79,6 +79,8 @@ def load_library(path: str = LIB_PATH) -> ctypes.CDLL:
     lib.capdec_cider_reward.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp, i32, ctypes.c_double, ctypes.c_double, vp, vp, vp]
     lib.capdec_launch_count.argtypes = [vp]
     lib.capdec_launch_count.restype = i64
+    lib.capdec_graph_captures.argtypes = [vp]
+    lib.capdec_graph_captures.restype = i64
     lib.capdec_test_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.capdec_profile.argtypes = [vp, i32]
     lib.capdec_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
@@ -208,6 +210,10 @@ class CaptionDecoder:
     @property
     def launch_count(self) -> int:
         return int(self.lib.capdec_launch_count(self._h))
+
+    @property
+    def graph_captures(self) -> int:
+        return int(self.lib.capdec_graph_captures(self._h))
 
     def profile(self, enable: bool):
         self._check(self.lib.capdec_profile(self._h, 1 if enable else 0), "capdec_profile")

@@ -106,6 +106,8 @@ class CnnFeed:
     """``feature_fn`` for :class:`engine.B200Captioner`: ``visual_inputs['img_tensors']`` (B,3,224,224) fp32, host
     (ideally pinned) or device -> the decoder's input as a CUDA fp32 tensor."""
 
+    accepts_host_inputs = True  # the pipelined eval loop may hand it (pinned) host images
+
     def __init__(self, model_type: str, state_dict: Mapping[str, object], *, enc_img_size: int = 7, device: int = 0,
                  dtype: str = "fp16", use_graph: bool = True, fuse: bool = True):
         torch = _torch()

@@ -9,6 +9,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -50,6 +52,21 @@ EncodeTiledFn get_encode_fn() {
 }
 
 constexpr int BN = 256;  // BLOCK_N of every GEMM instantiation
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: set it once per (kernel, device),
+// whichever handle on whichever GPU of the process launches the kernel first.
+cudaError_t smem_attr(const void* kern, int bytes) {
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int>> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.count({kern, dev})) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.insert({kern, dev});
+    return e;
+}
 
 }  // namespace
 
@@ -104,16 +121,33 @@ struct capdec_handle {
     // CUDA graph of one whole beam-search decode (all steps), replayed while the shapes / buffers stay the same
     bool use_pdl = false;    // CAPDEC_PDL=1: programmatic dependent launch inside the decode loop (measured neutral)
     bool use_graphs = true;  // CAPDEC_NO_GRAPH=1 disables
-    cudaGraphExec_t graph_exec = nullptr;
+    // cache of captured decodes, least recently used entry replaced (a ragged last batch or alternating beam sizes /
+    // decode kinds do not re-capture every call)
+    enum { GK_BEAM = 0, GK_SAMPLE = 1, GK_SCST = 2, GK_SCORE = 3 };
     struct GraphKey {
-        int B, R, K, T;
+        int kind, B, R, K, T, mode, outs;  // K = beam or rows per image; outs = which optional outputs are produced
         const void* feats;  // fp32-grade mode reads the caller's features inside the loop
         bool masked;
         bool operator==(const GraphKey& o) const {
-            return B == o.B && R == o.R && K == o.K && T == o.T && feats == o.feats && masked == o.masked;
+            return kind == o.kind && B == o.B && R == o.R && K == o.K && T == o.T && mode == o.mode && outs == o.outs &&
+                   feats == o.feats && masked == o.masked;
         }
-    } graph_key{};
-    int64_t graph_launches = 0;
+    };
+    struct GraphEntry {
+        GraphKey key;
+        cudaGraphExec_t exec;
+        int64_t launches;
+        uint64_t used;
+    };
+    static constexpr size_t GRAPH_CACHE = 8;
+    std::vector<GraphEntry> graphs;
+    uint64_t graph_clock = 0;
+    int64_t graph_captures = 0;
+    uint32_t* seed_dev = nullptr;     // sampling seed of the (replayed) rollout, written before every launch
+    int* out_sample_tokens = nullptr;  // library-owned outputs of a captured rollout (copied to the caller's buffers)
+    float* out_sample_logprobs = nullptr;
+    int* out_greedy = nullptr;
+    int* forced_buf = nullptr;         // teacher-forced words of capdec_score at a stable address
     float* mask_buf = nullptr;  // library-owned copy of the region mask (stable address for the captured decode)
     int* out_tokens = nullptr;
     float* out_scores = nullptr;
@@ -239,12 +273,8 @@ int map_b(capdec_handle* h, CUtensorMap* m, const Act16& a) {
 template <int EPI, int KTOP>
 int launch_gemm_t(capdec_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
     using Cfg = GemmCfg<BN>;
-    static bool attr_set = false;
     auto kern = gemm_kernel<BN, EPI, KTOP>;
-    if (!attr_set) {
-        CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
-    }
+    CK(h, smem_attr(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES));
     const int tiles = p.runs > 0 ? p.num_m_blocks * p.runs : p.num_m_blocks * p.num_n_blocks;
     const int grid = tiles < h->num_sms ? tiles : h->num_sms;
     GemmParams pg = p;
@@ -262,12 +292,8 @@ int launch_gemm_t(capdec_handle* h, const CUtensorMap& ma, const CUtensorMap& mb
 // D[M,N] = A[M,Kdim] * B[N,Kdim]^T with the chosen epilogue.
 template <int EPI, int KTOP>
 int launch_gemm2_t(capdec_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
-    static bool attr_set = false;
     auto kern = gemm2_kernel<EPI, KTOP>;
-    if (!attr_set) {
-        CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg2::SMEM_BYTES));
-        attr_set = true;
-    }
+    CK(h, smem_attr(reinterpret_cast<const void*>(kern), GemmCfg2::SMEM_BYTES));
     const int items = p.runs > 0 ? p.num_m_blocks * p.runs : p.num_m_blocks * p.num_n_blocks;
     const int pairs = items < h->num_sms / 2 ? items : h->num_sms / 2;
     GemmParams pg = p;
@@ -602,12 +628,8 @@ int finalize_refiner(capdec_handle* h, cudaStream_t st) {
 template <int NKT, int DH, int G>
 int launch_refine_att_mma_t(capdec_handle* h, int B, int R, const float* mask, cudaStream_t st) {
     using C = RefineMmaCfg<NKT, DH, G>;
-    static bool attr_set = false;
     auto kern = refine_attention_mma_kernel<NKT, DH, G>;
-    if (!attr_set) {
-        CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        attr_set = true;
-    }
+    CK(h, smem_attr(reinterpret_cast<const void*>(kern), C::SMEM_BYTES));
     const int items = B * (h->NH / G);
     const int cap = h->num_sms * C::CTAS_PER_SM;
     kern<<<items < cap ? items : cap, 32 * C::WARPS, C::SMEM_BYTES, st>>>(h->qkv16.p, h->qkv16.ld, mask, B, R, h->H, h->NH, h->XR.p,
@@ -635,18 +657,10 @@ int launch_refine_att(capdec_handle* h, int B, int R, const float* mask, cudaStr
         const size_t smem = (static_cast<size_t>(R) * (2 * d + 1) + 4 * (d + R)) * sizeof(float);
         if (smem > 227 * 1024) return fail(h, CAPDEC_ERR_INVALID, "refiner attention tile does not fit shared memory");
         if (h->split) {
-            static bool attr_set = false;
-            if (!attr_set) {
-                CK(h, cudaFuncSetAttribute(refine_attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                attr_set = true;
-            }
+            CK(h, smem_attr(reinterpret_cast<const void*>(refine_attention_kernel<float>), 227 * 1024));
             refine_attention_kernel<float><<<B * nh, 128, smem, st>>>(h->qkv32, 3 * H, mask, R, H, nh, h->XR.p, h->XR.ld, h->XR.lo);
         } else {
-            static bool attr_set = false;
-            if (!attr_set) {
-                CK(h, cudaFuncSetAttribute(refine_attention_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                attr_set = true;
-            }
+            CK(h, smem_attr(reinterpret_cast<const void*>(refine_attention_kernel<__half>), 227 * 1024));
             refine_attention_kernel<__half><<<B * nh, 128, smem, st>>>(h->qkv16.p, h->qkv16.ld, mask, R, H, nh, h->XR.p, h->XR.ld, h->XR.lo);
         }
     }
@@ -723,6 +737,7 @@ struct StepCtx {
     int logits_epi = EPI_TOPK;
     int ktop = 4;
     uint32_t seed = 0;
+    const uint32_t* seed_ptr = nullptr;  // captured rollouts read the seed from device memory
     int use_noise = 0;
     int scst_n = 0;  // > 0: rows = scst_n sampled + 1 greedy rollout per image
     bool first_from_c0 = false;
@@ -741,6 +756,7 @@ int run_logits(capdec_handle* h, const Act16& a, const StepCtx& c, cudaStream_t 
     e.part = h->part;
     e.n_tiles = logit_runs(h, c.M, h->V) * EPI_SPLIT;
     e.seed = c.seed;
+    e.seed_ptr = c.seed_ptr;
     e.step = c.t - 1;
     e.use_noise = c.use_noise;
     e.scst_n = c.scst_n;
@@ -751,13 +767,9 @@ int run_logits(capdec_handle* h, const Act16& a, const StepCtx& c, cudaStream_t 
 
 template <int KR, typename T>
 int launch_butd_att_t(capdec_handle* h, const StepCtx& c, const T* enc, int enc_ld, const T* feats, int feats_ld, cudaStream_t st) {
-    static bool attr_set = false;
     auto kern = butd_attention_kernel<KR, T>;
     const size_t smem = (static_cast<size_t>(KR) * h->R + 2 * 8 * AttCfg<KR>::NP) * sizeof(float);
-    if (!attr_set) {
-        CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        attr_set = true;
-    }
+    CK(h, smem_attr(reinterpret_cast<const void*>(kern), 160 * 1024));
     if (smem > 160 * 1024) return fail(h, CAPDEC_ERR_INVALID, "attention tile does not fit shared memory");
     prof_begin(h, CAPDEC_CAT_ATTENTION, 0.0, st);
     kern<<<h->B, 256, smem, st>>>(enc, enc_ld, feats, feats_ld, h->dec_ctx, h->w_aff, h->b_aff, h->R, h->A, h->D, c.K, h->XB.p, h->XB.ld,
@@ -771,14 +783,10 @@ int launch_butd_att_t(capdec_handle* h, const StepCtx& c, const T* enc, int enc_
 template <int KR, typename T>
 int launch_butd_att_stream_t(capdec_handle* h, const StepCtx& c, const T* enc, const T* feats, cudaStream_t st) {
     using C = AttStreamCfg<KR, T>;
-    static bool attr_set = false;
     auto kern = butd_attention_stream_kernel<KR, T>;
     const size_t smem = static_cast<size_t>(C::STAGES) * C::STAGE_BYTES + 2 * C::STAGES * 8 +
                         (static_cast<size_t>(KR) * h->R + 2 * 8 * C::NP) * sizeof(float) + 128;
-    if (!attr_set) {
-        CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    CK(h, smem_attr(reinterpret_cast<const void*>(kern), 200 * 1024));
     if (smem > 200 * 1024) return fail(h, CAPDEC_ERR_INVALID, "attention ring does not fit shared memory");
     const int per_sm = C::CTAS_PER_SM;
     const int grid = h->B < h->num_sms * per_sm ? h->B : h->num_sms * per_sm;
@@ -794,13 +802,9 @@ int launch_butd_att_stream_t(capdec_handle* h, const StepCtx& c, const T* enc, c
 template <int KR, int CTAS, bool FULL>
 int launch_butd_att_mma_t(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
     using C = AttMmaCfg<KR, CTAS>;
-    static bool attr_set = false;
     auto kern = butd_attention_mma_kernel<KR, CTAS, FULL>;
     const size_t smem = att_mma_smem_bytes(KR, C::STAGES, h->R, h->A, h->enc16.ld, h->feats16.ld);
-    if (!attr_set) {
-        CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
+    CK(h, smem_attr(reinterpret_cast<const void*>(kern), 227 * 1024));
     if (smem > 227 * 1024) return fail(h, CAPDEC_ERR_INVALID, "attention ring does not fit shared memory");
     const int cap = h->num_sms * C::CTAS_PER_SM;
     const int grid = h->B < cap ? h->B : cap;
@@ -848,7 +852,6 @@ bool aoa_mma_ok(const capdec_handle* h) {
 
 template <int KR>
 int launch_aoa_att_mma(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
-    static bool attr_set = false;
     auto kern = aoa_attention_mma_kernel<KR>;
     const size_t fixed = aoa_mma_fixed_smem(KR, h->R, h->H, h->NH);
     const size_t stage_bytes = static_cast<size_t>(16) * h->k16.ld * 2;
@@ -856,10 +859,7 @@ int launch_aoa_att_mma(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
     if (stages > 8) stages = 8;
     if (stages < 2) return fail(h, CAPDEC_ERR_INVALID, "AoA attention ring does not fit shared memory");
     const size_t smem = fixed + stages * stage_bytes;
-    if (!attr_set) {
-        CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
+    CK(h, smem_attr(reinterpret_cast<const void*>(kern), 227 * 1024));
     const int grid = h->B < h->num_sms ? h->B : h->num_sms;
     prof_begin(h, CAPDEC_CAT_ATTENTION, 0.0, st);
     CK(h, launch_pdl(h, kern, dim3(grid), dim3(288), smem, st, h->k16.p, h->v16.p, h->k16.ld, static_cast<size_t>(h->B) * h->R,
@@ -873,13 +873,9 @@ int launch_aoa_att_mma(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
 template <int KR>
 int launch_aoa_att(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
     if (aoa_mma_ok(h)) return launch_aoa_att_mma<KR>(h, c, st);
-    static bool attr_set = false;
     auto kern = aoa_attention_kernel<KR>;
     const size_t smem = (static_cast<size_t>(KR) * h->H + static_cast<size_t>(KR) * h->NH * h->R) * sizeof(float);
-    if (!attr_set) {
-        CK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        attr_set = true;
-    }
+    CK(h, smem_attr(reinterpret_cast<const void*>(kern), 160 * 1024));
     if (smem > 160 * 1024) return fail(h, CAPDEC_ERR_INVALID, "attention tile does not fit shared memory");
     prof_begin(h, CAPDEC_CAT_ATTENTION, 0.0, st);
     kern<<<h->B, 256, smem, st>>>(h->q32, h->kv32, h->mask, h->R, h->H, h->NH, c.K, h->XB.p, h->XB.ld, h->XB.lo, c.alphas,
@@ -1100,6 +1096,47 @@ int reset_state(capdec_handle* h, int M, cudaStream_t st) {
     return CAPDEC_OK;
 }
 
+// Launch the captured form of a decode (capturing it first when the cache has no entry for `key`): `enqueue` issues the
+// whole kernel sequence on `st` with library-owned output buffers.
+template <typename F>
+int replay_graph(capdec_handle* h, const capdec_handle::GraphKey& key, cudaStream_t st, F&& enqueue) {
+    capdec_handle::GraphEntry* hit = nullptr;
+    for (auto& g : h->graphs)
+        if (g.key == key) hit = &g;
+    if (!hit) {
+        cudaGraph_t graph = nullptr;
+        CK(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const int64_t l0 = h->launches;
+        const int status = enqueue();
+        const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        const int64_t n = h->launches - l0;
+        h->launches = l0;
+        if (status != CAPDEC_OK) {
+            if (graph) cudaGraphDestroy(graph);
+            return status;
+        }
+        CK(h, ce);
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        CK(h, ie);
+        if (h->graphs.size() >= capdec_handle::GRAPH_CACHE) {  // replace the least recently used entry
+            size_t lru = 0;
+            for (size_t i = 1; i < h->graphs.size(); ++i)
+                if (h->graphs[i].used < h->graphs[lru].used) lru = i;
+            cudaGraphExecDestroy(h->graphs[lru].exec);
+            h->graphs.erase(h->graphs.begin() + static_cast<long>(lru));
+        }
+        h->graphs.push_back({key, exec, n, 0});
+        hit = &h->graphs.back();
+        h->graph_captures++;
+    }
+    hit->used = ++h->graph_clock;
+    CK(h, cudaGraphLaunch(hit->exec, st));
+    h->launches += hit->launches;
+    return CAPDEC_OK;
+}
+
 }  // namespace
 
 struct capdec_cider {
@@ -1183,12 +1220,7 @@ int capdec_cider_reward(capdec_cider* c, const int32_t* gen, int32_t n_per_image
     }
     CK(c, cudaSetDevice(c->device));
     const size_t smem = static_cast<size_t>(n_per_image + 1 + CIDER_REF_SLOTS) * sizeof(CiderVec);
-    static bool attr_set = false;
-    if (!attr_set) {
-        CK(c, cudaFuncSetAttribute(cider_reward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>((CIDER_MAX_HYPS + CIDER_REF_SLOTS) * sizeof(CiderVec))));
-        attr_set = true;
-    }
+    CK(c, smem_attr(reinterpret_cast<const void*>(cider_reward_kernel), static_cast<int>((CIDER_MAX_HYPS + CIDER_REF_SLOTS) * sizeof(CiderVec))));
     CiderTable tab{c->keys, c->df, c->slots ? c->slots - 1 : 0, c->log_ref_len};
     cider_reward_kernel<<<batch, 32 * (n_per_image + 1), smem, static_cast<cudaStream_t>(stream)>>>(
         tab, gen, n_per_image, greedy, max_seq, ref_tokens, ref_lens, ref_offsets, ref_ld, sigma, weight, rewards, scores);
@@ -1202,10 +1234,12 @@ const char* capdec_last_error(const capdec_handle* h) { return h ? h->err.c_str(
 
 int64_t capdec_launch_count(const capdec_handle* h) { return h ? h->launches : 0; }
 
+int64_t capdec_graph_captures(const capdec_handle* h) { return h ? h->graph_captures : 0; }
+
 void capdec_destroy(capdec_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
-    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
     for (void* p : h->allocs) cudaFree(p);
     for (auto& kv : h->raw) cudaFree(kv.second.d);
     delete h;
@@ -1277,6 +1311,11 @@ static int create_impl(capdec_handle* h) {
     if (c.arch == CAPDEC_ARCH_AOA) CKS(h, dalloc(h, &h->mask_buf, static_cast<size_t>(h->Bmax) * h->Rmax));
     CKS(h, dalloc(h, &h->out_scores, h->Bmax));
     CKS(h, dalloc(h, &h->out_lengths, h->Bmax));
+    CKS(h, dalloc(h, &h->seed_dev, 1));
+    CKS(h, dalloc(h, &h->out_sample_tokens, static_cast<size_t>(M) * h->Tmax));
+    CKS(h, dalloc(h, &h->out_sample_logprobs, static_cast<size_t>(M) * h->Tmax));
+    CKS(h, dalloc(h, &h->out_greedy, static_cast<size_t>(h->Bmax) * h->Tmax));
+    CKS(h, dalloc(h, &h->forced_buf, static_cast<size_t>(M) * h->Tmax));
 
     if (c.arch == CAPDEC_ARCH_BUTD) {
         const int A = h->A, D = h->D;
@@ -1400,10 +1439,8 @@ int capdec_finalize_weights(capdec_handle* h, void* stream) {
         if (has_refiner_weights(h)) CKS(h, finalize_refiner(h, st));
     }
     CK(h, cudaStreamSynchronize(st));  // b_aff is read back; packing is a one-time load cost
-    if (h->graph_exec) {  // kernel parameters baked into the captured decode (e.g. b_aff) may have changed
-        cudaGraphExecDestroy(h->graph_exec);
-        h->graph_exec = nullptr;
-    }
+    for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);  // kernel parameters baked into a captured decode (e.g. b_aff) may have changed
+    h->graphs.clear();
     h->weights_ready = true;
     return CAPDEC_OK;
 }
@@ -1598,32 +1635,11 @@ int capdec_beam_search(capdec_handle* h, int32_t beam, int32_t max_seq, int32_t*
     // Not on the legacy default stream (cannot be captured), not while profiling, not with the attention-map output.
     if (!h->use_graphs || h->prof || alphas || st == nullptr)
         return enqueue_beam_search(h, beam, max_seq, tokens, seq_logprob, lengths, alphas, st);
-    const capdec_handle::GraphKey key{h->B, h->R, beam, max_seq, h->split ? static_cast<const void*>(h->feats) : nullptr,
-                                      h->mask != nullptr};
-    if (!h->graph_exec || !(key == h->graph_key)) {
-        if (h->graph_exec) {
-            cudaGraphExecDestroy(h->graph_exec);
-            h->graph_exec = nullptr;
-        }
-        cudaGraph_t graph = nullptr;
-        CK(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        const int64_t l0 = h->launches;
-        const int status = enqueue_beam_search(h, beam, max_seq, h->out_tokens, h->out_scores, h->out_lengths, nullptr, st);
-        const cudaError_t ce = cudaStreamEndCapture(st, &graph);
-        h->graph_launches = h->launches - l0;
-        h->launches = l0;
-        if (status != CAPDEC_OK) {
-            if (graph) cudaGraphDestroy(graph);
-            return status;
-        }
-        CK(h, ce);
-        const cudaError_t ie = cudaGraphInstantiate(&h->graph_exec, graph, 0);
-        cudaGraphDestroy(graph);
-        CK(h, ie);
-        h->graph_key = key;
-    }
-    CK(h, cudaGraphLaunch(h->graph_exec, st));
-    h->launches += h->graph_launches;
+    const capdec_handle::GraphKey key{capdec_handle::GK_BEAM, h->B, h->R, beam, max_seq, 0, 0,
+                                      h->split ? static_cast<const void*>(h->feats) : nullptr, h->mask != nullptr};
+    CKS(h, replay_graph(h, key, st, [&]() {
+        return enqueue_beam_search(h, beam, max_seq, h->out_tokens, h->out_scores, h->out_lengths, nullptr, st);
+    }));
     const int B = h->B;
     CK(h, cudaMemcpyAsync(tokens, h->out_tokens, static_cast<size_t>(B) * (max_seq + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     if (seq_logprob) CK(h, cudaMemcpyAsync(seq_logprob, h->out_scores, static_cast<size_t>(B) * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -1680,7 +1696,30 @@ static int enqueue_beam_search(capdec_handle* h, int32_t beam, int32_t max_seq, 
 }
 
 static int sample_impl(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t seed, int32_t max_seq, int32_t* tokens,
-                       float* logprobs, float* alphas, const int32_t* forced, cudaStream_t st, int32_t* greedy_tokens = nullptr);
+                       float* logprobs, float* alphas, const int32_t* forced, cudaStream_t st, int32_t* greedy_tokens = nullptr,
+                       const uint32_t* seed_ptr = nullptr);
+
+// Rollouts replay a captured graph like beam search does: the seed travels through device memory, the teacher-forced
+// words and the outputs through library-owned buffers (stable addresses), copied from / to the caller's around the launch.
+static int sample_entry(capdec_handle* h, int kind, int32_t mode, int32_t n, uint64_t seed, int32_t max_seq, int32_t* tokens,
+                        float* logprobs, float* alphas, const int32_t* forced, cudaStream_t st, int32_t* greedy_tokens = nullptr) {
+    if (!h->use_graphs || h->prof || alphas || st == nullptr)
+        return sample_impl(h, mode, n, seed, max_seq, tokens, logprobs, alphas, forced, st, greedy_tokens);
+    const int B = h->B, M = B * n, M_out = greedy_tokens ? B * (n - 1) : M;
+    set_u32_kernel<<<1, 1, 0, st>>>(h->seed_dev, static_cast<uint32_t>(seed & 0xFFFFFFFFu));
+    CK(h, cudaGetLastError());
+    if (forced) CK(h, cudaMemcpyAsync(h->forced_buf, forced, static_cast<size_t>(M) * max_seq * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    const capdec_handle::GraphKey key{kind, B, h->R, n, max_seq, mode, (tokens ? 1 : 0) | (logprobs ? 2 : 0),
+                                      h->split ? static_cast<const void*>(h->feats) : nullptr, h->mask != nullptr};
+    CKS(h, replay_graph(h, key, st, [&]() {
+        return sample_impl(h, mode, n, 0, max_seq, tokens ? h->out_sample_tokens : nullptr, logprobs ? h->out_sample_logprobs : nullptr,
+                           nullptr, forced ? h->forced_buf : nullptr, st, greedy_tokens ? h->out_greedy : nullptr, h->seed_dev);
+    }));
+    if (tokens) CK(h, cudaMemcpyAsync(tokens, h->out_sample_tokens, static_cast<size_t>(M_out) * max_seq * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    if (logprobs) CK(h, cudaMemcpyAsync(logprobs, h->out_sample_logprobs, static_cast<size_t>(M_out) * max_seq * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (greedy_tokens) CK(h, cudaMemcpyAsync(greedy_tokens, h->out_greedy, static_cast<size_t>(B) * max_seq * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    return CAPDEC_OK;
+}
 
 int capdec_sample(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t seed, int32_t max_seq, int32_t* tokens,
                   float* logprobs, float* alphas, void* stream) {
@@ -1691,7 +1730,8 @@ int capdec_sample(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t 
     if (mode != CAPDEC_SAMPLE_GREEDY && mode != CAPDEC_SAMPLE_MULTINOMIAL) return fail(h, CAPDEC_ERR_INVALID, "unknown sample mode");
     if (alphas && h->cfg.arch == CAPDEC_ARCH_NIC) return fail(h, CAPDEC_ERR_INVALID, "NIC has no attention maps; pass alphas = NULL");
     CK(h, cudaSetDevice(h->cfg.device));
-    return sample_impl(h, mode, n_per_image, seed, max_seq, tokens, logprobs, alphas, nullptr, static_cast<cudaStream_t>(stream));
+    return sample_entry(h, capdec_handle::GK_SAMPLE, mode, n_per_image, seed, max_seq, tokens, logprobs, alphas, nullptr,
+                        static_cast<cudaStream_t>(stream));
 }
 
 int capdec_scst_rollout(capdec_handle* h, int32_t n_per_image, uint64_t seed, int32_t max_seq, int32_t* sample_tokens,
@@ -1701,8 +1741,8 @@ int capdec_scst_rollout(capdec_handle* h, int32_t n_per_image, uint64_t seed, in
     if (n_per_image <= 0 || n_per_image + 1 > h->Kmax || max_seq <= 0 || max_seq > h->Tmax || !sample_tokens || !greedy_tokens)
         return fail(h, CAPDEC_ERR_INVALID, "scst_rollout: n_per_image + 1 must be <= max_rows; null outputs or max_seq out of range");
     CK(h, cudaSetDevice(h->cfg.device));
-    return sample_impl(h, CAPDEC_SAMPLE_MULTINOMIAL, n_per_image + 1, seed, max_seq, sample_tokens, sample_logprobs, nullptr, nullptr,
-                       static_cast<cudaStream_t>(stream), greedy_tokens);
+    return sample_entry(h, capdec_handle::GK_SCST, CAPDEC_SAMPLE_MULTINOMIAL, n_per_image + 1, seed, max_seq, sample_tokens,
+                        sample_logprobs, nullptr, nullptr, static_cast<cudaStream_t>(stream), greedy_tokens);
 }
 
 int capdec_score(capdec_handle* h, const int32_t* tokens, int32_t n_per_image, int32_t max_seq, float* logprobs, void* stream) {
@@ -1711,14 +1751,15 @@ int capdec_score(capdec_handle* h, const int32_t* tokens, int32_t n_per_image, i
     if (n_per_image <= 0 || n_per_image > h->Kmax || max_seq <= 0 || max_seq > h->Tmax || !tokens || !logprobs)
         return fail(h, CAPDEC_ERR_INVALID, "score: n_per_image / max_seq out of range or null tokens / logprobs");
     CK(h, cudaSetDevice(h->cfg.device));
-    return sample_impl(h, CAPDEC_SAMPLE_GREEDY, n_per_image, 0, max_seq, nullptr, logprobs, nullptr, tokens,
-                       static_cast<cudaStream_t>(stream));
+    return sample_entry(h, capdec_handle::GK_SCORE, CAPDEC_SAMPLE_GREEDY, n_per_image, 0, max_seq, nullptr, logprobs, nullptr, tokens,
+                        static_cast<cudaStream_t>(stream));
 }
 
 // greedy_tokens != null: the SCST pair of rollouts in one pass -- n_per_image rows per image of which the LAST is the greedy
 // rollout (written to greedy_tokens [B, T]); tokens / logprobs then hold the n_per_image - 1 sampled rows per image.
 static int sample_impl(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t seed, int32_t max_seq, int32_t* tokens,
-                       float* logprobs, float* alphas, const int32_t* forced, cudaStream_t st, int32_t* greedy_tokens) {
+                       float* logprobs, float* alphas, const int32_t* forced, cudaStream_t st, int32_t* greedy_tokens,
+                       const uint32_t* seed_ptr) {
     const int B = h->B, n = n_per_image, M = B * n;
     const int M_out = greedy_tokens ? B * (n - 1) : M;
     CKS(h, reset_state(h, M, st));
@@ -1742,6 +1783,7 @@ static int sample_impl(capdec_handle* h, int32_t mode, int32_t n_per_image, uint
     StepCtx c{};
     c.M = M, c.K = n, c.logits_epi = EPI_SAMPLE, c.ktop = 1;
     c.seed = static_cast<uint32_t>(seed & 0xFFFFFFFFu);
+    c.seed_ptr = seed_ptr;
     c.use_noise = s.multinomial;
     c.scst_n = greedy_tokens ? n - 1 : 0;
     c.forced = forced;

@@ -60,6 +60,7 @@ struct EpiParams {
     float* part;            // [M, n_tiles, PS] per-(row, N-tile) partials
     int n_tiles;
     uint32_t seed;          // SAMPLE: counter-based Gumbel noise (0 noise when use_noise == 0)
+    const uint32_t* seed_ptr;  // SAMPLE: when non-null the seed is read from device memory (captured rollouts)
     int step;
     int use_noise;
     int scst_n;             // SAMPLE, > 0: rows come in groups of scst_n sampled rollouts + ONE greedy rollout per image (the
@@ -538,7 +539,8 @@ struct DrawState {
             noisy = noisy && j < p.epi.scst_n;  // the last row of an image's group is its greedy rollout
             noise_row = img * p.epi.scst_n + j;
         }
-        rs = gumbel_row_step_hash(p.epi.seed, static_cast<uint32_t>(noise_row), static_cast<uint32_t>(p.epi.step));
+        const uint32_t seed = p.epi.seed_ptr ? __ldg(p.epi.seed_ptr) : p.epi.seed;
+        rs = gumbel_row_step_hash(seed, static_cast<uint32_t>(noise_row), static_cast<uint32_t>(p.epi.step));
         forced = (p.epi.forced && row < p.M) ? __ldg(p.epi.forced + static_cast<size_t>(row) * p.epi.forced_ld + p.epi.step) : -1;
     }
     __device__ __forceinline__ void tile(uint32_t taddr, int n_base, int c0, int c1, const GemmParams& p) {

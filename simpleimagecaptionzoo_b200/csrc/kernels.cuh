@@ -176,6 +176,8 @@ __global__ void __launch_bounds__(256) butd_ingest_kernel(const T* __restrict__ 
     }
 }
 
+__global__ void set_u32_kernel(uint32_t* p, uint32_t v) { *p = v; }
+
 __global__ void fill_f16_kernel(__half* p, size_t n, float v) {
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<size_t>(gridDim.x) * blockDim.x)

@@ -61,8 +61,10 @@ class B200Captioner:
         self._seed = sample_seed
         self._calls = 0
         if max_regions is None:
+            # Spatial: the CNN grid; AoADetection: adaptive bottom-up features carry 10-100 boxes per image
+            # (AoA_Engine.py:23-47 pads them and builds bu_masks); BUTDDetection: the fixed 36 boxes
             s = int(self.settings.get("enc_img_size", 0) or 0)
-            max_regions = s * s if model_type.endswith("Spatial") and s else 36
+            max_regions = s * s if model_type.endswith("Spatial") and s else (100 if model_type == "AoADetection" else 36)
         H, E = int(self.settings["hidden_dim"]), int(self.settings["embed_dim"])
         self.decoder = capdec.CaptionDecoder(
             self.arch, state_dict, hidden_dim=H, embed_dim=E, vocab_size=vocab_size,
@@ -127,23 +129,29 @@ class B200Captioner:
         tokens, self.last_scores, self.last_lengths = self.decoder.beam_search(beam_size, max_seq or self.max_seq)
         return tokens.long()
 
-    def beam_search_stream(self, batches, beam_size: int = 5, max_seq: Optional[int] = None):
+    def beam_search_stream(self, batches, beam_size: int = 5, max_seq: Optional[int] = None, slots: int = 3,
+                           on_device_tokens: Optional[Callable] = None):
         """Pipelined form of ``beam_search_sampler`` for a sequence of batches (what an evaluation loop feeds):
         yields one HOST int32 array [B, 1+max_seq] per input batch, in order.  The host->device copy of batch i+1
         runs on a copy stream while batch i decodes, and the captions of batch i are read back (pinned buffer,
         asynchronous) while batch i+1 is already enqueued -- the GPU never waits for the host.
-        ``batches`` yields ``visual_inputs`` dicts whose feature tensors may live on the host (ideally pinned)."""
+        ``batches`` yields ``visual_inputs`` dicts whose feature tensors may live on the host (ideally pinned).
+        ``slots`` device staging buffers are used in turn (>= 2); ``on_device_tokens(tokens)`` is called with every
+        batch's DEVICE caption tensor right after its decode was enqueued (multi-GPU: ``CaptionGather.add``)."""
         import collections
         torch = _torch()
         T = max_seq or self.max_seq
         main = torch.cuda.current_stream(self.device)
+        slots = max(2, int(slots))
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(self.device)
-            self._slots = [dict(buf=None, mask=None, free=None, ready=None) for _ in range(2)]
+            self._slots = []
+        while len(self._slots) < slots:
+            self._slots.append(dict(buf=None, mask=None, free=None, ready=None))
         copy = self._copy_stream
 
         def stage(i, visual_inputs):
-            slot = self._slots[i % 2]
+            slot = self._slots[i % slots]
             feats, mask = self._features(visual_inputs, to_device=False)
             with torch.cuda.stream(copy):
                 if slot["free"] is not None:
@@ -179,6 +187,8 @@ class B200Captioner:
             tokens, _, _ = self.decoder.beam_search(beam_size, T)
             cur["free"] = torch.cuda.Event()
             cur["free"].record(main)
+            if on_device_tokens is not None:
+                on_device_tokens(tokens)
             host = torch.empty(tokens.shape, dtype=tokens.dtype, pin_memory=True)
             host.copy_(tokens, non_blocking=True)
             done = torch.cuda.Event()
@@ -203,7 +213,7 @@ class B200Captioner:
         main = torch.cuda.current_stream(self.device)
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(self.device)
-            self._slots = [dict(buf=None, mask=None, free=None, ready=None) for _ in range(2)]
+            self._slots = []
         copy = self._copy_stream
         bufs, free = [dict(), dict()], [None, None]
 
@@ -366,7 +376,9 @@ class CaptionEngine:
         self.model.eval()
         ix2word = self.caption_vocab.ix2word
         result = []
-        if eval_beam_size != -1 and hasattr(self.model, "beam_search_stream"):
+        fn = getattr(self.model, "feature_fn", None)
+        host_ok = fn is None or getattr(fn, "accepts_host_inputs", False)  # a CUDA module as feature_fn needs device inputs
+        if eval_beam_size != -1 and hasattr(self.model, "beam_search_stream") and host_ok:
             # pipelined: copy of batch i+1 and caption read-back of batch i overlap the decode
             ids_q = []
 
@@ -459,10 +471,20 @@ class AoASpatial_Eng(CaptionEngine):
 ENGINES = {c.model_type: c for c in (NIC_Eng, BUTDSpatial_Eng, BUTDDetection_Eng, AoADetection_Eng, AoASpatial_Eng)}
 
 
-def install(engine, state_dict=None, **decoder_kwargs):
-    """Drop the extension into a LIVE reference ``Engine`` instance: the three decode methods of ``engine.model`` are
-    rebound to the B200 decoder built from the model's own ``state_dict`` (checkpoint loaded unchanged).  Training
-    methods are untouched.  See INTEGRATION.md."""
+def install(engine, state_dict=None, rebind_rl: bool = False, max_seq: int = 50, **decoder_kwargs):
+    """Drop the extension into a LIVE reference ``Engine`` instance: the EVALUATION-time decode methods of
+    ``engine.model`` -- ``sampler``, ``beam_search_sampler``, ``eval_test_image`` -- are rebound to the B200 decoder built
+    from the model's own ``state_dict`` (checkpoint loaded unchanged).  See INTEGRATION.md.
+
+    ``sampler_rl`` is the SCST TRAINING rollout (Engine.py:262): the reference calls it in train mode and back-propagates
+    through the log-probs it returns, which the extension's forward-only rollout cannot provide.  It is therefore left
+    alone unless ``rebind_rl=True``; even then the original method runs whenever autograd is recording and the model is
+    in training mode, so ``Engine.SCST_training_epoch`` keeps working on an installed engine.
+
+    ``max_seq`` is the beam-search step limit; the default is the reference's hard-coded 50 (BUTD_Model.py:260,
+    NIC_Model.py:169, AoA_Model.py:435).  ``max_regions`` (decoder keyword) bounds the boxes per image: default 36 for
+    BUTDDetection, 100 for AoADetection's adaptive features, the CNN grid for the Spatial models."""
+    torch = _torch()
     sd = state_dict if state_dict is not None else engine.model.state_dict()
     model_type = engine.settings["model_type"]
     feature_fn = None
@@ -478,9 +500,18 @@ def install(engine, state_dict=None, **decoder_kwargs):
     dev = str(engine.device)
     fast = B200Captioner(model_type, engine.settings, len(engine.caption_vocab), sd, feature_fn=feature_fn,
                          feature_fn_returns="bottom_up" if model_type == "AoASpatial" else "decoder_input",
-                         device=int(dev.split(":")[1]) if ":" in dev else 0, **decoder_kwargs)
-    ref.sampler, ref.sampler_rl, ref.beam_search_sampler = fast.sampler, fast.sampler_rl, fast.beam_search_sampler
+                         device=int(dev.split(":")[1]) if ":" in dev else 0, max_seq=max_seq, **decoder_kwargs)
+    ref.sampler, ref.beam_search_sampler = fast.sampler, fast.beam_search_sampler
     ref.eval_test_image = fast.eval_test_image
+    if rebind_rl:
+        original_rl = ref.sampler_rl
+
+        def sampler_rl(visual_inputs, max_len=20, **kw):
+            if torch.is_grad_enabled() and getattr(ref, "training", False):
+                return original_rl(visual_inputs, max_len=max_len)  # SCST training: needs dropout + an autograd graph
+            return fast.sampler_rl(visual_inputs, max_len=max_len, **kw)
+
+        ref.sampler_rl = sampler_rl
     return fast
 
 
@@ -520,6 +551,44 @@ def shard_bounds(n_images: int, rank: int, world: int):
     per = (n_images + world - 1) // world
     lo = min(rank * per, n_images)
     return lo, min(lo + per, n_images)
+
+
+class CaptionGather:
+    """One collective per EPOCH (north_star: "a single NCCL all-gather collects the captions"): every rank appends the
+    [B_local, L] device caption block of each batch it decodes (``add``: a stream-ordered device copy, no communication,
+    so the ranks never run in lock-step), and ``finish`` gathers all ranks' blocks with ONE ``all_gather_into_tensor``
+    and returns them in original image order: ``[steps, world * B_local, L]`` where batch s is the concatenation of the
+    ranks' shards of batch s in rank order (``shard_bounds``).  NCCL on GPUs, gloo on CPU for the tests."""
+
+    def __init__(self, steps: int, b_local: int, length: int, device, dtype=None, group=None):
+        torch = _torch()
+        self.group = group
+        self.buf = torch.zeros((steps, b_local, length), dtype=dtype or torch.int32, device=device)
+        self.n = 0
+
+    def reset(self):
+        self.n = 0
+
+    def add(self, tokens_local):
+        if self.n >= self.buf.shape[0]:
+            raise RuntimeError("CaptionGather: more batches than the epoch was sized for")
+        rows = tokens_local.shape[0]
+        self.buf[self.n, :rows].copy_(tokens_local, non_blocking=True)
+        if rows < self.buf.shape[1]:
+            self.buf[self.n, rows:].zero_()  # ragged last batch: <pad> rows
+        self.n += 1
+
+    def finish(self):
+        torch = _torch()
+        import torch.distributed as dist
+        steps, b, L = self.n, self.buf.shape[1], self.buf.shape[2]
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return self.buf[:steps]
+        world = dist.get_world_size(self.group)
+        mine = self.buf[:steps].contiguous()
+        out = torch.empty((world * steps, b, L), dtype=mine.dtype, device=mine.device)  # rank-major concatenation
+        dist.all_gather_into_tensor(out, mine, group=self.group)
+        return out.view(world, steps, b, L).permute(1, 0, 2, 3).reshape(steps, world * b, L)
 
 
 def all_gather_captions(tokens_local, n_images: int, group=None):

@@ -120,7 +120,9 @@ class FeatureShard:
         self.bboxes = (np.memmap(path, np.float32, "r", header["off_bboxes"], (self.N, self.R, 4))
                        if header["with_bboxes"] else None)
         self.feats = np.memmap(path, np.float16, "r", header["off_feats"], (self.N, self.R, self.D))
-        expect = max(header["off_feats"] + 2 * self.N * self.R * self.D, header["off_lens"] + 4 * self.N)
+        expect = max(header["off_feats"] + 2 * self.N * self.R * self.D, header["off_lens"] + 4 * self.N,
+                     header["off_ids"] + 8 * self.N,
+                     header["off_bboxes"] + 16 * self.N * self.R if header["with_bboxes"] else 0)
         if os.path.getsize(path) < expect:
             raise ValueError(f"{path} is truncated: {os.path.getsize(path)} < {expect} bytes")
 
@@ -137,12 +139,21 @@ class FeatureShard:
         ``BUTDDetection_Eng.modify_visual_inputs`` builds (BUTD_Engine.py:23-47).  The buffers belong to a ring of ``ring``
         slots refilled by a background thread.  A consumer that copies a batch asynchronously hands the copy's CUDA event
         to ``visual_inputs['_on_copied'](event)`` (``beam_search_stream`` does): the slot is not refilled before that event
-        has completed.  Other consumers must be done with a batch before they ask for the one after the next."""
+        has completed.  Other consumers must be done with a batch before they ask for the one after the next.  ``ring`` >= 2;
+        3 or more slots let the refill of the next batch overlap the consumer's work on the current two."""
         import torch
         stop = self.N if stop is None else min(stop, self.N)
         pin = pinned and torch.cuda.is_available()
+        if ring < 2:
+            raise ValueError("ring must be >= 2 (one slot with the consumer, one being filled)")
         slots = [torch.empty((batch_size, self.R, self.D), dtype=torch.float16, pin_memory=pin) for _ in range(ring)]
-        q: "queue.Queue" = queue.Queue(maxsize=max(ring - 2, 1))
+        q: "queue.Queue" = queue.Queue()
+        # Explicit hand-back of slots: the fill thread takes a slot from ``free`` (blocking), the consumer side returns
+        # the slot of batch k when batch k+2 is requested, together with the CUDA event of its asynchronous copy if one
+        # was registered -- so a slot is never rewritten under a pending or not-yet-issued copy, whatever ``ring`` is.
+        free: "queue.Queue" = queue.Queue()
+        for i in range(ring):
+            free.put((i, None))
         copied = [None] * ring  # CUDA event of the last asynchronous copy out of each slot
 
         def on_copied(slot):
@@ -152,33 +163,45 @@ class FeatureShard:
 
         def fill():
             try:
-                for k, lo in enumerate(range(start, stop, batch_size)):
+                for lo in range(start, stop, batch_size):
                     hi = min(lo + batch_size, stop)
-                    if copied[k % ring] is not None:
-                        copied[k % ring].synchronize()
-                        copied[k % ring] = None
-                    buf = slots[k % ring][:hi - lo]
+                    item = free.get()
+                    if item is None:  # the consumer went away
+                        return
+                    slot, event = item
+                    if event is not None:
+                        event.synchronize()
+                    buf = slots[slot][:hi - lo]
                     np.copyto(buf.numpy(), self.feats[lo:hi])  # page-cache -> pinned memory, no decompression
                     lens = np.asarray(self.lengths[lo:hi])
                     mask = None
                     if (lens != self.R).any():
                         mask = torch.from_numpy((np.arange(self.R)[None, :] < lens[:, None]).astype(np.float32))
                     boxes = None if self.bboxes is None else [np.asarray(self.bboxes[i, :lens[i - lo]]) for i in range(lo, hi)]
-                    q.put((np.asarray(self.image_ids[lo:hi]),
-                           {"bu_feats": buf, "bu_bboxes": boxes, "bu_masks": mask, "_on_copied": on_copied(k % ring)}))
+                    q.put((slot, (np.asarray(self.image_ids[lo:hi]),
+                                  {"bu_feats": buf, "bu_bboxes": boxes, "bu_masks": mask, "_on_copied": on_copied(slot)})))
                 q.put(None)
             except BaseException as e:  # noqa: BLE001  (surface loader errors in the consumer)
                 q.put(e)
 
         t = threading.Thread(target=fill, daemon=True)
         t.start()
-        while True:
-            item = q.get()
-            if item is None:
-                break
-            if isinstance(item, BaseException):
-                raise item
-            yield item
+        held = []  # slots of the batches the consumer may still be using (the last two yielded)
+        try:
+            while True:
+                if len(held) == 2:  # asking for batch k+2 releases batch k
+                    s0 = held.pop(0)
+                    free.put((s0, copied[s0]))
+                    copied[s0] = None
+                item = q.get()
+                if item is None:
+                    break
+                if isinstance(item, BaseException):
+                    raise item
+                held.append(item[0])
+                yield item[1]
+        finally:
+            free.put(None)
         t.join()
 
 

@@ -50,6 +50,45 @@ def test_ragged_features_give_masks_and_batches(tmp_path):
     assert seen == ids  # file order, last batch short
 
 
+@pytest.mark.parametrize("ring", [2, 3, 5])
+def test_ring_slots_are_never_rewritten_under_the_consumer(tmp_path, ring):
+    """The slot of batch k goes back to the fill thread only when batch k+2 is requested (and after the consumer's
+    registered copy event): a consumer that holds the last two batches always sees their own rows, for every ring size."""
+    pytest.importorskip("torch")
+    path, feats, ids = _write(tmp_path, n=23, seed=2)
+    sh = fs.FeatureShard(path)
+
+    class Event:  # stands in for the CUDA event beam_search_stream registers
+        def __init__(self):
+            self.synced = False
+
+        def synchronize(self):
+            self.synced = True
+
+    held, events = [], []
+    for image_ids, vi in sh.batches(2, pinned=False, ring=ring):
+        ev = Event()
+        vi["_on_copied"](ev)
+        events.append(ev)
+        held.append((list(image_ids), vi["bu_feats"]))
+        for hid, buf in held[-2:]:  # the two batches a consumer may still be using
+            for b, image_id in enumerate(hid):
+                assert np.array_equal(buf[b].numpy(), feats[ids.index(int(image_id))].astype(np.float16))
+    assert [i for h, _ in held for i in h] == ids
+    assert all(e.synced for e in events[:max(0, len(events) - ring - 1)])  # refilled slots waited for their copy
+    with pytest.raises(ValueError):
+        next(sh.batches(2, pinned=False, ring=1))
+
+
+def test_truncated_shard_is_rejected(tmp_path):
+    path, _, _ = _write(tmp_path, n=6)
+    size = __import__("os").path.getsize(path)
+    with open(path, "r+b") as f:
+        f.truncate(size - 8)  # cuts into the last block of the file
+    with pytest.raises(ValueError):
+        fs.FeatureShard(path)
+
+
 def test_writer_rejects_bad_rows(tmp_path):
     w = fs.FeatureShardWriter(str(tmp_path / "x.shard"), 4, 8)
     with pytest.raises(ValueError):

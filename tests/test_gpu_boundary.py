@@ -1,0 +1,204 @@
+"""GPU tests of the drop-in boundary proper: ``engine.install()`` on a live (stand-in) reference Engine, the captioner's
+``sampler_rl`` wrapper, the captured-decode cache, and the direct agreement with the reference's captions on the committed
+agreement sets.  Everything goes through the C ABI."""
+import os
+import types
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import capdec_oracle as orc  # noqa: E402
+from tests import agreement_util as au  # noqa: E402
+from tests.golden_util import load_case, rebuild  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+class _Vocab:
+    def __init__(self, n):
+        self.ix2word = {0: "<pad>", 1: "<sta>", 2: "<end>", 3: "<unk>", **{i: f"w{i}" for i in range(4, n)}}
+
+    def __len__(self):
+        return len(self.ix2word)
+
+
+class _RefModel(torch.nn.Module):
+    """Stands in for the reference's ``BUTDDetection_Captioner``: the same ``state_dict()`` a loaded checkpoint gives
+    (Engine.py:43-70) and the four methods ``install`` may rebind (here they only record that they were called)."""
+
+    def __init__(self, sd):
+        super().__init__()
+        self._sd = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
+        self.called = []
+
+    def state_dict(self, *a, **k):
+        return dict(self._sd)
+
+    def sampler(self, visual_inputs, max_len=20):
+        self.called.append("sampler")
+
+    def sampler_rl(self, visual_inputs, max_len=20):
+        self.called.append("sampler_rl")
+        return "reference rollout"
+
+    def beam_search_sampler(self, visual_inputs, beam_size=5):
+        self.called.append("beam_search_sampler")
+
+    def eval_test_image(self, *a, **k):
+        self.called.append("eval_test_image")
+
+
+def _live_engine(name):
+    meta, gold = load_case(name)
+    sd, feats, mask = rebuild(meta)
+    d = meta["dims"]
+    eng = types.SimpleNamespace(
+        model=_RefModel(sd), device="cuda:0", caption_vocab=_Vocab(d["vocab_size"]),
+        settings=dict(model_type="BUTDDetection", embed_dim=d["embed_dim"], hidden_dim=d["hidden_dim"], atten_dim=d["atten_dim"]))
+    return eng, meta, gold, feats, d
+
+
+def test_install_rebinds_the_eval_methods_of_a_live_engine():
+    """INTEGRATION.md section 3 / Main.py:111-129: after ``install(engine)`` the model's eval-time decode methods give the
+    reference's golden outputs; ``sampler_rl`` (the SCST training rollout) is left alone."""
+    from simpleimagecaptionzoo_b200 import engine
+    eng, meta, gold, feats, d = _live_engine("butd_tiny_k3")
+    fast = engine.install(eng, max_seq=meta["T"], max_batch=meta["B"], max_regions=meta["R"], max_rows=meta["K"],
+                          enc_dim=d["enc_dim"], math="f16x3")
+    vi = {"bu_feats": torch.from_numpy(feats).cuda(), "bu_bboxes": None, "bu_masks": None}
+    tok = eng.model.beam_search_sampler(vi, beam_size=meta["K"])
+    assert tok.dtype == torch.int64 and tuple(tok.shape) == (meta["B"], 1 + meta["T"])
+    o = orc.make_decoder("BUTD", rebuild(meta)[0])
+    o.prepare(feats)
+    res = orc.beam_search_batched(o, meta["K"], meta["T"])
+    verdict = orc.agreement(tok.cpu().numpy(), gold["tokens"], res.min_gap, tol=1e-4)
+    assert "diff" not in verdict and np.mean([v == "exact" for v in verdict]) >= 0.95, verdict
+    greedy = eng.model.sampler(vi, max_len=meta["T"])
+    assert greedy.dtype == torch.int64 and (greedy.cpu().numpy() == gold["greedy"]).all(1).mean() >= 0.95
+    assert eng.model.sampler_rl(vi, max_len=meta["T"]) == "reference rollout"  # not rebound by default
+    assert eng.model.called == ["sampler_rl"]  # ... and none of the rebound methods reached the reference's code
+    # single-image test path: caption words + attention maps of the generated words
+    words, alphas = eng.model.eval_test_image({"bu_feats": vi["bu_feats"][:1], "bu_masks": None}, eng.caption_vocab,
+                                              max_len=meta["T"], eval_beam_size=meta["K"])
+    want = orc.ids_to_caption(gold["tokens"][0], eng.caption_vocab.ix2word).split()
+    if verdict[0] == "exact":
+        assert words == want
+    assert len(alphas) == 1 and alphas[0].shape[0] == 1 and alphas[0].shape[2] == meta["R"]
+    assert torch.allclose(alphas[0].sum(-1), torch.ones_like(alphas[0].sum(-1)), atol=1e-3)
+    fast.decoder.close()
+
+
+def test_install_with_rebind_rl_keeps_scst_training_on_the_reference_path():
+    """an installed engine must still train.  With ``rebind_rl=True`` the fast rollout serves no-grad / eval
+    calls; with autograd recording and the model in training mode the reference's own ``sampler_rl`` runs."""
+    from simpleimagecaptionzoo_b200 import engine
+    eng, meta, gold, feats, d = _live_engine("butd_tiny_k3")
+    fast = engine.install(eng, rebind_rl=True, max_seq=meta["T"], max_batch=meta["B"], max_regions=meta["R"], max_rows=meta["K"],
+                          enc_dim=d["enc_dim"], math="f16x3")
+    vi = {"bu_feats": torch.from_numpy(feats).cuda(), "bu_bboxes": None, "bu_masks": None}
+    eng.model.train()
+    with torch.enable_grad():
+        assert eng.model.sampler_rl(vi, max_len=meta["T"]) == "reference rollout"
+    assert eng.model.called == ["sampler_rl"]
+    eng.model.eval()
+    with torch.no_grad():
+        seq, logp = eng.model.sampler_rl(vi, max_len=meta["T"], n_per_image=meta["n_samples"], seed=meta["sample_seed"])
+    assert eng.model.called == ["sampler_rl"]
+    n = meta["n_samples"]
+    assert seq.dtype == torch.int64 and tuple(seq.shape) == (meta["B"] * n, meta["T"]) and tuple(logp.shape) == tuple(seq.shape)
+    same = (seq.cpu().numpy().reshape(meta["B"], n, -1) == gold["sample_seq"]).all(2)
+    assert same.mean() >= 0.95
+    err = np.abs(logp.cpu().numpy().reshape(meta["B"], n, -1) - gold["sample_logprobs"])[same]
+    assert err.max() < 1e-3
+    fast.decoder.close()
+
+
+def test_captioner_sampler_rl_and_scst_rollouts_wrappers():
+    """``B200Captioner.sampler_rl`` / ``scst_rollouts`` == the decoder calls they wrap == the reference's golden rollout."""
+    from simpleimagecaptionzoo_b200 import capdec, engine
+    meta, gold = load_case("butd_tiny_k3")
+    sd, feats, _ = rebuild(meta)
+    d = meta["dims"]
+    n = meta["n_samples"]
+    cap = engine.B200Captioner("BUTDDetection", dict(embed_dim=d["embed_dim"], hidden_dim=d["hidden_dim"], atten_dim=d["atten_dim"]),
+                               d["vocab_size"], sd, max_batch=meta["B"], max_regions=meta["R"], max_rows=n + 1, max_seq=meta["T"],
+                               math="f16x3", enc_dim=d["enc_dim"])
+    vi = {"bu_feats": torch.from_numpy(feats).cuda()}
+    seq, logp = cap.sampler_rl(vi, max_len=meta["T"], n_per_image=n, seed=meta["sample_seed"])
+    tok, lp = cap.decoder.sample(capdec.SAMPLE_MULTINOMIAL, n, meta["sample_seed"], meta["T"])
+    assert torch.equal(seq, tok.long()) and torch.equal(logp, lp)
+    assert (seq.cpu().numpy().reshape(meta["B"], n, -1) == gold["sample_seq"]).all(2).mean() >= 0.95
+    greedy, seq2, logp2 = cap.scst_rollouts(vi, max_len=meta["T"], n_per_image=n, seed=meta["sample_seed"])
+    assert torch.equal(seq2, seq) and torch.allclose(logp2, logp, atol=1e-5)
+    assert torch.equal(greedy, cap.sampler(vi, max_len=meta["T"]))
+    # consecutive calls without a seed draw from different streams
+    a, _ = cap.sampler_rl(vi, max_len=meta["T"])
+    b, _ = cap.sampler_rl(vi, max_len=meta["T"])
+    assert not torch.equal(a, b)
+    cap.decoder.close()
+
+
+def test_decode_graph_cache_serves_alternating_shapes(monkeypatch):
+    """A ragged last batch, alternating beam sizes and the rollouts each capture ONCE (8-entry cache); replayed results are
+    identical to eager launches (CAPDEC_NO_GRAPH=1)."""
+    from simpleimagecaptionzoo_b200 import capdec
+    meta, gold = load_case("butd_tiny_k3")
+    sd, feats, _ = rebuild(meta)
+    d = meta["dims"]
+    kw = dict(hidden_dim=d["hidden_dim"], embed_dim=d["embed_dim"], vocab_size=d["vocab_size"], atten_dim=d["atten_dim"],
+              enc_dim=d["enc_dim"], max_batch=meta["B"], max_regions=meta["R"], max_rows=5, max_seq=meta["T"], math="f16x3")
+    ft = torch.from_numpy(feats).cuda()
+
+    def run(dec):
+        out = []
+        for B, K in ((meta["B"], 3), (5, 3), (meta["B"], 2), (meta["B"], 3), (5, 3), (meta["B"], 2)):
+            dec.prepare(ft[:B])
+            out.append(dec.beam_search(K, meta["T"])[0].clone())
+        for seed in (11, 12, 11):
+            out += [t.clone() for t in dec.sample(capdec.SAMPLE_MULTINOMIAL, 2, seed, meta["T"])]
+        out += [t.clone() for t in dec.sample(capdec.SAMPLE_GREEDY, 1, 0, meta["T"])]
+        out += [t.clone() for t in dec.scst_rollout(2, 11, meta["T"])]
+        out.append(dec.score(out[-3], 2).clone())  # re-score the sampled rows of the one-pass rollout
+        torch.cuda.synchronize()
+        return out
+
+    dec = capdec.CaptionDecoder("BUTD", sd, **kw)
+    got = run(dec)
+    # beam: (B,3) (5,3) (B,2); multinomial n=2; greedy; scst; score
+    assert dec.graph_captures == 7, dec.graph_captures
+    got2 = run(dec)
+    assert dec.graph_captures == 7
+    dec.close()
+    monkeypatch.setenv("CAPDEC_NO_GRAPH", "1")
+    eager = capdec.CaptionDecoder("BUTD", sd, **kw)
+    want = run(eager)
+    assert eager.graph_captures == 0
+    eager.close()
+    for a, b, c in zip(got, got2, want):
+        assert torch.equal(a, c) and torch.equal(b, c)
+    assert torch.equal(got[9], got[13]) and not torch.equal(got[9], got[11])  # same seed same rollout, other seed another one
+    assert torch.allclose(got[-1], got[-3], atol=1e-4)  # the re-scored log-probs are the rollout's own
+
+
+AGREEMENT = [
+    # set, images, math, required exact-or-tie fraction vs the reference's own tokens
+    ("butd", 5000, "f16", 0.99),
+    ("butd", 5000, "f16x3", 0.999),
+    ("aoa_bu", 1000, "f16", 0.95),
+    ("aoa_bu", 1000, "f16x3", 0.99),
+]
+
+
+@pytest.mark.parametrize("name,images,math,need", AGREEMENT)
+def test_agreement_with_the_reference_tokens(name, images, math, need):
+    """north_star's agreement target, measured DIRECTLY against captions the reference's own code produced."""
+    if not os.path.exists(au.set_path(name, images)):
+        pytest.skip(f"{au.set_path(name, images)} not generated (tests/golden/make_agreement_set.py)")
+    r = au.evaluate(name, images, math)
+    assert r["exact_or_tie_frac"] >= need, {k: v for k, v in r.items() if k != "diffs"}
+    # every remaining difference sits where the reference's own top-(k+1) gap is inside the mode's operand-rounding error
+    bound = 2e-2 if math == "f16" else 1e-3
+    wide = [x for x in r["diffs"] if x["min_gap_up_to_step"] >= bound]
+    assert len(wide) <= max(1, images // 1000), wide

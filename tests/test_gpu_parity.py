@@ -16,7 +16,10 @@ pytestmark = pytest.mark.gpu
 
 TINY = case_names("tiny")
 FULL = case_names("full")
-F16_SCORE_BOUND = 5e-2   # stated bound on |seq log-prob error| for single-pass fp16 operands at full dims (T=20)
+# Stated bounds on |sequence log-prob error| of the single-pass fp16 mode at full dims, T = 20 (north_star: "a stated bound
+# for bf16"): measured maxima are 6.0e-3 over 5000 BUTD images and 1.12e-2 over 1000 AoA images (profiles/*agreement*.json).
+F16_SCORE_BOUND = 1e-2
+F16_AOA_SCORE_BOUND = 2e-2
 
 
 def _capdec():
@@ -115,9 +118,8 @@ def test_beam_search_fp16_mode_full_dims():
     for name in FULL:
         v, err = _fp16_verdicts(name)
         verdicts += v
-        worst = max(worst, err)
+        assert err <= (F16_AOA_SCORE_BOUND if name.startswith("aoa") else F16_SCORE_BOUND), (name, err)
     assert np.mean([v != "diff" for v in verdicts]) >= 0.90, verdicts
-    assert worst <= F16_SCORE_BOUND, worst
 
 
 @pytest.mark.parametrize("name", TINY + FULL)
@@ -372,8 +374,8 @@ def test_bottom_up_to_caption_fp32_grade(name):
 
 
 def test_bottom_up_fp16_mode_full_dims():
-    """Throughput mode at BASELINE dims: captions from bottom-up features agree with the oracle or are tie-justified at the
-    fp16 operand-rounding level (gap below the stated score bound)."""
+    """Throughput mode at BASELINE dims: captions from bottom-up features agree with the oracle or are tie-justified
+    (north_star's 1e-4 rule); scores of the agreeing captions within the stated fp16 bound."""
     meta, gold = load_case("aoaref_full_k3")
     dec, sd, bu, mask = _make_refiner(meta, "f16")
     tok, score, _ = dec.beam_search(meta["K"], meta["T"])
@@ -381,10 +383,15 @@ def test_bottom_up_fp16_mode_full_dims():
     o = orc.make_decoder("AOA", sd, num_heads=meta["dims"]["num_heads"])
     o.prepare(orc.aoa_project_refine(sd, bu, mask, num_heads=meta["dims"]["num_heads"]), mask)
     res = orc.beam_search_batched(o, meta["K"], meta["T"])
-    verdict = orc.agreement(tok.cpu().numpy(), res.tokens, res.min_gap, tol=F16_SCORE_BOUND)
-    assert "diff" not in verdict, verdict
+    verdict = orc.agreement(tok.cpu().numpy(), res.tokens, res.min_gap, tol=1e-4)
+    # 4 images: a caption may legitimately flip where the oracle's gap is inside the fp16 rounding error, but never more than one
+    assert sum(v == "diff" for v in verdict) <= 1, verdict
+    for b, v in enumerate(verdict):
+        if v == "diff":  # ... and then only at a gap below the stated fp16 bound
+            t = int(np.argmax(tok[b].cpu().numpy() != res.tokens[b]))
+            assert res.min_gap[b, :max(t, 1)].min() < F16_AOA_SCORE_BOUND, (b, t, res.min_gap[b])
     exact = np.array([v == "exact" for v in verdict])
-    assert np.allclose(score.cpu().numpy()[exact], res.scores[exact], atol=F16_SCORE_BOUND)
+    assert np.allclose(score.cpu().numpy()[exact], res.scores[exact], atol=F16_AOA_SCORE_BOUND)
     dec.close()
 
 

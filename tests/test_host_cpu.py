@@ -111,6 +111,61 @@ def test_all_gather_captions_world_size_2_gloo(tmp_path):
         assert p.returncode == 0, o
 
 
+_EPOCH_GATHER_SCRIPT = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+from simpleimagecaptionzoo_b200.engine import CaptionGather
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank, steps, b, L = dist.get_rank(), 3, 4, 5
+# global batch s = rows [s*8, s*8+8): rank r decodes rows [s*8 + r*4, s*8 + r*4 + 4); the last batch of rank 1 is ragged (3 rows)
+full = torch.arange(steps * 2 * b * L, dtype=torch.int32).reshape(steps, 2 * b, L) + 1
+g = CaptionGather(steps, b, L, "cpu")
+for s in range(steps):
+    blk = full[s, rank * b:(rank + 1) * b]
+    g.add(blk[:3] if (s == steps - 1 and rank == 1) else blk)
+out = g.finish()
+want = full.clone()
+want[steps - 1, 2 * b - 1] = 0  # the missing row of the ragged batch is <pad>
+assert out.shape == (steps, 2 * b, L) and torch.equal(out, want), out
+try:
+    g.add(full[0, :b])
+    raise SystemExit("overflow not detected")
+except RuntimeError:
+    pass
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_epoch_caption_gather_world_size_2_gloo(tmp_path):
+    """One all-gather per epoch (CaptionGather): [steps, world * B_local, L] in original image order, ragged last batch."""
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "epoch_gather.py"
+    script.write_text(_EPOCH_GATHER_SCRIPT.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+
+
+def test_caption_gather_single_process():
+    import torch
+    from simpleimagecaptionzoo_b200.engine import CaptionGather
+    g = CaptionGather(2, 3, 4, "cpu")
+    a, b = torch.ones(3, 4, dtype=torch.int32), torch.full((3, 4), 7, dtype=torch.int32)
+    g.add(a)
+    g.add(b)
+    assert torch.equal(g.finish(), torch.stack([a, b]))
+    g.reset()
+    g.add(b)
+    assert g.finish().shape == (1, 3, 4)
+
+
 def test_bottom_up_collate_matches_reference_shapes():
     """ModelEngines/BUTD_Engine.py:23-47: fixed 36-box features -> mask None; ragged boxes -> {0,1} mask."""
     import torch

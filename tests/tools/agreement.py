@@ -1,13 +1,9 @@
 #!/usr/bin/env python
-"""Caption agreement of the throughput math mode (fp16 operands) with the reference algorithm on many synthetic
-images (north_star: >= 90 % exact-or-tie-justified on 5k images).
+"""Caption agreement of both math modes with the REFERENCE's own tokens on the committed agreement sets (north_star:
+>= 90 % exact-or-tie-justified on 5k synthetic images) -- a direct comparison: tests/golden/agree_*.npz hold the captions
+the reference's code produced for these images (tests/golden/make_agreement_set.py) and the tie mask of the 1e-4 rule.
 
-The reference is too slow to decode thousands of images on the box's CPU (about 7 captions/s), so the check is
-staged: (1) the fp32-grade CUDA mode (f16x3) is validated against the numpy oracle on a random sample and on every
-image where the two CUDA modes disagree; (2) the fp16 mode is compared with f16x3 on all images; disagreements are
-classified with the oracle's top-(k+1) gaps (tie-justified if a gap < 1e-4 occurs at or before the first divergence).
-
-    python tests/tools/agreement.py [--images 5000] [--arch BUTD] [--beam 3] [--out gpurun_out/agreement.json]
+    python tests/tools/agreement.py [--set butd --images 5000] [--out gpurun_out/agreement.json]
 """
 import argparse
 import json
@@ -15,101 +11,31 @@ import os
 import sys
 import time
 
-import numpy as np
-import torch
-
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
-from oracle import capdec_oracle as orc  # noqa: E402
-from simpleimagecaptionzoo_b200 import capdec, synth  # noqa: E402
+from tests import agreement_util as au  # noqa: E402
 
 
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--set", default="butd", choices=sorted(au.SETS))
     ap.add_argument("--images", type=int, default=5000)
-    ap.add_argument("--arch", default="BUTD", choices=["BUTD", "NIC", "AOA"])
-    ap.add_argument("--beam", type=int, default=3)
-    ap.add_argument("--regions", type=int, default=36)
-    ap.add_argument("--max-seq", type=int, default=20)
-    ap.add_argument("--oracle-sample", type=int, default=48)
-    ap.add_argument("--chunk", type=int, default=1000)
-    ap.add_argument("--bottom-up", action="store_true",
-                    help="AOA: start from 36x2048 bottom-up features (img_feats_porjection + aoa_refine + decoder in the library)")
-    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "agreement.json"))
+    ap.add_argument("--out", default=None)
     args = ap.parse_args()
-
-    dims = synth.DIMS[args.arch]
-    sd = synth.make_state_dict(args.arch, seed=0, **dims)
-    bottom_up = args.bottom_up and args.arch == "AOA"
-    if bottom_up:
-        sd.update(synth.make_refiner_state_dict(hidden_dim=dims["hidden_dim"], enc_dim=2048, seed=0))
-    K, T, R = args.beam, args.max_seq, args.regions
-    kw = dict(hidden_dim=dims["hidden_dim"], embed_dim=dims["embed_dim"], vocab_size=dims["vocab_size"],
-              atten_dim=dims.get("atten_dim", 0), enc_dim=dims.get("enc_dim", 2048), num_heads=dims.get("num_heads", 8),
-              max_batch=args.chunk, max_regions=max(R, 1), max_rows=K, max_seq=T)
-    fast = capdec.CaptionDecoder(args.arch, sd, math="f16", **kw)
-    exact = capdec.CaptionDecoder(args.arch, sd, math="f16x3", **kw)
-    o = orc.make_decoder(args.arch, sd)
-
-    def feats_for(lo, n):
-        if args.arch == "BUTD" or bottom_up:
-            return synth.make_region_feats(n, R, dims.get("enc_dim", 2048), 7000 + lo)
-        if args.arch == "NIC":
-            return synth.make_image_embed(n, dims["embed_dim"], 7000 + lo)
-        return synth.make_refined_feats(n, R, dims["hidden_dim"], 7000 + lo)
-
-    rng = np.random.default_rng(0)
-    n_same = n_tie = n_diff = 0
-    n_x3_checked = n_x3_exact = n_x3_tie = 0
-    score_err = []
-    t0 = time.time()
-    for lo in range(0, args.images, args.chunk):
-        n = min(args.chunk, args.images - lo)
-        f = feats_for(lo, n)
-        ft = torch.from_numpy(f).cuda()
-        (fast.prepare_bottom_up if bottom_up else fast.prepare)(ft)
-        tf, sf, _ = fast.beam_search(K, T)
-        (exact.prepare_bottom_up if bottom_up else exact.prepare)(ft)
-        tx, sx, _ = exact.beam_search(K, T)
-        torch.cuda.synchronize()
-        tf, tx, sf, sx = tf.cpu().numpy(), tx.cpu().numpy(), sf.cpu().numpy(), sx.cpu().numpy()
-        same = (tf == tx).all(1)
-        score_err.append(np.abs(sf[same] - sx[same]))
-        n_same += int(same.sum())
-        bad = np.nonzero(~same)[0]
-        sample = rng.choice(np.nonzero(same)[0], size=min(args.oracle_sample * n // args.images + 1, int(same.sum())), replace=False)
-        for i in list(bad) + list(sample):
-            o.prepare(orc.aoa_project_refine(sd, f[i:i + 1]) if bottom_up else f[i:i + 1])
-            res = orc.beam_search_batched(o, K, T)
-            vx = orc.agreement(tx[i:i + 1], res.tokens, res.min_gap, tol=1e-4)[0]
-            n_x3_checked += 1
-            n_x3_exact += vx == "exact"
-            n_x3_tie += vx == "tie"
-            if i in bad:
-                vf = orc.agreement(tf[i:i + 1], res.tokens, res.min_gap, tol=1e-4)[0]
-                if vf == "exact":
-                    n_same += 1  # f16 agrees with the oracle, f16x3 took the other side of a tie
-                elif vf == "tie":
-                    n_tie += 1
-                else:
-                    n_diff += 1
-        print(f"[{lo + n}/{args.images}] exact={n_same} tie={n_tie} diff={n_diff}  f16x3 vs oracle: {n_x3_exact}+{n_x3_tie}tie/{n_x3_checked}"
-              f"  ({time.time() - t0:.0f}s)", flush=True)
-    score_err = np.concatenate(score_err)
-    out = {
-        "arch": args.arch, "from_bottom_up_features": bottom_up, "images": args.images, "beam": K, "max_seq": T, "regions": R, "vocab": dims["vocab_size"],
-        "f16_vs_reference": {"exact": n_same, "tie_justified": n_tie, "diff": n_diff,
-                             "exact_or_tie_frac": (n_same + n_tie) / args.images, "exact_frac": n_same / args.images},
-        "f16x3_vs_oracle": {"checked": n_x3_checked, "exact": int(n_x3_exact), "tie_justified": int(n_x3_tie),
-                            "note": "every image where the two CUDA modes disagree + a random sample of the others"},
-        "f16_seq_logprob_abs_err_vs_f16x3": {"max": float(score_err.max()), "p99": float(np.quantile(score_err, 0.99)),
-                                             "mean": float(score_err.mean())},
-        "tie_tolerance": 1e-4, "seconds": time.time() - t0,
-    }
-    os.makedirs(os.path.dirname(args.out), exist_ok=True)
-    json.dump(out, open(args.out, "w"), indent=1)
-    print(json.dumps(out))
+    out = {}
+    for math in ("f16", "f16x3"):
+        t0 = time.time()
+        r = au.evaluate(args.set, args.images, math)
+        r["seconds"] = time.time() - t0
+        gaps = sorted(d["min_gap_up_to_step"] for d in r["diffs"])
+        r["diff_gap_quantiles"] = {"min": gaps[0], "median": gaps[len(gaps) // 2], "max": gaps[-1]} if gaps else None
+        out[math] = r
+        print(f"{args.set} {math}: exact {r['exact']} tie {r['tie_justified']} diff {r['diff']} of {r['images']}"
+              f" -> {r['exact_or_tie_frac']:.4f}  diff gaps {r['diff_gap_quantiles']}", flush=True)
+    path = args.out or os.path.join(ROOT, "gpurun_out", f"agreement_{args.set}_{args.images}.json")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    json.dump(out, open(path, "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -8,12 +8,12 @@ python -m pytest tests -m gpu -x -q > gpurun_out/pytest_${tag}.log 2>&1; echo "p
 tail -3 gpurun_out/pytest_${tag}.log
 python bench.py "$@" > gpurun_out/bench_${tag}.json 2> gpurun_out/bench_${tag}.err; echo "bench rc=$?"
 tail -c 3000 gpurun_out/bench_${tag}.json; tail -5 gpurun_out/bench_${tag}.err
-python bench.py --steps 1 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/plain_${tag}.log 2>&1 &&
+python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras "$@" > gpurun_out/plain_${tag}.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_${tag}.csv \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/ncu_list_${tag}.log 2>&1
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras "$@" > gpurun_out/ncu_list_${tag}.log 2>&1
 echo "ncu list rc=$?"
 # one decode step = 6 launches (TD-LSTM, dec_att, attention, LM-LSTM, logits, beam_step); skip warm-up decodes
 ncu --set full --clock-control none --import-source on -k regex:'gemm2_kernel|attention|beam_step' -s 380 -c 6 -o gpurun_out/prof_${tag} -f \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/ncu_full_${tag}.log 2>&1
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras "$@" > gpurun_out/ncu_full_${tag}.log 2>&1
 echo "ncu full rc=$?"
 ls -la gpurun_out | tail -8
