@@ -189,6 +189,10 @@ int64_t capdec_launch_count(const capdec_handle* h);
  * replaced -- so a ragged last batch or alternating beam sizes capture once each. */
 int64_t capdec_graph_captures(const capdec_handle* h);
 
+/* Tuning hook (CAPDEC_TRACE=1 in the environment at create): %globaltimer stamps CTA 0 of the small-batch GEMM kernel took
+ * along its phases -- dst[0] = launches recorded, then 16 stamps (ns) per launch; resets the launch counter.  HOST buffer. */
+int capdec_debug_trace(capdec_handle* h, uint64_t* dst, int64_t n);
+
 /* Per-launch timing for bench.py's roofline line: while enabled, every kernel the handle launches is bracketed by
  * CUDA events on the launching stream.  capdec_profile_read waits for the recorded events and returns, per
  * category, the summed device time (ms), the algorithmic FLOPs of the GEMM launches (2*M*N*K, one pass) and the

@@ -27,7 +27,7 @@ SYMBOLS = (
     "capdec_test_gemm", "capdec_profile", "capdec_profile_read", "capdec_test_gemm_time",
     "capdec_prepare_bottom_up", "capdec_get_refined", "capdec_score", "capdec_prepare_f16", "capdec_scst_rollout",
     "capdec_cider_create", "capdec_cider_destroy", "capdec_cider_last_error", "capdec_cider_ngram_key", "capdec_cider_set_df",
-    "capdec_cider_reward", "capdec_graph_captures",
+    "capdec_cider_reward", "capdec_graph_captures", "capdec_debug_trace",
 )
 CATEGORIES = ("gemm_lstm", "gemm_store", "gemm_glu", "gemm_logits", "attention", "bookkeeping", "other")
 
@@ -81,6 +81,7 @@ def load_library(path: str = LIB_PATH) -> ctypes.CDLL:
     lib.capdec_launch_count.restype = i64
     lib.capdec_graph_captures.argtypes = [vp]
     lib.capdec_graph_captures.restype = i64
+    lib.capdec_debug_trace.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64), i64]
     lib.capdec_test_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.capdec_profile.argtypes = [vp, i32]
     lib.capdec_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
@@ -214,6 +215,15 @@ class CaptionDecoder:
     @property
     def graph_captures(self) -> int:
         return int(self.lib.capdec_graph_captures(self._h))
+
+    def debug_trace(self, max_launches: int = 4000):
+        """CAPDEC_TRACE=1: -> int64 array [launches, 16] of %globaltimer stamps (ns) of the small-batch kernel's CTA 0."""
+        n = 1 + 16 * max_launches
+        buf = (ctypes.c_uint64 * n)()
+        self._check(self.lib.capdec_debug_trace(self._h, buf, n), "capdec_debug_trace")
+        a = np.frombuffer(buf, dtype=np.uint64).astype(np.int64)
+        k = min(int(a[0]), max_launches)
+        return a[1:1 + 16 * k].reshape(k, 16)
 
     def profile(self, enable: bool):
         self._check(self.lib.capdec_profile(self._h, 1 if enable else 0), "capdec_profile")

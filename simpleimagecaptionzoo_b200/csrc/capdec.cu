@@ -16,6 +16,7 @@
 
 #include "../../include/capdec.h"
 #include "kernels.cuh"
+#include "smallm.cuh"
 #include "cider.cuh"
 
 using namespace capdec;
@@ -33,6 +34,14 @@ struct Raw {
     float* d = nullptr;
     std::vector<int64_t> shape;
     size_t numel = 0;
+};
+
+// A GEMM operand as the launchers see it: the tensor map the large-tile kernels load through, plus where it came from (the
+// small-batch kernel builds maps with its own box shapes from the same rows).
+struct Operand {
+    CUtensorMap map;
+    const __half* base = nullptr;  // first element (column offset applied)
+    int rows = 0, ld = 0, cols = 0;
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -84,6 +93,15 @@ struct capdec_handle {
     bool pair_gemm = true;             // CAPDEC_GEMM_1CTA=1 selects the single-CTA GEMM kernel instead of the CTA-pair one
     bool no_stream_attention = false;  // CAPDEC_NO_STREAM_ATTENTION=1: use the non-persistent attention kernel
     int att_variant = 0;               // CAPDEC_ATT_VARIANT=1: FFMA streaming kernel instead of the MMA-fragment kernel
+    // small-batch path (smallm.cuh): swap-AB split-K GEMMs for <= small_rows activation rows (CAPDEC_NO_SMALLM=1 disables,
+    // CAPDEC_SMALLM_ROWS overrides the row limit, CAPDEC_NO_FUSE=1 keeps every GEMM of a step in its own launch)
+    int small_rows = 128;
+    bool small_fuse = true;
+    float* small_slabs = nullptr;
+    int* small_counters = nullptr;
+    unsigned* small_bar = nullptr;  // 2 sets x SM_MAX_PHASES grid-barrier counters, used by consecutive launches in turn
+    int small_parity = 0;
+    unsigned long long* small_trace = nullptr;  // CAPDEC_TRACE=1: device-side timeline of the small-batch kernel (capdec_debug_trace)
     bool prof = false;  // bracket every launch with CUDA events (capdec_profile)
     struct ProfRec {
         int cat;
@@ -262,12 +280,19 @@ int make_map(capdec_handle* h, CUtensorMap* m, const __half* base, int rows, int
     if (r != CUDA_SUCCESS) return fail(h, CAPDEC_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string(static_cast<int>(r)));
     return CAPDEC_OK;
 }
-int map_a(capdec_handle* h, CUtensorMap* m, const Act16& a, int col_off = 0) {
-    return make_map(h, m, a.p, a.rows, a.ld, col_off, BLOCK_M);
+int make_operand(capdec_handle* h, Operand* o, const __half* base, int rows, int ld, int col_off, int box_rows) {
+    o->base = base + col_off;
+    o->rows = rows;
+    o->ld = ld;
+    o->cols = ld - col_off;
+    return make_map(h, &o->map, base, rows, ld, col_off, box_rows);
+}
+int map_a(capdec_handle* h, Operand* m, const Act16& a, int col_off = 0) {
+    return make_operand(h, m, a.p, a.rows, a.ld, col_off, BLOCK_M);
 }
 // weight operand: the single-CTA kernel loads 256-row boxes, the CTA-pair kernel 128-row halves
-int map_b(capdec_handle* h, CUtensorMap* m, const Act16& a) {
-    return make_map(h, m, a.p, a.rows, a.ld, 0, h->pair_gemm ? BN / 2 : BN);
+int map_b(capdec_handle* h, Operand* m, const Act16& a) {
+    return make_operand(h, m, a.p, a.rows, a.ld, 0, h->pair_gemm ? BN / 2 : BN);
 }
 
 template <int EPI, int KTOP>
@@ -319,10 +344,135 @@ int logit_runs(const capdec_handle* h, int M, int N) {
     return runs;
 }
 
-int launch_gemm(capdec_handle* h, int epi, int ktop, const CUtensorMap& ma, int a_lo, const CUtensorMap& mb, int b_lo, int M,
+// ------------------------------------------------------------------------------------------------ small-batch path
+struct SmallDesc {
+    int epi, ktop;
+    const Operand* x;  // activations [M, K]
+    int x_lo;
+    const Operand* w;  // weights [N, K]
+    int w_lo;
+    int M, N, Kdim;
+    EpiParams e;
+};
+
+bool small_ok(const capdec_handle* h, int M) { return h->small_slabs != nullptr && M <= h->small_rows; }
+
+constexpr int SMALL_MAX_ITEMS = 2 * 148;
+
+// K split of a phase.  An item costs its k-blocks (~0.3 us each: the weight stream is L2-bound) plus a fixed ~6 us chain of
+// L2 round trips (partial store, arrive / wait at the tile's counter, reduction loads, epilogue), so a second round over
+// the SMs is never worth it: the largest split that keeps every item in ONE round wins -- top-down gates (32 tiles x 32
+// k-blocks) -> 4, dec_att (8 x 16) -> 8, language gates (32 x 64) -> 4, logits (75 x 16) -> 1
+int small_ksplit(int tiles, int total_kb, int num_sms) {
+    int best = 1;
+    double best_cost = 1e30;
+    for (int ks = 1; ks <= 8 && ks <= total_kb; ++ks) {
+        const int items = tiles * ks;
+        if (items > SMALL_MAX_ITEMS) break;
+        const int rounds = (items + num_sms - 1) / num_sms;
+        const int per = (total_kb + ks - 1) / ks;
+        const double cost = rounds * (per + 20.0) + 0.5 * ((ks + 3) / 4);  // + one reduction round trip per four splits
+        if (cost < best_cost) best_cost = cost, best = ks;
+    }
+    return best;
+}
+
+template <int N_ACT>
+int launch_small_t(capdec_handle* h, SmallParams& p, const SmallDesc* d, int n, cudaStream_t st) {
+    using C = SmallCfg<N_ACT>;
+    auto kern = smallm_kernel<N_ACT>;
+    CK(h, smem_attr(reinterpret_cast<const void*>(kern), C::SMEM_BYTES));
+    int max_items = 1;
+    for (int q = 0; q < n; ++q) {
+        SmallPhase& P = p.ph[q];
+        CKS(h, make_map(h, &P.map_w, d[q].w->base, d[q].w->rows, d[q].w->ld, 0, SM_TILE_N));
+        CKS(h, make_map(h, &P.map_x, d[q].x->base, d[q].x->rows, d[q].x->ld, 0, N_ACT));
+        if (P.tiles * P.ksplit > max_items) max_items = P.tiles * P.ksplit;
+    }
+    const int grid = max_items < h->num_sms ? max_items : h->num_sms;
+    CK(h, launch_pdl(h, kern, dim3(n > 1 ? h->num_sms : grid), dim3(SM_THREADS), C::SMEM_BYTES, st, p));
+    return CAPDEC_OK;
+}
+
+// One launch for up to SM_MAX_PHASES dependent GEMMs on the same <= small_rows activation rows.
+int launch_small(capdec_handle* h, const SmallDesc* d, int n, cudaStream_t st) {
+    if (n < 1 || n > SM_MAX_PHASES) return fail(h, CAPDEC_ERR_INVALID, "small-batch launch: bad phase count");
+    SmallParams p{};
+    p.n_phases = n;
+    p.slabs = h->small_slabs;
+    p.counters = h->small_counters;
+    p.bar = h->small_bar + h->small_parity * SM_MAX_PHASES;
+    p.bar_other = h->small_bar + (h->small_parity ^ 1) * SM_MAX_PHASES;
+    p.trace = h->small_trace;
+    if (n > 1) h->small_parity ^= 1;
+    int max_m = 0;
+    double flops = 0.0;
+    for (int q = 0; q < n; ++q) {
+        const SmallDesc& D = d[q];
+        if (D.Kdim % BLOCK_K || D.M <= 0 || D.N <= 0) return fail(h, CAPDEC_ERR_INVALID, "small-batch GEMM: K must be a multiple of 64");
+        SmallPhase& P = p.ph[q];
+        P.N_w = D.N, P.M = D.M;
+        P.k_blocks = D.Kdim / BLOCK_K;
+        P.passes = h->split ? 3 : 1;
+        P.w_lo_off = D.w_lo, P.x_lo_off = D.x_lo;
+        P.tiles = (D.N + SM_TILE_N - 1) / SM_TILE_N;
+        P.ksplit = small_ksplit(P.tiles, P.k_blocks * P.passes, h->num_sms);
+        P.epi = D.epi, P.ktop = D.ktop;
+        P.e = D.e;
+        if (D.epi == EPI_TOPK || D.epi == EPI_SAMPLE) P.e.n_tiles = P.tiles;  // one partial record per (row, 128-word tile)
+        if (D.M > max_m) max_m = D.M;
+        flops += 2.0 * D.M * D.N * D.Kdim;
+    }
+    const int epi0 = d[0].epi;
+    const int cat = epi0 == EPI_LSTM ? CAPDEC_CAT_GEMM_LSTM : epi0 == EPI_STORE ? CAPDEC_CAT_GEMM_STORE
+                  : epi0 == EPI_GLU ? CAPDEC_CAT_GEMM_GLU : CAPDEC_CAT_GEMM_LOGITS;
+    prof_begin(h, cat, flops, st);
+    int status;
+    if (max_m <= 16) status = launch_small_t<16>(h, p, d, n, st);
+    else if (max_m <= 64) status = launch_small_t<64>(h, p, d, n, st);
+    else status = launch_small_t<128>(h, p, d, n, st);
+    prof_end(h, st);
+    CKS(h, status);
+    CK(h, cudaGetLastError());
+    h->launches++;
+    return CAPDEC_OK;
+}
+
+// number of partial records per row the logit GEMM writes for M rows (what the bookkeeping kernels merge)
+int logit_slots(const capdec_handle* h, int M, int N);
+
+int logit_slots(const capdec_handle* h, int M, int N) {
+    if (small_ok(h, M)) return (N + SM_TILE_N - 1) / SM_TILE_N;
+    return logit_runs(h, M, N) * EPI_SPLIT;
+}
+
+int alloc_small(capdec_handle* h) {
+    const char* off = getenv("CAPDEC_NO_SMALLM");
+    if (off && off[0] == '1') return CAPDEC_OK;
+    const char* rows = getenv("CAPDEC_SMALLM_ROWS");
+    if (rows) h->small_rows = atoi(rows) < 128 ? atoi(rows) : 128;
+    const char* nf = getenv("CAPDEC_NO_FUSE");
+    h->small_fuse = !(nf && nf[0] == '1');
+    if (h->small_rows <= 0) return CAPDEC_OK;
+    CKS(h, dalloc(h, &h->small_counters, 4096));
+    {
+        const char* tr = getenv("CAPDEC_TRACE");
+        if (tr && tr[0] == '1') CKS(h, dalloc(h, &h->small_trace, 1 + 16 * 4000));
+    }
+    CKS(h, dalloc(h, &h->small_bar, 2 * SM_MAX_PHASES));
+    return dalloc(h, &h->small_slabs, static_cast<size_t>(SMALL_MAX_ITEMS) * 128 * SM_TILE_N, false);
+}
+
+int launch_gemm(capdec_handle* h, int epi, int ktop, const Operand& oa, int a_lo, const Operand& ob, int b_lo, int M,
                 int N, int Kdim, const EpiParams& e, cudaStream_t st) {
     if (Kdim % BLOCK_K) return fail(h, CAPDEC_ERR_INVALID, "GEMM K must be a multiple of 64");
     if (M <= 0 || N <= 0) return fail(h, CAPDEC_ERR_INVALID, "empty GEMM");
+    if (small_ok(h, M)) {
+        SmallDesc d{epi, ktop, &oa, a_lo, &ob, b_lo, M, N, Kdim, e};
+        return launch_small(h, &d, 1, st);
+    }
+    const CUtensorMap& ma = oa.map;
+    const CUtensorMap& mb = ob.map;
     GemmParams p{};
     p.M = M;
     p.N = N;
@@ -416,7 +566,7 @@ int build_embedding_gates(capdec_handle* h, const Raw* emb, int relu, cudaStream
     const int V = h->V, E = h->E, H = h->H;
     cvt_f16_kernel<<<grid_for(static_cast<size_t>(V) * E / 4), 256, 0, st>>>(emb->d, V, E, h->emb16.p, h->emb16.ld, h->emb16.lo, 0, relu);
     CK(h, cudaGetLastError());
-    CUtensorMap ma, mb;
+    Operand ma, mb;
     CKS(h, map_a(h, &ma, h->emb16));
     CKS(h, map_b(h, &mb, h->W_emb));
     EpiParams e{};
@@ -676,7 +826,7 @@ int run_refiner(capdec_handle* h, const float* bu, const float* mask, int B, int
     const int H = h->H, D = h->D;
     const size_t BR = static_cast<size_t>(B) * R;
     const int N = static_cast<int>(BR);
-    CUtensorMap ma, mb;
+    Operand ma, mb;
     if (bu_f16) {  // packed fp16 shard rows are the GEMM operand as they are
         CK(h, cudaMemcpyAsync(h->bu16.p, bu_f16, BR * D * sizeof(__half), cudaMemcpyDeviceToDevice, st));
     } else {
@@ -747,14 +897,11 @@ struct StepCtx {
     size_t alpha_stride = 0;
 };
 
-int run_logits(capdec_handle* h, const Act16& a, const StepCtx& c, cudaStream_t st) {
-    CUtensorMap ma, mb;
-    CKS(h, map_a(h, &ma, a));
-    CKS(h, map_b(h, &mb, h->W_pred));
+EpiParams logits_epi(capdec_handle* h, const StepCtx& c) {
     EpiParams e{};
     e.bias = h->b_pred;
     e.part = h->part;
-    e.n_tiles = logit_runs(h, c.M, h->V) * EPI_SPLIT;
+    e.n_tiles = logit_slots(h, c.M, h->V);
     e.seed = c.seed;
     e.seed_ptr = c.seed_ptr;
     e.step = c.t - 1;
@@ -762,7 +909,16 @@ int run_logits(capdec_handle* h, const Act16& a, const StepCtx& c, cudaStream_t 
     e.scst_n = c.scst_n;
     e.forced = c.forced;
     e.forced_ld = c.forced_ld;
-    return launch_gemm(h, c.logits_epi, c.ktop, ma, a.lo, mb, h->W_pred.lo, c.M, h->V, h->H, e, st);
+    return e;
+}
+
+// Run dependent GEMMs on the same activation rows: ONE persistent launch with grid barriers between them on the
+// small-batch path (smallm.cuh), one launch each otherwise (or while per-launch timing is on).
+int run_gemms(capdec_handle* h, const SmallDesc* d, int n, int M, cudaStream_t st) {
+    if (n > 1 && small_ok(h, M) && h->small_fuse && !h->prof) return launch_small(h, d, n, st);
+    for (int q = 0; q < n; ++q)
+        CKS(h, launch_gemm(h, d[q].epi, d[q].ktop, *d[q].x, d[q].x_lo, *d[q].w, d[q].w_lo, d[q].M, d[q].N, d[q].Kdim, d[q].e, st));
+    return CAPDEC_OK;
 }
 
 template <int KR, typename T>
@@ -889,10 +1045,11 @@ int launch_aoa_att(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
 // BUTD: XA = [h2 | h1] (top-down LSTM operand), XB = [ctx | h1 | h2] (language LSTM operand), Hb2 = new h2.
 int step_butd(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
     const int H = h->H, A = h->A, D = h->D;
-    CUtensorMap ma, mb;
+    Operand x_td, w_td, x_da, w_da, x_lm, w_lm, x_pr, w_pr;
+    SmallDesc g[2];
     {  // top-down attention LSTM (BUTD_Model.py:265)
-        CKS(h, map_a(h, &ma, h->XA));
-        CKS(h, map_b(h, &mb, h->W_l1));
+        CKS(h, map_a(h, &x_td, h->XA));
+        CKS(h, map_b(h, &w_td, h->W_l1));
         EpiParams e{};
         e.rowadd = h->G0;
         e.rowadd_ld = 4 * H;
@@ -907,24 +1064,25 @@ int step_butd(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
         e.out16 = h->XB.p + D;
         e.ld16 = h->XB.ld;
         e.lo16 = h->XB.lo;
-        CKS(h, launch_gemm(h, EPI_LSTM, 1, ma, h->XA.lo, mb, h->W_l1.lo, c.M, 4 * H, H + H, e, st));
+        g[0] = SmallDesc{EPI_LSTM, 1, &x_td, h->XA.lo, &w_td, h->W_l1.lo, c.M, 4 * H, H + H, e};
     }
     {  // dec_att(h1) (BUTD_Model.py:58)
-        CKS(h, map_a(h, &ma, h->XB, D));
-        CKS(h, map_b(h, &mb, h->W_aux2));
+        CKS(h, map_a(h, &x_da, h->XB, D));
+        CKS(h, map_b(h, &w_da, h->W_aux2));
         EpiParams e{};
         e.bias = h->b_aux2;
         e.out32 = h->dec_ctx;
         e.ld32 = A;
-        CKS(h, launch_gemm(h, EPI_STORE, 1, ma, h->XB.lo, mb, h->W_aux2.lo, c.M, A, H, e, st));
+        g[1] = SmallDesc{EPI_STORE, 1, &x_da, h->XB.lo, &w_da, h->W_aux2.lo, c.M, A, H, e};
     }
+    CKS(h, run_gemms(h, g, 2, c.M, st));
     if (c.K <= 1) CKS(h, launch_butd_att<1>(h, c, st));
     else if (c.K <= 3) CKS(h, launch_butd_att<3>(h, c, st));
     else if (c.K <= 5) CKS(h, launch_butd_att<5>(h, c, st));
     else CKS(h, launch_butd_att<8>(h, c, st));
     {  // language LSTM (BUTD_Model.py:268)
-        CKS(h, map_a(h, &ma, h->XB));
-        CKS(h, map_b(h, &mb, h->W_l2));
+        CKS(h, map_a(h, &x_lm, h->XB));
+        CKS(h, map_b(h, &w_lm, h->W_l2));
         EpiParams e{};
         e.bias = h->b_l2;
         e.c_in = h->c2[c.cur];
@@ -934,9 +1092,12 @@ int step_butd(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
         e.out16 = h->Hb2.p;
         e.ld16 = h->Hb2.ld;
         e.lo16 = h->Hb2.lo;
-        CKS(h, launch_gemm(h, EPI_LSTM, 1, ma, h->XB.lo, mb, h->W_l2.lo, c.M, 4 * H, D + H + H, e, st));
+        g[0] = SmallDesc{EPI_LSTM, 1, &x_lm, h->XB.lo, &w_lm, h->W_l2.lo, c.M, 4 * H, D + H + H, e};
     }
-    return run_logits(h, h->Hb2, c, st);
+    CKS(h, map_a(h, &x_pr, h->Hb2));
+    CKS(h, map_b(h, &w_pr, h->W_pred));
+    g[1] = SmallDesc{c.logits_epi, c.ktop, &x_pr, h->Hb2.lo, &w_pr, h->W_pred.lo, c.M, h->V, H, logits_epi(h, c)};
+    return run_gemms(h, g, 2, c.M, st);
 }
 
 AdvOp op_copy(const Act16& src, int src_col, const Act16& dst, int dst_col, int n) {
@@ -965,9 +1126,10 @@ AdvOps adv_butd(capdec_handle* h, bool init) {
 // NIC: XA = [h], Hb = new h.
 int step_nic(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
     const int H = h->H;
-    CUtensorMap ma, mb;
-    CKS(h, map_a(h, &ma, h->XA));
-    CKS(h, map_b(h, &mb, h->W_l1));
+    Operand x_l, w_l, x_pr, w_pr;
+    SmallDesc g[2];
+    CKS(h, map_a(h, &x_l, h->XA));
+    CKS(h, map_b(h, &w_l, h->W_l1));
     EpiParams e{};
     e.bias = h->b_l1;
     e.gather = h->emb_gates;
@@ -980,8 +1142,11 @@ int step_nic(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
     e.out16 = h->Hb.p;
     e.ld16 = h->Hb.ld;
     e.lo16 = h->Hb.lo;
-    CKS(h, launch_gemm(h, EPI_LSTM, 1, ma, h->XA.lo, mb, h->W_l1.lo, c.M, 4 * H, H, e, st));
-    return run_logits(h, h->Hb, c, st);
+    g[0] = SmallDesc{EPI_LSTM, 1, &x_l, h->XA.lo, &w_l, h->W_l1.lo, c.M, 4 * H, H, e};
+    CKS(h, map_a(h, &x_pr, h->Hb));
+    CKS(h, map_b(h, &w_pr, h->W_pred));
+    g[1] = SmallDesc{c.logits_epi, c.ktop, &x_pr, h->Hb.lo, &w_pr, h->W_pred.lo, c.M, h->V, H, logits_epi(h, c)};
+    return run_gemms(h, g, 2, c.M, st);
 }
 
 AdvOps adv_nic(capdec_handle* h, bool init) {
@@ -1000,7 +1165,8 @@ AdvOps adv_nic(capdec_handle* h, bool init) {
 // AoA: XA = [mean+ctx | h] (LSTM operand), XB = [att | query] (AoA gate operand), Hb = new h, Hb2 = ctx fp16.
 int step_aoa(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
     const int H = h->H;
-    CUtensorMap ma, mb;
+    Operand ma, mb;
+    SmallDesc g[2];
     {
         CKS(h, map_a(h, &ma, h->XA));
         CKS(h, map_b(h, &mb, h->W_l1));
@@ -1049,9 +1215,13 @@ int step_aoa(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
         e.out16 = h->Hb2.p;
         e.ld16 = h->Hb2.ld;
         e.lo16 = h->Hb2.lo;
-        CKS(h, launch_gemm(h, EPI_GLU, 1, ma, h->XB.lo, mb, h->W_aux3.lo, c.M, 2 * H, 2 * H, e, st));
+        g[0] = SmallDesc{EPI_GLU, 1, &ma, h->XB.lo, &mb, h->W_aux3.lo, c.M, 2 * H, 2 * H, e};
     }
-    return run_logits(h, h->Hb2, c, st);
+    Operand x_pr, w_pr;
+    CKS(h, map_a(h, &x_pr, h->Hb2));
+    CKS(h, map_b(h, &w_pr, h->W_pred));
+    g[1] = SmallDesc{c.logits_epi, c.ktop, &x_pr, h->Hb2.lo, &w_pr, h->W_pred.lo, c.M, h->V, H, logits_epi(h, c)};
+    return run_gemms(h, g, 2, c.M, st);
 }
 
 AdvOps adv_aoa(capdec_handle* h, bool init) {
@@ -1236,6 +1406,17 @@ int64_t capdec_launch_count(const capdec_handle* h) { return h ? h->launches : 0
 
 int64_t capdec_graph_captures(const capdec_handle* h) { return h ? h->graph_captures : 0; }
 
+int capdec_debug_trace(capdec_handle* h, uint64_t* dst, int64_t n) {
+    if (!h || !dst || n <= 0) return CAPDEC_ERR_INVALID;
+    if (!h->small_trace) return fail(h, CAPDEC_ERR_STATE, "debug trace is off (CAPDEC_TRACE=1 before capdec_create)");
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaDeviceSynchronize());
+    const int64_t m = n < 1 + 16 * 4000 ? n : 1 + 16 * 4000;
+    CK(h, cudaMemcpy(dst, h->small_trace, static_cast<size_t>(m) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    CK(h, cudaMemset(h->small_trace, 0, sizeof(uint64_t)));
+    return CAPDEC_OK;
+}
+
 void capdec_destroy(capdec_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
@@ -1312,6 +1493,7 @@ static int create_impl(capdec_handle* h) {
     CKS(h, dalloc(h, &h->out_scores, h->Bmax));
     CKS(h, dalloc(h, &h->out_lengths, h->Bmax));
     CKS(h, dalloc(h, &h->seed_dev, 1));
+    CKS(h, alloc_small(h));
     CKS(h, dalloc(h, &h->out_sample_tokens, static_cast<size_t>(M) * h->Tmax));
     CKS(h, dalloc(h, &h->out_sample_logprobs, static_cast<size_t>(M) * h->Tmax));
     CKS(h, dalloc(h, &h->out_greedy, static_cast<size_t>(h->Bmax) * h->Tmax));
@@ -1515,7 +1697,7 @@ static int prepare_impl(capdec_handle* h, const float* feats, const float* mask,
                         const __half* feats16) {
     const int H = h->H, E = h->E;
     h->prepared = false;
-    CUtensorMap ma, mb;
+    Operand ma, mb;
     if (h->cfg.arch == CAPDEC_ARCH_NIC) {
         // priming step: (h,c) = lstm(image_embedding, (0,0))  (NIC_Model.py:52-56)
         cvt_f16_kernel<<<grid_for(static_cast<size_t>(batch) * E / 4), 256, 0, st>>>(feats, batch, E, h->Xp.p, h->Xp.ld, h->Xp.lo, 0);
@@ -1581,8 +1763,8 @@ static int prepare_impl(capdec_handle* h, const float* feats, const float* mask,
             CKS(h, map_a(h, &ma, h->feats16));
             if (aoa_mma_ok(h)) {  // fp16 K and V as separate row-padded matrices for the fragment kernel
                 for (int part = 0; part < 2; ++part) {
-                    CKS(h, make_map(h, &mb, h->W_aux2.p + static_cast<size_t>(part) * H * h->W_aux2.ld, H, h->W_aux2.ld, 0,
-                                    h->pair_gemm ? BN / 2 : BN));
+                    CKS(h, make_operand(h, &mb, h->W_aux2.p + static_cast<size_t>(part) * H * h->W_aux2.ld, H, h->W_aux2.ld, 0,
+                                        h->pair_gemm ? BN / 2 : BN));
                     EpiParams e{};
                     e.bias = h->b_aux2 + part * H;
                     Act16& dst = part == 0 ? h->k16 : h->v16;
@@ -1666,7 +1848,7 @@ static int enqueue_beam_search(capdec_handle* h, int32_t beam, int32_t max_seq, 
     else beam_init_kernel<8><<<B, 128, 0, st>>>(s, adv_ops(h, true), nic ? 1 : 0);
     CK(h, cudaGetLastError());
     h->launches++;
-    const int n_slots = logit_runs(h, M, h->V) * EPI_SPLIT;  // partial records per row written by the logit GEMM
+    const int n_slots = logit_slots(h, M, h->V);  // partial records per row written by the logit GEMM
     StepCtx c{};
     c.M = M, c.K = K, c.logits_epi = EPI_TOPK, c.ktop = ktop_for(K);
     const AdvOps ops = adv_ops(h, false);
@@ -1779,7 +1961,7 @@ static int sample_impl(capdec_handle* h, int32_t mode, int32_t n_per_image, uint
     else sample_init_kernel<8><<<B, 128, 0, st>>>(s, adv_ops(h, true), nic ? 1 : 0);
     CK(h, cudaGetLastError());
     h->launches++;
-    const int n_slots = logit_runs(h, M, h->V) * EPI_SPLIT;
+    const int n_slots = logit_slots(h, M, h->V);
     StepCtx c{};
     c.M = M, c.K = n, c.logits_epi = EPI_SAMPLE, c.ktop = 1;
     c.seed = static_cast<uint32_t>(seed & 0xFFFFFFFFu);
@@ -1856,11 +2038,12 @@ int capdec_test_gemm(const float* a, const float* b, const float* bias, float* d
     int status = CAPDEC_OK;
     Act16 A16, B16;
     do {
+        if ((status = alloc_small(h)) != CAPDEC_OK) break;
         if ((status = alloc_act(h, &A16, m, k)) != CAPDEC_OK) break;
         if ((status = alloc_act(h, &B16, n, k)) != CAPDEC_OK) break;
         cvt_f16_kernel<<<grid_for(static_cast<size_t>(m) * k / 4), 256, 0, st>>>(a, m, k, A16.p, A16.ld, A16.lo, 0);
         cvt_f16_kernel<<<grid_for(static_cast<size_t>(n) * k / 4), 256, 0, st>>>(b, n, k, B16.p, B16.ld, B16.lo, 0);
-        CUtensorMap ma, mb;
+        Operand ma, mb;
         if ((status = map_a(h, &ma, A16)) != CAPDEC_OK) break;
         if ((status = map_b(h, &mb, B16)) != CAPDEC_OK) break;
         EpiParams e{};
@@ -1902,12 +2085,13 @@ int capdec_test_gemm_time(int32_t m, int32_t n, int32_t k, int32_t epi, int32_t 
     do {
         Act16 A16, B16, H16;
         float *bias = nullptr, *c0 = nullptr, *c1 = nullptr, *out = nullptr, *part = nullptr;
+        if ((status = alloc_small(h)) != CAPDEC_OK) break;
         if ((status = alloc_act(h, &A16, m, k)) != CAPDEC_OK) break;
         if ((status = alloc_act(h, &B16, n, k)) != CAPDEC_OK) break;
         fill_f16_kernel<<<1024, 256>>>(A16.p, static_cast<size_t>(m) * A16.ld, 0.01f);
         fill_f16_kernel<<<1024, 256>>>(B16.p, static_cast<size_t>(n) * B16.ld, 0.01f);
         if ((status = dalloc(h, &bias, n)) != CAPDEC_OK) break;
-        CUtensorMap ma, mb;
+        Operand ma, mb;
         if ((status = map_a(h, &ma, A16)) != CAPDEC_OK) break;
         if ((status = map_b(h, &mb, B16)) != CAPDEC_OK) break;
         EpiParams e{};
@@ -1923,7 +2107,7 @@ int capdec_test_gemm_time(int32_t m, int32_t n, int32_t k, int32_t epi, int32_t 
             e.c_in = c0, e.c_out = c1, e.ldc = n / 4;
             e.out16 = H16.p, e.ld16 = H16.ld, e.lo16 = H16.lo;
         } else if (epi == EPI_TOPK) {
-            const int nt = logit_runs(h, m, n) * EPI_SPLIT;
+            const int nt = logit_slots(h, m, n);
             if ((status = dalloc(h, &part, static_cast<size_t>(m) * nt * topk_part_stride(4))) != CAPDEC_OK) break;
             e.part = part;
             e.n_tiles = nt;

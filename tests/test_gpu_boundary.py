@@ -131,7 +131,7 @@ def test_captioner_sampler_rl_and_scst_rollouts_wrappers():
     assert torch.equal(seq, tok.long()) and torch.equal(logp, lp)
     assert (seq.cpu().numpy().reshape(meta["B"], n, -1) == gold["sample_seq"]).all(2).mean() >= 0.95
     greedy, seq2, logp2 = cap.scst_rollouts(vi, max_len=meta["T"], n_per_image=n, seed=meta["sample_seed"])
-    assert torch.equal(seq2, seq) and torch.allclose(logp2, logp, atol=1e-5)
+    assert torch.equal(seq2, seq) and torch.allclose(logp2, logp, atol=2e-4)  # other row count -> other GEMM tiling / summation order
     assert torch.equal(greedy, cap.sampler(vi, max_len=meta["T"]))
     # consecutive calls without a seed draw from different streams
     a, _ = cap.sampler_rl(vi, max_len=meta["T"])
@@ -178,8 +178,73 @@ def test_decode_graph_cache_serves_alternating_shapes(monkeypatch):
     eager.close()
     for a, b, c in zip(got, got2, want):
         assert torch.equal(a, c) and torch.equal(b, c)
-    assert torch.equal(got[9], got[13]) and not torch.equal(got[9], got[11])  # same seed same rollout, other seed another one
-    assert torch.allclose(got[-1], got[-3], atol=1e-4)  # the re-scored log-probs are the rollout's own
+    assert torch.equal(got[6], got[10]) and not torch.equal(got[6], got[8])  # same seed same rollout, other seed another one
+    # the re-scored log-probs are the rollout's own up to the first stored 0 (sample_rl stores <end> and everything after it
+    # as 0 while its log-probs stay those of the words it drew, BUTD_Model.py:226-232)
+    live = (got[-4] != 0).long().cumprod(1).bool()
+    assert live.any() and torch.allclose(got[-1][live], got[-3][live], atol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["butd_full_k3", "butd_full_k5_r196", "nic_full_k3", "aoa_full_k3", "butd_tiny_k1", "nic_tiny_k5"])
+def test_small_batch_path_matches_large_tile_path(name, monkeypatch):
+    """<= 128 activation rows take the swap-AB split-K kernel (smallm.cuh), with the dependent GEMMs of a step fused into one
+    launch; the same decode through separate launches (CAPDEC_NO_FUSE=1) and through the large-tile kernels
+    (CAPDEC_NO_SMALLM=1) must give the same captions and (up to fp32 summation order) the same scores / log-probs."""
+    from simpleimagecaptionzoo_b200 import capdec
+    meta, gold = load_case(name)
+    sd, feats, mask = rebuild(meta)
+    d = meta["dims"]
+    B = min(meta["B"], 128 // max(meta["K"], 2))
+    assert B * meta["K"] <= 128
+    kw = dict(hidden_dim=d["hidden_dim"], embed_dim=d["embed_dim"], vocab_size=d["vocab_size"], atten_dim=d.get("atten_dim", 0),
+              enc_dim=d.get("enc_dim", 2048), num_heads=d.get("num_heads", 8), max_batch=B, max_regions=max(meta["R"], 1),
+              max_rows=max(meta["K"], 2), max_seq=meta["T"], math="f16x3")
+    ft = torch.from_numpy(feats[:B]).cuda()
+    mk = None if mask is None else torch.from_numpy(mask[:B]).cuda()
+
+    def run():
+        dec = capdec.CaptionDecoder(meta["arch"], sd, **kw)
+        dec.prepare(ft, mk)
+        out = list(dec.beam_search(meta["K"], meta["T"]))
+        out += list(dec.sample(capdec.SAMPLE_MULTINOMIAL, 2, 5, meta["T"]))
+        out += list(dec.sample(capdec.SAMPLE_GREEDY, 1, 0, meta["T"]))
+        out = [t.clone() for t in out]
+        torch.cuda.synchronize()
+        dec.close()
+        return out
+
+    fused = run()
+    monkeypatch.setenv("CAPDEC_NO_FUSE", "1")
+    unfused = run()
+    monkeypatch.setenv("CAPDEC_NO_SMALLM", "1")
+    large = run()
+    for a, b in zip(fused, unfused):
+        assert torch.equal(a, b)  # same kernels, same split-K order: bit-identical
+    tok, score, length, seq, logp, gseq, glogp = fused
+    ltok, lscore, llength, lseq, llogp, lgseq, lglogp = large
+    same = (tok == ltok).all(1)
+    assert same.float().mean() >= 0.9 and torch.allclose(score[same], lscore[same], atol=2e-4)
+    assert (tok.cpu().numpy() == gold["tokens"][:B]).all(1).mean() >= 0.9
+    srow = (seq == lseq).all(1)
+    assert srow.float().mean() >= 0.9 and torch.allclose(logp[srow], llogp[srow], atol=2e-4)
+    grow = (gseq == lgseq).all(1)
+    assert grow.float().mean() >= 0.9 and torch.allclose(glogp[grow], lglogp[grow], atol=2e-4)
+
+
+@pytest.mark.parametrize("shape", [(1, 9487, 1024), (3, 4096, 2048), (48, 1000, 64), (64, 130, 192), (65, 4096, 4096), (128, 96, 640)])
+@pytest.mark.parametrize("math", ["f16", "f16x3"])
+def test_small_batch_gemm_against_torch_fp64(shape, math):
+    """The swap-AB split-K GEMM (1..128 rows; partial weight tiles, every K split) against a plain fp64 matmul."""
+    from simpleimagecaptionzoo_b200 import capdec
+    m, n, k = shape
+    g = torch.Generator().manual_seed(m * 131 + n)
+    a = torch.randn(m, k, generator=g).cuda()
+    b = (torch.randn(n, k, generator=g) * 0.05).cuda()
+    bias = torch.randn(n, generator=g).cuda()
+    d = capdec.test_gemm(a, b, bias, math)
+    ref = (a.half().double() @ b.half().double().T if math == "f16" else a.double() @ b.double().T) + bias.double()
+    err = (d.double() - ref).abs().max().item()
+    assert err <= 4e-6 * max(ref.abs().max().item(), 1.0) * max(1.0, (k / 64) ** 0.5), err
 
 
 AGREEMENT = [
