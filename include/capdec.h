@@ -157,6 +157,14 @@ int capdec_scst_rollout(capdec_handle* h, int32_t n_per_image, uint64_t seed, in
  *   logprobs [B*n_per_image, max_seq] fp32 log p(word t | image, previous words) */
 int capdec_score(capdec_handle* h, const int32_t* tokens, int32_t n_per_image, int32_t max_seq, float* logprobs, void* stream);
 
+/* capdec_score that also exports what `predict` was applied to at every step -- h2 (BUTD_Model.py:270), h (NIC_Model.py:174),
+ * the AoA context (AoA_Model.py:455) -- as states [B*n_per_image, max_seq, hidden_dim] fp32: with it the host rebuilds
+ * predict + log_softmax + gather under autograd (scst.differentiable_logprobs), i.e. `seqLogprobs` WITH a graph through the
+ * vocabulary layer for RewardCriterion (Utils.py:290-317, Engine.py:261-272).  Gradients of the recurrent weights (BPTT
+ * through the LSTMs / attention) are the training path and stay with the reference.  states = NULL: same as capdec_score. */
+int capdec_score_states(capdec_handle* h, const int32_t* tokens, int32_t n_per_image, int32_t max_seq, float* logprobs, float* states,
+                        void* stream);
+
 /* ---- CIDEr-D self-critical reward (the SCST step after the two rollouts) --------------------------------------------
  * Replaces Utils.get_self_critical_reward (Utils.py:319-367) -> CiderD.compute_score (cider/pyciderevalcap/ciderD/
  * ciderD.py:32-55) -> CiderScorer.compute_cider (ciderD_scorer.py:127-206, df mode "<dataset>-train") on word ids. */

@@ -27,7 +27,7 @@ SYMBOLS = (
     "capdec_test_gemm", "capdec_profile", "capdec_profile_read", "capdec_test_gemm_time",
     "capdec_prepare_bottom_up", "capdec_get_refined", "capdec_score", "capdec_prepare_f16", "capdec_scst_rollout",
     "capdec_cider_create", "capdec_cider_destroy", "capdec_cider_last_error", "capdec_cider_ngram_key", "capdec_cider_set_df",
-    "capdec_cider_reward", "capdec_graph_captures", "capdec_debug_trace",
+    "capdec_cider_reward", "capdec_graph_captures", "capdec_debug_trace", "capdec_score_states",
 )
 CATEGORIES = ("gemm_lstm", "gemm_store", "gemm_glu", "gemm_logits", "attention", "bookkeeping", "other")
 
@@ -67,6 +67,7 @@ def load_library(path: str = LIB_PATH) -> ctypes.CDLL:
     lib.capdec_beam_search.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
     lib.capdec_sample.argtypes = [vp, i32, i32, ctypes.c_uint64, i32, vp, vp, vp, vp]
     lib.capdec_score.argtypes = [vp, vp, i32, i32, vp, vp]
+    lib.capdec_score_states.argtypes = [vp, vp, i32, i32, vp, vp, vp]
     lib.capdec_scst_rollout.argtypes = [vp, i32, ctypes.c_uint64, i32, vp, vp, vp, vp]
     lib.capdec_cider_create.argtypes = [i32, ctypes.POINTER(vp)]
     lib.capdec_cider_destroy.argtypes = [vp]
@@ -321,22 +322,28 @@ class CaptionDecoder:
             torch.cuda.current_stream(self.device).wait_stream(self.stream)
         return tokens, logprobs, greedy
 
-    def score(self, tokens, n_per_image: int = 1):
+    def score(self, tokens, n_per_image: int = 1, return_states: bool = False):
         """Teacher-forced log-probs of given words: tokens [B*n, T] int (no <sta>, the layout ``sample`` returns) ->
-        logprobs [B*n, T] fp32 CUDA tensor, log p(word t | image, <sta>, words < t)."""
+        logprobs [B*n, T] fp32 CUDA tensor, log p(word t | image, <sta>, words < t)
+        [, states [B*n, T, H] fp32: the rows ``predict`` was applied to -- see ``scst.differentiable_logprobs``]."""
         torch = _torch()
         tokens = tokens.to(self.device, torch.int32).contiguous()
         M, T = tokens.shape
         if M != self.B * n_per_image:
             raise ValueError(f"tokens has {M} rows, the prepared batch has {self.B} images x {n_per_image}")
         logprobs = torch.empty((M, T), dtype=torch.float32, device=self.device)
+        states = torch.empty((M, T, self.H), dtype=torch.float32, device=self.device) if return_states else None
         with torch.cuda.device(self.device):
             self.stream.wait_stream(torch.cuda.current_stream(self.device))
-            self._check(self.lib.capdec_score(self._h, tokens.data_ptr(), n_per_image, T, logprobs.data_ptr(),
-                                              self.stream.cuda_stream), "capdec_score")
+            if return_states:
+                self._check(self.lib.capdec_score_states(self._h, tokens.data_ptr(), n_per_image, T, logprobs.data_ptr(),
+                                                         states.data_ptr(), self.stream.cuda_stream), "capdec_score_states")
+            else:
+                self._check(self.lib.capdec_score(self._h, tokens.data_ptr(), n_per_image, T, logprobs.data_ptr(),
+                                                  self.stream.cuda_stream), "capdec_score")
             torch.cuda.current_stream(self.device).wait_stream(self.stream)
         self._keep_tokens = tokens
-        return logprobs
+        return (logprobs, states) if return_states else logprobs
 
     def sample(self, mode: int, n_per_image: int = 1, seed: int = 0, max_seq: int = 20, return_alphas: bool = False):
         """-> tokens [B*n,max_seq] int32, logprobs [B*n,max_seq] fp32 (CUDA tensors) [, alphas [B*n,max_seq,R] fp32]."""

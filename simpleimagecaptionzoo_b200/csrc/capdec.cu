@@ -101,6 +101,9 @@ struct capdec_handle {
     int* small_counters = nullptr;
     unsigned* small_bar = nullptr;  // 2 sets x SM_MAX_PHASES grid-barrier counters, used by consecutive launches in turn
     int small_parity = 0;
+    bool chain = false;          // CAPDEC_CHAIN=1: top-down gates and dec_att in ONE launch of the chained pair kernel (measured slower)
+    int* chain_sync = nullptr;   // [2][row blocks] ready / passed counters of the chained pair kernel (zero between launches)
+    int chain_blocks = 0;
     unsigned long long* small_trace = nullptr;  // CAPDEC_TRACE=1: device-side timeline of the small-batch kernel (capdec_debug_trace)
     bool prof = false;  // bracket every launch with CUDA events (capdec_profile)
     struct ProfRec {
@@ -166,6 +169,7 @@ struct capdec_handle {
     float* out_sample_logprobs = nullptr;
     int* out_greedy = nullptr;
     int* forced_buf = nullptr;         // teacher-forced words of capdec_score at a stable address
+    float* states_out = nullptr;       // capdec_score_states: where the per-step predict inputs go ([M, T, H] fp32) or null
     float* mask_buf = nullptr;  // library-owned copy of the region mask (stable address for the captured decode)
     int* out_tokens = nullptr;
     float* out_scores = nullptr;
@@ -893,6 +897,8 @@ struct StepCtx {
     bool first_from_c0 = false;
     const int* forced = nullptr;  // teacher-forced words [row * forced_ld + step] (capdec_score) or null
     int forced_ld = 0;
+    float* states = nullptr;  // capdec_score_states: this step's slice of the [M, T, H] predict-input export (row stride states_ld) or null
+    size_t states_ld = 0;
     float* alphas = nullptr;  // where this step's attention maps go ([row * alpha_stride + region]) or null
     size_t alpha_stride = 0;
 };
@@ -912,10 +918,42 @@ EpiParams logits_epi(capdec_handle* h, const StepCtx& c) {
     return e;
 }
 
+// Gate GEMM (LSTM epilogue) -> bias/store GEMM on the h' it wrote, as ONE launch of the chained pair kernel (gemm.cuh).
+int launch_chain(capdec_handle* h, const SmallDesc& d1, const SmallDesc& d2, cudaStream_t st) {
+    auto fill = [&](const SmallDesc& d, GemmParams& p) {
+        p = GemmParams{};
+        p.M = d.M, p.N = d.N;
+        p.k_blocks = d.Kdim / BLOCK_K;
+        p.passes = h->split ? 3 : 1;
+        p.a_lo_off = d.x_lo, p.b_lo_off = d.w_lo;
+        p.num_m_blocks = (d.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+        p.num_n_blocks = (d.N + BN - 1) / BN;
+        p.runs = 0;
+        p.epi = d.e;
+    };
+    GemmParams p1, p2;
+    fill(d1, p1);
+    fill(d2, p2);
+    const int items1 = p1.num_m_blocks * p1.num_n_blocks, items2 = p2.num_m_blocks * p2.num_n_blocks;
+    const int most = items1 > items2 ? items1 : items2;
+    const int pairs = most < h->num_sms / 2 ? most : h->num_sms / 2;
+    p1.m_group = pairs, p2.m_group = pairs;
+    ChainSync cs{h->chain_sync, h->chain_sync + h->chain_blocks, EPI_WARPS * 2 * p1.num_n_blocks, 2 * p2.num_n_blocks};
+    auto kern = gemm2_chain_kernel;
+    CK(h, smem_attr(reinterpret_cast<const void*>(kern), GemmCfg2::SMEM_BYTES));
+    CK(h, launch_pdl(h, kern, dim3(2 * pairs), dim3(GEMM_THREADS), GemmCfg2::SMEM_BYTES, st, d1.x->map, d1.w->map, p1, d2.x->map, d2.w->map, p2, cs));
+    CK(h, cudaGetLastError());
+    h->launches++;
+    return CAPDEC_OK;
+}
+
 // Run dependent GEMMs on the same activation rows: ONE persistent launch with grid barriers between them on the
 // small-batch path (smallm.cuh), one launch each otherwise (or while per-launch timing is on).
 int run_gemms(capdec_handle* h, const SmallDesc* d, int n, int M, cudaStream_t st) {
     if (n > 1 && small_ok(h, M) && h->small_fuse && !h->prof) return launch_small(h, d, n, st);
+    if (n == 2 && !small_ok(h, M) && h->chain && h->pair_gemm && !h->prof && d[0].epi == EPI_LSTM && d[1].epi == EPI_STORE &&
+        d[0].M == d[1].M && (d[0].M + 2 * BLOCK_M - 1) / (2 * BLOCK_M) <= h->chain_blocks)
+        return launch_chain(h, d[0], d[1], st);
     for (int q = 0; q < n; ++q)
         CKS(h, launch_gemm(h, d[q].epi, d[q].ktop, *d[q].x, d[q].x_lo, *d[q].w, d[q].w_lo, d[q].M, d[q].N, d[q].Kdim, d[q].e, st));
     return CAPDEC_OK;
@@ -1242,11 +1280,20 @@ AdvOps adv_aoa(capdec_handle* h, bool init) {
 }
 
 int run_step(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
+    int status;
     switch (h->cfg.arch) {
-        case CAPDEC_ARCH_BUTD: return step_butd(h, c, st);
-        case CAPDEC_ARCH_NIC: return step_nic(h, c, st);
-        default: return step_aoa(h, c, st);
+        case CAPDEC_ARCH_BUTD: status = step_butd(h, c, st); break;
+        case CAPDEC_ARCH_NIC: status = step_nic(h, c, st); break;
+        default: status = step_aoa(h, c, st); break;
     }
+    CKS(h, status);
+    if (c.states) {  // the rows `predict` was applied to in this step (BUTD_Model.py:270 h2, NIC_Model.py:174 h, AoA_Model.py:455 ctx)
+        const Act16& x = h->cfg.arch == CAPDEC_ARCH_NIC ? h->Hb : h->Hb2;
+        export_f32_kernel<<<grid_for(static_cast<size_t>(c.M) * h->H), 256, 0, st>>>(x.p, x.ld, x.lo, c.M, h->H, c.states, c.states_ld);
+        CK(h, cudaGetLastError());
+        h->launches++;
+    }
+    return CAPDEC_OK;
 }
 AdvOps adv_ops(capdec_handle* h, bool init) {
     switch (h->cfg.arch) {
@@ -1494,6 +1541,12 @@ static int create_impl(capdec_handle* h) {
     CKS(h, dalloc(h, &h->out_lengths, h->Bmax));
     CKS(h, dalloc(h, &h->seed_dev, 1));
     CKS(h, alloc_small(h));
+    {
+        const char* nc = getenv("CAPDEC_CHAIN");
+        h->chain = nc && nc[0] == '1';
+        h->chain_blocks = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M) + 1;
+        CKS(h, dalloc(h, &h->chain_sync, 2 * static_cast<size_t>(h->chain_blocks)));
+    }
     CKS(h, dalloc(h, &h->out_sample_tokens, static_cast<size_t>(M) * h->Tmax));
     CKS(h, dalloc(h, &h->out_sample_logprobs, static_cast<size_t>(M) * h->Tmax));
     CKS(h, dalloc(h, &h->out_greedy, static_cast<size_t>(h->Bmax) * h->Tmax));
@@ -1937,6 +1990,21 @@ int capdec_score(capdec_handle* h, const int32_t* tokens, int32_t n_per_image, i
                         static_cast<cudaStream_t>(stream));
 }
 
+int capdec_score_states(capdec_handle* h, const int32_t* tokens, int32_t n_per_image, int32_t max_seq, float* logprobs, float* states,
+                        void* stream) {
+    if (!h) return CAPDEC_ERR_INVALID;
+    if (!states) return capdec_score(h, tokens, n_per_image, max_seq, logprobs, stream);
+    if (!h->prepared) return fail(h, CAPDEC_ERR_STATE, "capdec_score_states before capdec_prepare");
+    if (n_per_image <= 0 || n_per_image > h->Kmax || max_seq <= 0 || max_seq > h->Tmax || !tokens || !logprobs)
+        return fail(h, CAPDEC_ERR_INVALID, "score_states: n_per_image / max_seq out of range or null tokens / logprobs");
+    CK(h, cudaSetDevice(h->cfg.device));
+    h->states_out = states;  // caller's buffer: this pass is enqueued directly (not replayed from the graph cache)
+    const int status = sample_impl(h, CAPDEC_SAMPLE_GREEDY, n_per_image, 0, max_seq, nullptr, logprobs, nullptr, tokens,
+                                   static_cast<cudaStream_t>(stream));
+    h->states_out = nullptr;
+    return status;
+}
+
 // greedy_tokens != null: the SCST pair of rollouts in one pass -- n_per_image rows per image of which the LAST is the greedy
 // rollout (written to greedy_tokens [B, T]); tokens / logprobs then hold the n_per_image - 1 sampled rows per image.
 static int sample_impl(capdec_handle* h, int32_t mode, int32_t n_per_image, uint64_t seed, int32_t max_seq, int32_t* tokens,
@@ -1975,6 +2043,8 @@ static int sample_impl(capdec_handle* h, int32_t mode, int32_t n_per_image, uint
         c.t = t;
         c.cur = (t - 1) & 1;
         c.first_from_c0 = nic && t == 1;
+        c.states = (forced && h->states_out) ? h->states_out + static_cast<size_t>(t - 1) * h->H : nullptr;  // [row, t, unit]
+        c.states_ld = static_cast<size_t>(max_seq) * h->H;
         c.alphas = alphas ? alphas + static_cast<size_t>(t - 1) * h->R : nullptr;  // [row, t, region]
         c.alpha_stride = static_cast<size_t>(max_seq) * h->R;
         CKS(h, run_step(h, c, st));

@@ -967,4 +967,195 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ chained pair kernel
+// Two dependent GEMMs in ONE persistent launch of the CTA-pair kernel: phase 1 = a gate GEMM with the LSTM epilogue whose
+// fp16 h' rows are phase 2's A operand (top-down LSTM -> dec_att(h1), BUTD_Model.py:265,58), phase 2 = bias + store.
+// Phase-2 tiles are appended to every pair's work list, so they fill the last, partial wave of phase 1 and the second
+// launch (ramp, pipeline fill, drain of a single-wave GEMM) disappears.  A phase-2 tile of row block m may read h' only
+// once all column tiles of phase 1 have written it: every epilogue warp of phase 1 release-increments ready[m] after its
+// stores; the TMA producers of phase 2 acquire-wait for the full count (all phase-1 tiles are in flight or done by then:
+// they precede the phase-2 tiles in every pair's list).  The last producer to pass re-arms the counters.
+// Measured on B200 at the benchmark batch (4608 rows): SLOWER than two launches (8.17 vs 7.63 ms per decode) -- with 288 + 72
+// tiles on 74 pairs the phase-2 tiles queue behind four gate tiles on most pairs anyway, and every gate tile's epilogue now
+// ends in a gpu-scope release; kept for CAPDEC_CHAIN=1 experiments, off by default.
+struct ChainSync {
+    int* ready;   // [num_m_blocks] arrivals of phase-1 epilogue warps (zero between launches)
+    int* passed;  // [num_m_blocks] phase-2 producers that have passed the wait
+    int ready_target;   // EPI_WARPS * 2 CTAs * num_n_blocks of phase 1
+    int passed_target;  // 2 CTAs * num_n_blocks of phase 2
+};
+
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_chain_kernel(const __grid_constant__ CUtensorMap tma_a1, const __grid_constant__ CUtensorMap tma_b1, const GemmParams p1,
+                   const __grid_constant__ CUtensorMap tma_a2, const __grid_constant__ CUtensorMap tma_b2, const GemmParams p2,
+                   const ChainSync cs) {
+    using Cfg = GemmCfg2;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int BLOCK_N = Cfg::BLOCK_N;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    const uint32_t full_bar = smem_u32(bars);
+    const uint32_t empty_bar = smem_u32(bars + STAGES);
+    const uint32_t tfull_bar = smem_u32(bars + 2 * STAGES);
+    const uint32_t tempty_bar = smem_u32(bars + 2 * STAGES + 2);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    const uint32_t smem_base = smem_u32(smem);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tma_a1);
+        tma_prefetch_desc(&tma_b1);
+        tma_prefetch_desc(&tma_a2);
+        tma_prefetch_desc(&tma_b2);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar + 8 * s, 1);
+            mbar_init(empty_bar + 8 * s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar + 8 * s, 1);
+            mbar_init(tempty_bar + 8 * s, 2 * EPI_WARPS);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc_cg2(smem_u32(tmem_slot), Cfg::TMEM_COLS);
+        tmem_relinquish_cg2();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    griddep_launch();
+    griddep_wait();
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int ph = 0; ph < 2; ++ph) {
+                const GemmParams& p = ph == 0 ? p1 : p2;
+                const CUtensorMap* ma = ph == 0 ? &tma_a1 : &tma_a2;
+                const CUtensorMap* mb = ph == 0 ? &tma_b1 : &tma_b2;
+                const int total_kb = p.k_blocks * p.passes;
+                TileIter it(p, pair, npairs);
+                bool f, l;
+                while (it.next(f, l)) {
+                    const int m_blk = 2 * it.m_blk + static_cast<int>(rank), n_blk = it.n_blk;
+                    if (ph == 1) {  // phase 1 must have written every column of this row block's h'
+                        const int* rdy = cs.ready + it.m_blk;
+                        const long long t0 = clock64();
+                        while (true) {
+                            int v;
+                            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(rdy) : "memory");
+                            if (v >= cs.ready_target) break;
+                            if (clock64() - t0 > 4000000000LL) {
+                                printf("capdec: chained GEMM wait timed out (block %d row block %d: %d of %d)\n", blockIdx.x, it.m_blk, v,
+                                       cs.ready_target);
+                                __trap();
+                            }
+                        }
+                        fence_proxy_async_global();  // the generic-proxy stores of h' are ordered before this thread's TMA reads
+                        if (atomicAdd(cs.passed + it.m_blk, 1) == cs.passed_target - 1) cs.ready[it.m_blk] = 0, cs.passed[it.m_blk] = 0;
+                    }
+                    for (int kk = 0; kk < total_kb; ++kk) {
+                        const int pass = kk / p.k_blocks;
+                        const int kb = kk - pass * p.k_blocks;
+                        const int ka = kb * BLOCK_K + (pass == 2 ? p.a_lo_off : 0);
+                        const int kbb = kb * BLOCK_K + (pass == 1 ? p.b_lo_off : 0);
+                        mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                        const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                        const uint32_t sb = sa + Cfg::A_BYTES;
+                        const uint32_t lead_full = mapa_shared(full_bar + 8 * stage, 0);
+                        if (leader) mbar_arrive_expect_tx(full_bar + 8 * stage, 2 * Cfg::STAGE_BYTES);
+                        tma_load_2d_cg2(sa, ma, lead_full, ka, m_blk * BLOCK_M);
+                        tma_load_2d_cg2(sb, mb, lead_full, kbb, n_blk * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2));
+                        if (++stage == STAGES) stage = 0, phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = make_idesc_f16(2 * BLOCK_M, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int ph = 0; ph < 2; ++ph) {
+                const GemmParams& p = ph == 0 ? p1 : p2;
+                const int total_kb = p.k_blocks * p.passes;
+                TileIter it(p, pair, npairs);
+                bool f, l;
+                while (it.next(f, l)) {
+                    mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                    for (int kk = 0; kk < total_kb; ++kk) {
+                        mbar_wait(full_bar + 8 * stage, phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                        const uint64_t da = make_smem_desc_sw128(sa);
+                        const uint64_t db = make_smem_desc_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                            umma_f16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kk | k) != 0 ? 1u : 0u);
+                        umma_commit_cg2(empty_bar + 8 * stage, 3);
+                        if (++stage == STAGES) stage = 0, phase ^= 1;
+                    }
+                    umma_commit_cg2(tfull_bar + 8 * acc, 3);
+                    if (++acc == 2) acc = 0, acc_phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        const int quarter = warp & 3;
+        const int split = (warp - 2) >> 2;
+        constexpr int CHUNKS = BLOCK_N / 32;
+        const int c0 = split * (CHUNKS / EPI_SPLIT), c1 = c0 + CHUNKS / EPI_SPLIT;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int ph = 0; ph < 2; ++ph) {
+            const GemmParams& p = ph == 0 ? p1 : p2;
+            TileIter it(p, pair, npairs);
+            bool first, last;
+            while (it.next(first, last)) {
+                const int m_blk = 2 * it.m_blk + static_cast<int>(rank), n_blk = it.n_blk;
+                const int row = m_blk * BLOCK_M + quarter * 32 + lane;
+                const int n_base = n_blk * BLOCK_N;
+                if (ph == 0) epi_lstm_prefetch<BLOCK_N>(row, n_base, c0, c1, p);
+                mbar_wait(tfull_bar + 8 * acc, acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quarter * 32) << 16);
+                if (ph == 0) epi_lstm<BLOCK_N>(taddr, row, n_base, c0, c1, p);
+                else epi_store<BLOCK_N>(taddr, row, n_base, c0, c1, p);
+                __syncwarp();
+                tc_fence_before();
+                if (lane == 0) {
+                    mbar_arrive_cluster(mapa_shared(tempty_bar + 8 * acc, 0));
+                    if (ph == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(cs.ready + it.m_blk) : "memory");
+                }
+                if (++acc == 2) acc = 0, acc_phase ^= 1;
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
 }  // namespace capdec

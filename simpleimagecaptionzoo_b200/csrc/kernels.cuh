@@ -178,6 +178,17 @@ __global__ void __launch_bounds__(256) butd_ingest_kernel(const T* __restrict__ 
 
 __global__ void set_u32_kernel(uint32_t* p, uint32_t v) { *p = v; }
 
+// fp16 operand rows (hi, + lo in the fp32-grade mode) -> fp32 rows at a caller-chosen row stride
+__global__ void export_f32_kernel(const __half* __restrict__ src, int ld, int lo, int M, int n, float* __restrict__ dst, size_t dst_ld) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < static_cast<size_t>(M) * n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t r = i / n, c = i - r * n;
+        float v = __half2float(src[r * ld + c]);
+        if (lo > 0) v += __half2float(src[r * ld + lo + c]);
+        dst[r * dst_ld + c] = v;
+    }
+}
+
 __global__ void fill_f16_kernel(__half* p, size_t n, float v) {
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<size_t>(gridDim.x) * blockDim.x)

@@ -201,3 +201,20 @@ class CiderDReward:
         ``get_self_critical_reward`` returns it (Utils.py:364-365) for ``RewardCriterion`` (Utils.py:290-317)."""
         _, r = self.scores_and_rewards(gen_result, greedy_res, ground_truth, img_ids, n_per_image)
         return r[:, None].expand(-1, gen_result.shape[1]).contiguous()
+
+
+def differentiable_logprobs(states, tokens, weight_g, weight_v, bias):
+    """``seqLogprobs`` WITH an autograd graph through the vocabulary layer, for ``RewardCriterion`` (Utils.py:290-317) on
+    rollouts produced by the fused decoder: ``states`` [M, T, H] are the rows ``predict`` saw at every step
+    (``CaptionDecoder.score(tokens, n, return_states=True)``), ``tokens`` [M, T] the rollout, ``weight_g / weight_v / bias``
+    the LIVE parameters of the reference's weight-normed ``decoder.predict`` (BUTD_Model.py:84).  Returns [M, T] fp32
+    ``log_softmax(predict(state))[token]`` -- forward values equal to ``score``'s, gradients flow into the three parameters.
+    Gradients of the recurrent weights need back-propagation through the decode loop: that is the reference's training
+    path, outside this library."""
+    import torch
+    W = weight_v * (weight_g / weight_v.norm(dim=1, keepdim=True))  # torch.nn.utils.weight_norm, dim=0
+    out = []
+    for t in range(states.shape[1]):  # one step at a time: [M, V] logits live only for the step's backward
+        logp = torch.log_softmax(torch.addmm(bias, states[:, t], W.t()), dim=1)
+        out.append(logp.gather(1, tokens[:, t:t + 1].long()))
+    return torch.cat(out, dim=1)

@@ -8,6 +8,7 @@ top-(k+1) gaps needed by the tie-justified rule.  The committed ``agree_*.npz`` 
 
     tokens   int16  [N, 1+T]   reference tokens (<sta> first, <pad>=0 after <end>)
     tie_bits uint32 [N]        bit t-1 set <=> the oracle's top-(k+1) gap at step t is below 1e-4
+    gaps     f16    [N, T]     the oracle's top-(k+1) gap at every step (how close a differing caption's decision was)
     min_gap  f32    [N]        smallest gap of the image (diagnostic)
     oracle_equal bool [N]      the oracle's caption == the reference's caption
 
@@ -74,7 +75,7 @@ def _work(job):
     f = feats_for(name, lo, CHUNK)[off:off + n]
     tokens = np.zeros((n, 1 + T), np.int16)
     with torch.no_grad():
-        for b in range(n):
+        for b in range(0 if os.environ.get("AGREE_GAPS_ONLY") == "1" else n):
             fb = torch.from_numpy(f[b:b + 1])
             if name == "aoa_bu":
                 seq_t = ref.beam_search_sampler({"bu_feats": fb, "bu_masks": None}, beam_size=K)
@@ -90,7 +91,7 @@ def _work(job):
     bits = np.zeros(n, np.uint32)
     for t in range(T):
         bits |= (res.min_gap[:, t] < TOL).astype(np.uint32) << np.uint32(t)
-    return lo + off, tokens, bits, res.min_gap.min(1).astype(np.float32), (res.tokens == tokens).all(1)
+    return lo + off, tokens, bits, res.min_gap.min(1).astype(np.float32), (res.tokens == tokens).all(1), np.minimum(res.min_gap, 1e3).astype(np.float16)
 
 
 def main():
@@ -102,20 +103,26 @@ def main():
     tokens = np.zeros((n_img, 1 + T), np.int16)
     bits = np.zeros(n_img, np.uint32)
     gap = np.zeros(n_img, np.float32)
+    gaps = np.zeros((n_img, T), np.float16)
     same = np.zeros(n_img, bool)
     t0 = time.time()
     done = 0
     with mp.get_context("fork").Pool(procs, initializer=_init, initargs=(name,)) as pool:
-        for start, tk, bt, g, eq in pool.imap_unordered(_work, jobs):
+        for start, tk, bt, g, eq, gs in pool.imap_unordered(_work, jobs):
             n = tk.shape[0]
             tokens[start:start + n], bits[start:start + n], gap[start:start + n], same[start:start + n] = tk, bt, g, eq
+            gaps[start:start + n] = gs
             done += n
             print(f"[{done}/{n_img}] oracle==reference {int(same.sum())}  ({time.time() - t0:.0f}s)", flush=True)
     import torch
     meta = dict(set=name, arch=SETS[name], images=n_img, beam=K, max_seq=T, regions=R, tol=TOL, chunk=CHUNK, seed_base=7000,
                 torch=torch.__version__, oracle_equal=int(same.sum()))
     path = os.path.join(ROOT, "tests", "golden", f"agree_{name}_{n_img}.npz")
-    np.savez_compressed(path, tokens=tokens, tie_bits=bits, min_gap=gap, oracle_equal=same, meta=np.array(json.dumps(meta)))
+    if os.environ.get("AGREE_GAPS_ONLY") == "1":  # add the per-step gaps to a set whose reference tokens exist already
+        old = np.load(path)
+        assert (old["tie_bits"] == bits).all()
+        tokens, same, meta = old["tokens"], old["oracle_equal"], json.loads(str(old["meta"]))
+    np.savez_compressed(path, tokens=tokens, tie_bits=bits, min_gap=gap, gaps=gaps, oracle_equal=same, meta=np.array(json.dumps(meta)))
     print(json.dumps(meta), "->", path, os.path.getsize(path), "bytes")
 
 

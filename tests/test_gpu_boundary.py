@@ -247,6 +247,37 @@ def test_small_batch_gemm_against_torch_fp64(shape, math):
     assert err <= 4e-6 * max(ref.abs().max().item(), 1.0) * max(1.0, (k / 64) ** 0.5), err
 
 
+@pytest.mark.parametrize("name", ["butd_tiny_k3", "nic_tiny_k3", "aoa_tiny_k3_masked", "butd_full_k3"])
+def test_rescore_with_autograd_through_the_vocabulary_layer(name):
+    """seqLogprobs of a fused rollout WITH a graph -- capdec_score_states exports the rows `predict` saw,
+    scst.differentiable_logprobs rebuilds predict + log_softmax + gather on the live weight-normed parameters."""
+    from simpleimagecaptionzoo_b200 import capdec, scst
+    meta, gold = load_case(name)
+    sd, feats, mask = rebuild(meta)
+    d = meta["dims"]
+    dec = capdec.CaptionDecoder(meta["arch"], sd, hidden_dim=d["hidden_dim"], embed_dim=d["embed_dim"], vocab_size=d["vocab_size"],
+                                atten_dim=d.get("atten_dim", 0), enc_dim=d.get("enc_dim", 2048), num_heads=d.get("num_heads", 8),
+                                max_batch=meta["B"], max_regions=max(meta["R"], 1), max_rows=2, max_seq=meta["T"], math="f16x3")
+    dec.prepare(torch.from_numpy(feats).cuda(), None if mask is None else torch.from_numpy(mask).cuda())
+    seq, logp = dec.sample(capdec.SAMPLE_MULTINOMIAL, 2, 7, meta["T"])
+    want = dec.score(seq, 2)
+    got, states = dec.score(seq, 2, return_states=True)
+    assert torch.equal(got, want) and tuple(states.shape) == (meta["B"] * 2, meta["T"], d["hidden_dim"])
+    pre = "decoder." if "decoder.predict.weight_g" in sd else ""
+    g, v, b = (torch.from_numpy(np.array(sd[pre + "predict." + k])).cuda().requires_grad_(True) for k in ("weight_g", "weight_v", "bias"))
+    lp = scst.differentiable_logprobs(states, seq, g, v, b)
+    assert lp.requires_grad and torch.allclose(lp, want, atol=1e-3)
+    # the policy-gradient loss of RewardCriterion: -(logprob * reward * mask).sum() / mask.sum()  (Utils.py:305-316)
+    reward = torch.linspace(-1, 1, lp.numel(), device=lp.device).view_as(lp)
+    live = (seq != 0).long().cumprod(1).float()
+    loss = -(lp * reward * live).sum() / live.sum().clamp(min=1)
+    loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in (g, v, b))
+    # d loss / d bias[w] = -sum_pos reward*live*(1[word == w] - p_w) / n: the entries sum to zero
+    assert abs(float(b.grad.sum())) < 1e-3 * float(b.grad.abs().sum() + 1e-6) + 1e-5
+    dec.close()
+
+
 AGREEMENT = [
     # set, images, math, required exact-or-tie fraction vs the reference's own tokens
     ("butd", 5000, "f16", 0.99),
