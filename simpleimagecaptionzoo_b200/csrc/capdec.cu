@@ -101,6 +101,7 @@ struct capdec_handle {
     int* small_counters = nullptr;
     unsigned* small_bar = nullptr;  // 2 sets x SM_MAX_PHASES grid-barrier counters, used by consecutive launches in turn
     int small_parity = 0;
+    bool small_hint = true;      // CAPDEC_SMALL_HINT=0: no L2 eviction-priority hints on the small-batch kernel's weight loads
     bool chain = false;          // CAPDEC_CHAIN=1: top-down gates and dec_att in ONE launch of the chained pair kernel (measured slower)
     int* chain_sync = nullptr;   // [2][row blocks] ready / passed counters of the chained pair kernel (zero between launches)
     int chain_blocks = 0;
@@ -422,6 +423,9 @@ int launch_small(capdec_handle* h, const SmallDesc* d, int n, cudaStream_t st) {
         P.tiles = (D.N + SM_TILE_N - 1) / SM_TILE_N;
         P.ksplit = small_ksplit(P.tiles, P.k_blocks * P.passes, h->num_sms);
         P.epi = D.epi, P.ktop = D.ktop;
+        // the step's weights (72 MB) cycle through an L2 that keeps ~60 MB of them: the vocabulary matrix is streamed
+        // evict-first so that the gate matrices (evict-last) survive from one step to the next
+        P.w_hint = h->small_hint ? ((D.epi == EPI_TOPK || D.epi == EPI_SAMPLE) ? 1 : 2) : 0;
         P.e = D.e;
         if (D.epi == EPI_TOPK || D.epi == EPI_SAMPLE) P.e.n_tiles = P.tiles;  // one partial record per (row, 128-word tile)
         if (D.M > max_m) max_m = D.M;
@@ -455,6 +459,8 @@ int alloc_small(capdec_handle* h) {
     if (off && off[0] == '1') return CAPDEC_OK;
     const char* rows = getenv("CAPDEC_SMALLM_ROWS");
     if (rows) h->small_rows = atoi(rows) < 128 ? atoi(rows) : 128;
+    const char* hint = getenv("CAPDEC_SMALL_HINT");
+    h->small_hint = !(hint && hint[0] == '0');
     const char* nf = getenv("CAPDEC_NO_FUSE");
     h->small_fuse = !(nf && nf[0] == '1');
     if (h->small_rows <= 0) return CAPDEC_OK;

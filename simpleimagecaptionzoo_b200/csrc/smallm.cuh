@@ -41,6 +41,7 @@ struct SmallPhase {
     int k_blocks, passes, w_lo_off, x_lo_off;
     int tiles, ksplit;
     int epi, ktop;
+    int w_hint;         // L2 priority of the weight lines: 0 = default, 1 = evict-first, 2 = evict-last
     EpiParams e;
 };
 
@@ -527,6 +528,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) smallm_kernel(const __grid_cons
             // The first `pre` k-blocks of this CTA's first item had their WEIGHT tiles requested before the grid barrier
             // that precedes the phase (weights do not depend on the previous phase); only the activation tiles follow here.
             if (lane == 0) {
+                const uint64_t pol_first = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
                 for (int item = blockIdx.x; item < items; item += gridDim.x) {
                     const int tile = item / P.ksplit, split = item - tile * P.ksplit;
                     const int kk0 = (split * total_kb) / P.ksplit, kk1 = ((split + 1) * total_kb) / P.ksplit;
@@ -544,7 +546,8 @@ __global__ void __launch_bounds__(SM_THREADS, 1) smallm_kernel(const __grid_cons
                         mbar_wait(empty_bar + 8 * stage, phase ^ 1);
                         const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                         mbar_arrive_expect_tx(full_bar + 8 * stage, Cfg::STAGE_BYTES);
-                        tma_load_2d(sa, &P.map_w, full_bar + 8 * stage, kw, tile * SM_TILE_N);
+                        if (P.w_hint == 0) tma_load_2d(sa, &P.map_w, full_bar + 8 * stage, kw, tile * SM_TILE_N);
+                        else tma_load_2d_hint(sa, &P.map_w, full_bar + 8 * stage, kw, tile * SM_TILE_N, P.w_hint == 1 ? pol_first : pol_last);
                         tma_load_2d(sa + Cfg::A_BYTES, &P.map_x, full_bar + 8 * stage, kx, 0);
                         if (++stage == STAGES) stage = 0, phase ^= 1;
                     }
@@ -562,7 +565,9 @@ __global__ void __launch_bounds__(SM_THREADS, 1) smallm_kernel(const __grid_cons
                             const int kw = (kk - pass * Pn.k_blocks) * BLOCK_K + (pass == 1 ? Pn.w_lo_off : 0);
                             mbar_wait(empty_bar + 8 * stage, phase ^ 1);
                             mbar_arrive_expect_tx(full_bar + 8 * stage, Cfg::STAGE_BYTES);
-                            tma_load_2d(smem_base + stage * Cfg::STAGE_BYTES, &Pn.map_w, full_bar + 8 * stage, kw, tile * SM_TILE_N);
+                            if (Pn.w_hint == 0) tma_load_2d(smem_base + stage * Cfg::STAGE_BYTES, &Pn.map_w, full_bar + 8 * stage, kw, tile * SM_TILE_N);
+                            else tma_load_2d_hint(smem_base + stage * Cfg::STAGE_BYTES, &Pn.map_w, full_bar + 8 * stage, kw, tile * SM_TILE_N,
+                                                  Pn.w_hint == 1 ? pol_first : pol_last);
                             if (++stage == STAGES) stage = 0, phase ^= 1;
                         }
                     }
