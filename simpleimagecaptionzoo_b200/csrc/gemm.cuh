@@ -205,6 +205,12 @@ __device__ __forceinline__ void epi_store(uint32_t taddr, int row, int n_base, i
     const bool keep = !(e.row_keep && row_ok && __ldg(e.row_keep + row) == 0.f);
     float4 nb[8];  // bias of the next chunk, requested one chunk ahead
     if (e.bias && vec_ok && row_ok) request_bias32(nb, e.bias, n_base + c0 * 32, p.N);
+    // fp16 output rows that start at 16 (mod 32) bytes are written through a 16-byte carry (see below)
+    const bool shifted = e.out16 && row_ok &&
+                         (reinterpret_cast<uintptr_t>(e.out16 + static_cast<size_t>(row) * e.ld16 + n_base + c0 * 32) & 31) == 16;
+    uint4 carry = make_uint4(0, 0, 0, 0);
+    bool have_carry = false;
+    __half* carry_at = nullptr;
 #pragma unroll 1
     for (int c = c0; c < c1; ++c) {
         const int n0 = n_base + c * 32;
@@ -254,7 +260,29 @@ __device__ __forceinline__ void epi_store(uint32_t taddr, int row, int n_base, i
         }
         if (e.out16) {
             __half* o = e.out16 + static_cast<size_t>(row) * e.ld16 + n0;
-            if (n0 + 32 <= p.N) {
+            if (n0 + 32 <= p.N && e.lo16 == 0 && shifted) {
+                // Row at 16 (mod 32) bytes -- every second row of the attention kernel's padded operands (pitch = cols + 8
+                // halves): two 16-byte stores per sector would make L2 fetch each sector before merging (the projection GEMM
+                // read 1.6x its algorithmic bytes).  The chunk's 64 bytes are written as [carry | first 16 B] + one aligned
+                // 32-byte store + a new 16-byte carry, so only the two ends of the thread's 256-byte segment are partial.
+                __align__(16) __half hh[32];
+#pragma unroll
+                for (int u = 0; u < 32; ++u) hh[u] = __float2half_rn(v[u]);
+                const uint4* q = reinterpret_cast<const uint4*>(hh);
+                if (c == c0) {
+                    *reinterpret_cast<uint4*>(o) = q[0];
+                } else {
+                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o - 8), "r"(carry.x), "r"(carry.y), "r"(carry.z),
+                                 "r"(carry.w), "r"(q[0].x), "r"(q[0].y), "r"(q[0].z), "r"(q[0].w)
+                                 : "memory");
+                }
+                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o + 8), "r"(q[1].x), "r"(q[1].y), "r"(q[1].z), "r"(q[1].w),
+                             "r"(q[2].x), "r"(q[2].y), "r"(q[2].z), "r"(q[2].w)
+                             : "memory");
+                carry = q[3];
+                have_carry = true;
+                carry_at = o + 24;
+            } else if (n0 + 32 <= p.N) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 16) {
                     float h[16];
@@ -273,6 +301,10 @@ __device__ __forceinline__ void epi_store(uint32_t taddr, int row, int n_base, i
                     }
                 }
             }
+        }
+        if (have_carry && (c + 1 == c1 || n0 + 64 > p.N)) {  // last full chunk of this thread's segment: flush the trailing 16 bytes
+            *reinterpret_cast<uint4*>(carry_at) = carry;
+            have_carry = false;
         }
     }
 }

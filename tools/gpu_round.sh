@@ -17,3 +17,9 @@ ncu --set full --clock-control none --import-source on -k regex:'gemm2_kernel|at
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras "$@" > gpurun_out/ncu_full_${tag}.log 2>&1
 echo "ncu full rc=$?"
 ls -la gpurun_out | tail -8
+# the one-time projection GEMM (EPI_STORE, 55296 x 1024 x 2048): 22 store-epilogue launches per decode (projection, hoisted mean
+# term, 20 x dec_att); skip the warm-up decodes
+# (ncu matches -k on the base name: 1 gemm2_kernel launch at load + 82 per decode -> the 4th decode's first three launches)
+ncu --set full --clock-control none --import-source on -k regex:gemm2_kernel -s 247 -c 3 -o gpurun_out/prof_proj_${tag} -f \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras "$@" > gpurun_out/ncu_proj_${tag}.log 2>&1
+echo "ncu projection rc=$?"
