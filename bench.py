@@ -47,6 +47,11 @@ if ROOT not in sys.path:
 from simpleimagecaptionzoo_b200 import synth  # noqa: E402
 
 METRIC = "captions/sec (beam=3, max_seq=20)"
+# /root/reference does not travel to the GPU box, so the CPU arm times the numpy port.  Where both run (the build container,
+# 8 cores, tests/tools/cpu_reference_rate.py -> profiles/r02_cpu_reference_vs_port.json) the reference's OWN PyTorch code
+# decodes 3.85 captions/s and the port 2.54: divide a GPU/port ratio by ~1.5 to compare with the real reference.
+PORT_VS_REFERENCE = ("build-container measurement on the same 16 images and 8 cores: reference's own code 3.85 captions/s, this "
+                     "port 2.54 (0.66x) -- profiles/r02_cpu_reference_vs_port.json")
 UNIT = "captions/s"
 
 WORKLOADS = {
@@ -571,7 +576,8 @@ def measure(ctx, args, wname, batch, math, steps, warmup, cpu_images, headline):
             verdict = orc.agreement(gpu_tok, res.tokens, res.min_gap, tol=1e-4)
             out["cpu_baseline"] = {"value": n_cpu / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                    "sample": f"first {n_cpu} images of the same batch, one image per call (reference form), "
-                                             f"numpy/BLAS on {os.cpu_count()} threads, {dt:.1f} s"}
+                                             f"numpy/BLAS on {os.cpu_count()} threads, {dt:.1f} s",
+                                   "port_vs_reference": PORT_VS_REFERENCE}
             out["parity_sample"] = {"images": n_cpu, "exact": sum(v == "exact" for v in verdict),
                                     "tie_justified": sum(v == "tie" for v in verdict), "diff": sum(v == "diff" for v in verdict)}
     # release this workload's device memory before the next one

@@ -185,6 +185,33 @@ def test_decode_graph_cache_serves_alternating_shapes(monkeypatch):
     assert live.any() and torch.allclose(got[-1][live], got[-3][live], atol=1e-4)
 
 
+@pytest.mark.parametrize("B", [5, 70])  # 15 rows: the small-batch GEMM path; 210 rows: the 256-row pair tiles
+def test_aoa_detection_adaptive_features_default_region_limit(B):
+    """AoADetection takes adaptive bottom-up features (10-100 boxes per image, padded + bu_masks, AoA_Engine.py:23-47): the
+    captioner's default region limit covers them without the caller passing max_regions, and the masked decode
+    from 100-box features matches the oracle."""
+    from simpleimagecaptionzoo_b200 import engine, synth
+    d = dict(synth.TINY_DIMS["AOA"])
+    sd = synth.make_state_dict("AOA", seed=3, chaotic=0.3, end_boost=0.2, **d)  # a mix of immediate <end> and full-length captions
+    sd.update(synth.make_refiner_state_dict(hidden_dim=d["hidden_dim"], enc_dim=2048, seed=3, chaotic=0.3))
+    R, K, T = 100, 3, 20
+    mask = synth.make_region_mask(B, R, 10, 3)
+    mask[0] = 1  # one image with all 100 boxes
+    bu = synth.make_region_feats(B, R, 2048, 3) * mask[:, :, None]
+    cap = engine.B200Captioner("AoADetection", dict(embed_dim=d["embed_dim"], hidden_dim=d["hidden_dim"]), d["vocab_size"], sd,
+                               max_batch=B, max_rows=K, max_seq=T, math="f16x3", num_heads=d["num_heads"])
+    assert cap.decoder.max_regions == 100 and cap.native_refiner
+    tok = cap.beam_search_sampler({"bu_feats": torch.from_numpy(bu).cuda(), "bu_masks": torch.from_numpy(mask).cuda()}, beam_size=K)
+    o = orc.make_decoder("AOA", sd, num_heads=d["num_heads"])
+    o.prepare(orc.aoa_project_refine(sd, bu, mask, num_heads=d["num_heads"]), mask)
+    res = orc.beam_search_batched(o, K, T)
+    verdict = orc.agreement(tok.cpu().numpy(), res.tokens, res.min_gap, tol=1e-4)
+    assert "diff" not in verdict and np.mean([v == "exact" for v in verdict]) >= 0.9, verdict
+    with pytest.raises(RuntimeError, match="regions"):
+        cap.beam_search_sampler({"bu_feats": torch.zeros(1, 101, 2048).cuda(), "bu_masks": None}, beam_size=K)
+    cap.decoder.close()
+
+
 @pytest.mark.parametrize("name", ["butd_full_k3", "butd_full_k5_r196", "nic_full_k3", "aoa_full_k3", "butd_tiny_k1", "nic_tiny_k5"])
 def test_small_batch_path_matches_large_tile_path(name, monkeypatch):
     """<= 128 activation rows take the swap-AB split-K kernel (smallm.cuh), with the dependent GEMMs of a step fused into one
