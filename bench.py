@@ -605,31 +605,38 @@ def run_gpu_arm(args, w):
         if k in head:
             line[k] = head[k]
     default_run = args.workload == "butd_det" and args.batch == WORKLOADS["butd_det"]["batch"] and args.math == "f16"
-    if default_run and not args.no_extras:
-        line["workloads"] = {}
-        for name, wname, batch, math in EXTRAS:
-            b = batch or WORKLOADS[wname]["batch"]
-            n_steps = args.extra_steps if b >= 128 else 10 * args.extra_steps  # a 16-image batch takes ~1 ms
-            try:
-                r = measure(ctx, args, wname, b, math, n_steps, 3, 0 if args.no_cpu_baseline else args.extra_cpu_images, headline=False)
-            except Exception as exc:  # noqa: BLE001  (one workload must not take the headline line down with it)
-                line["workloads"][name] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
-                continue
-            dom = r["roofline"]
-            line["workloads"][name] = {
-                "value": r["value"], "unit": UNIT if wname != "scst" else "image rollout sets/s (5 samples + greedy + CIDEr-D reward)",
-                "ms_per_step": r["ms_per_step"], "steps": n_steps, "images_per_gpu": b, "global_batch": b * ctx.world, "math": math,
-                "workload": r["config"]["workload"], "e2e": r["e2e"], "clocks": r["clocks"], "gpu_launches": r["launches"],
-                "dominant_kernel": {"kernel": dom["kernel"], "frac": dom["frac"], "achieved_tflops": dom["achieved"],
-                                    "us_per_launch": dom["us_per_launch"], "share_of_step": dom["share_of_step"]},
-                "kernels": {c: {"ms_per_step": round(v["ms_per_step"], 4), "tflops": v["tflops"] and round(v["tflops"], 1),
-                                **({"hbm_frac": round(v["hbm_frac"], 3)} if "hbm_frac" in v else {})} for c, v in r["kernels"].items()},
-                "parity_sample": r.get("parity_sample"), "cpu_baseline": r.get("cpu_baseline"),
-            }
-    if ctx.rank == 0:
-        emit(line)
+    try:  # whatever happens in the extra passes, the headline line is printed
+        if default_run and not args.no_extras:
+            line["workloads"] = {}
+            for name, wname, batch, math in EXTRAS:
+                b = batch or WORKLOADS[wname]["batch"]
+                n_steps = args.extra_steps if b >= 128 else 10 * args.extra_steps  # a 16-image batch takes ~1 ms
+                try:
+                    r = measure(ctx, args, wname, b, math, n_steps, 3, 0 if args.no_cpu_baseline else args.extra_cpu_images, headline=False)
+                except Exception as exc:  # noqa: BLE001  (one workload must not take the headline line down with it)
+                    line["workloads"][name] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+                    continue
+                dom = r["roofline"]
+                line["workloads"][name] = {
+                    "value": r["value"], "unit": UNIT if wname != "scst" else "image rollout sets/s (5 samples + greedy + CIDEr-D reward)",
+                    "ms_per_step": r["ms_per_step"], "steps": n_steps, "images_per_gpu": b, "global_batch": b * ctx.world, "math": math,
+                    "workload": r["config"]["workload"], "e2e": r["e2e"], "clocks": r["clocks"], "gpu_launches": r["launches"],
+                    "dominant_kernel": {"kernel": dom["kernel"], "frac": dom["frac"], "achieved_tflops": dom["achieved"],
+                                        "us_per_launch": dom["us_per_launch"], "share_of_step": dom["share_of_step"]},
+                    "kernels": {c: {"ms_per_step": round(v["ms_per_step"], 4), "tflops": v["tflops"] and round(v["tflops"], 1),
+                                    **({"hbm_frac": round(v["hbm_frac"], 3)} if "hbm_frac" in v else {})} for c, v in r["kernels"].items()},
+                    "parity_sample": r.get("parity_sample"), "cpu_baseline": r.get("cpu_baseline"),
+                }
+    except BaseException as exc:  # noqa: BLE001
+        line["workloads_aborted"] = f"{type(exc).__name__}: {exc}"[:300]
+    finally:
+        if ctx.rank == 0:
+            emit(line)
     if ctx.world > 1:
-        ctx.dist.destroy_process_group()
+        try:
+            ctx.dist.destroy_process_group()
+        except Exception:  # noqa: BLE001
+            pass
     return 0
 
 
