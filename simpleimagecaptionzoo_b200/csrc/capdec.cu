@@ -91,6 +91,7 @@ struct capdec_handle {
     const float* mask = nullptr;
     int64_t launches = 0;
     bool pair_gemm = true;             // CAPDEC_GEMM_1CTA=1 selects the single-CTA GEMM kernel instead of the CTA-pair one
+    bool mgroup_split = true;          // CAPDEC_MGROUP_SPLIT=0: one row block per pair in the large-M tile walk (round 1's walk)
     bool no_stream_attention = false;  // CAPDEC_NO_STREAM_ATTENTION=1: use the non-persistent attention kernel
     int att_variant = 0;               // CAPDEC_ATT_VARIANT=1: FFMA streaming kernel instead of the MMA-fragment kernel
     // small-batch path (smallm.cuh): swap-AB split-K GEMMs for <= small_rows activation rows (CAPDEC_NO_SMALLM=1 disables,
@@ -327,7 +328,16 @@ int launch_gemm2_t(capdec_handle* h, const CUtensorMap& ma, const CUtensorMap& m
     const int items = p.runs > 0 ? p.num_m_blocks * p.runs : p.num_m_blocks * p.num_n_blocks;
     const int pairs = items < h->num_sms / 2 ? items : h->num_sms / 2;
     GemmParams pg = p;
+    // Tile walk: groups of m_group row blocks, all column blocks of a group before the next group.  With one row block per
+    // pair (m_group = pairs) a pair re-reads its 256 x K operand rows once per column block, with the other pairs' rows and
+    // the group's output in between -- ~110 MB at K = 2048, more than L2 keeps: the projection GEMM read 1.66x its algorithmic
+    // bytes.  Groups of pairs / column-blocks row blocks put the column blocks of a row block on DIFFERENT pairs at the same
+    // time, so the operand rows are fetched once and shared in L2 while they are hot.
     pg.m_group = pairs;
+    if (h->mgroup_split && p.runs == 0 && p.num_m_blocks >= pairs && p.num_n_blocks >= 2) {
+        pg.m_group = pairs / p.num_n_blocks;
+        if (pg.m_group < 1) pg.m_group = 1;
+    }
     const int cat = EPI == EPI_LSTM ? CAPDEC_CAT_GEMM_LSTM : EPI == EPI_STORE ? CAPDEC_CAT_GEMM_STORE
                   : EPI == EPI_GLU ? CAPDEC_CAT_GEMM_GLU : CAPDEC_CAT_GEMM_LOGITS;
     prof_begin(h, cat, 2.0 * p.M * p.N * (static_cast<double>(p.k_blocks) * BLOCK_K), st);
@@ -1508,6 +1518,8 @@ static int create_impl(capdec_handle* h) {
         h->no_stream_attention = e && e[0] == '1';
         const char* g1 = getenv("CAPDEC_GEMM_1CTA");
         h->pair_gemm = !(g1 && g1[0] == '1');
+        const char* mg = getenv("CAPDEC_MGROUP_SPLIT");
+        h->mgroup_split = !(mg && mg[0] == '0');
         const char* ng = getenv("CAPDEC_NO_GRAPH");
         h->use_graphs = !(ng && ng[0] == '1');
         const char* np = getenv("CAPDEC_PDL");
