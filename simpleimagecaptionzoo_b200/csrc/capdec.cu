@@ -100,8 +100,7 @@ struct capdec_handle {
     bool small_fuse = true;
     float* small_slabs = nullptr;
     int* small_counters = nullptr;
-    unsigned* small_bar = nullptr;  // 2 sets x SM_MAX_PHASES grid-barrier counters, used by consecutive launches in turn
-    int small_parity = 0;
+    unsigned* small_bar = nullptr;  // SM_MAX_PHASES x (arrivals, departures) grid-barrier counters, zero between uses
     bool small_hint = true;      // CAPDEC_SMALL_HINT=0: no L2 eviction-priority hints on the small-batch kernel's weight loads
     bool chain = false;          // CAPDEC_CHAIN=1: top-down gates and dec_att in ONE launch of the chained pair kernel (measured slower)
     int* chain_sync = nullptr;   // [2][row blocks] ready / passed counters of the chained pair kernel (zero between launches)
@@ -416,10 +415,8 @@ int launch_small(capdec_handle* h, const SmallDesc* d, int n, cudaStream_t st) {
     p.n_phases = n;
     p.slabs = h->small_slabs;
     p.counters = h->small_counters;
-    p.bar = h->small_bar + h->small_parity * SM_MAX_PHASES;
-    p.bar_other = h->small_bar + (h->small_parity ^ 1) * SM_MAX_PHASES;
+    p.bar = h->small_bar;
     p.trace = h->small_trace;
-    if (n > 1) h->small_parity ^= 1;
     int max_m = 0;
     double flops = 0.0;
     for (int q = 0; q < n; ++q) {

@@ -49,8 +49,7 @@ struct SmallParams {
     int n_phases;
     float* slabs;        // [item][N_ACT][128] fp32 partial tiles (L2-resident scratch)
     int* counters;       // [tile][2] arrivals at / departures from the tile's reduction (zero between uses)
-    unsigned* bar;       // grid-barrier counters of this launch (SM_MAX_PHASES entries, zero on entry)
-    unsigned* bar_other; // the set the previous / next launch uses: reset here once this launch's first barrier has passed
+    unsigned* bar;       // grid-barrier counters: [SM_MAX_PHASES][2] arrivals / departures, zero between uses
     unsigned long long* trace;  // CAPDEC_TRACE=1: [0] = launch counter, then 16 %globaltimer stamps of CTA 0 per launch; else null
     SmallPhase ph[SM_MAX_PHASES];
 };
@@ -404,7 +403,9 @@ __device__ __forceinline__ void small_epi_sample(const SmallPhase& P, const floa
 }
 
 // All CTAs of the (co-resident, one per SM) grid meet; the phase's global writes -- made with generic stores -- are
-// ordered before the next phase's TMA (async proxy) reads of them.
+// ordered before the next phase's TMA (async proxy) reads of them.  ctr[0] counts arrivals, ctr[1] departures: the last
+// CTA to leave zeroes both, so a barrier's counters are always zero between two uses whatever launches (captured graphs,
+// eager launches, other phase counts) follow each other.
 __device__ __forceinline__ void small_grid_barrier(unsigned* ctr) {
     fence_proxy_async_all();
     __syncthreads();  // every thread's writes of the phase happen-before thread 0's release below
@@ -423,6 +424,12 @@ __device__ __forceinline__ void small_grid_barrier(unsigned* ctr) {
     }
     __syncthreads();
     fence_proxy_async_all();
+    if (threadIdx.x == 33) {  // an idle lane of the MMA warp: the producer thread is not delayed by the round trip
+        if (atomicAdd(ctr + 1, 1u) == gridDim.x - 1) {
+            ctr[0] = 0;
+            ctr[1] = 0;
+        }
+    }
 }
 
 __device__ __forceinline__ void small_stamp(unsigned long long* trace, int slot, int k) {
@@ -685,11 +692,8 @@ __global__ void __launch_bounds__(SM_THREADS, 1) smallm_kernel(const __grid_cons
             }
         }
         if (q + 1 < p.n_phases) {
-            small_grid_barrier(p.bar + q);
+            small_grid_barrier(p.bar + 2 * q);
             if (threadIdx.x == 0 && q < 2) small_stamp(p.trace, slot, 7 + 6 * q);
-            if (q == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
-                for (int i = 0; i < SM_MAX_PHASES; ++i) p.bar_other[i] = 0;  // the neighbouring launches' set
-            }
         }
     }
 

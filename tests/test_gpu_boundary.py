@@ -258,6 +258,44 @@ def test_small_batch_path_matches_large_tile_path(name, monkeypatch):
     assert grow.float().mean() >= 0.9 and torch.allclose(glogp[grow], lglogp[grow], atol=2e-4)
 
 
+def test_small_batch_launches_of_any_count_and_kind_follow_each_other(monkeypatch):
+    """The fused small-batch launches synchronise through global counters that must be back at zero whenever a launch ends:
+    an ODD number of fused launches per decode (NIC: one per step, 15 steps), graph replays back to back, and eager launches
+    (attention maps requested) between two replays all give the captions of the unfused path."""
+    from simpleimagecaptionzoo_b200 import capdec
+    out = {}
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("CAPDEC_NO_FUSE", "0" if fuse == "1" else "1")
+        meta, gold = load_case("nic_full_k3")
+        sd, feats, _ = rebuild(meta)
+        d = meta["dims"]
+        nic = capdec.CaptionDecoder("NIC", sd, hidden_dim=d["hidden_dim"], embed_dim=d["embed_dim"], vocab_size=d["vocab_size"],
+                                    max_batch=meta["B"], max_rows=3, max_seq=20, math="f16x3")
+        nic.prepare(torch.from_numpy(feats).cuda())
+        res = [nic.beam_search(3, 15)[0].clone() for _ in range(3)]  # 15 fused launches per decode, replayed
+        res += [nic.beam_search(3, 20)[0].clone(), nic.beam_search(3, 15)[0].clone()]
+        nic.close()
+        meta, gold = load_case("butd_full_k3")
+        sd, feats, _ = rebuild(meta)
+        d = meta["dims"]
+        butd = capdec.CaptionDecoder("BUTD", sd, hidden_dim=d["hidden_dim"], embed_dim=d["embed_dim"], vocab_size=d["vocab_size"],
+                                     atten_dim=d["atten_dim"], enc_dim=d["enc_dim"], max_batch=meta["B"], max_regions=meta["R"], max_rows=3,
+                                     max_seq=meta["T"], math="f16x3")
+        butd.prepare(torch.from_numpy(feats).cuda())
+        res.append(butd.beam_search(3, meta["T"])[0].clone())                     # captured
+        res.append(butd.beam_search(3, meta["T"], return_alphas=True)[0].clone())  # eager (attention maps)
+        res.append(butd.beam_search(3, 7)[0].clone())                              # another graph, odd step count
+        res.append(butd.beam_search(3, meta["T"])[0].clone())                      # replay of the first
+        torch.cuda.synchronize()
+        assert torch.equal(res[5], res[6]) and torch.equal(res[5], res[8])
+        assert (res[5].cpu().numpy() == gold["tokens"]).all(1).mean() >= 0.9
+        butd.close()
+        out[fuse] = res
+    for a, b in zip(out["1"], out["0"]):
+        assert torch.equal(a, b)
+    assert torch.equal(out["1"][0], out["1"][1]) and torch.equal(out["1"][0], out["1"][2]) and torch.equal(out["1"][0], out["1"][4])
+
+
 @pytest.mark.parametrize("shape", [(1, 9487, 1024), (3, 4096, 2048), (48, 1000, 64), (64, 130, 192), (65, 4096, 4096), (128, 96, 640)])
 @pytest.mark.parametrize("math", ["f16", "f16x3"])
 def test_small_batch_gemm_against_torch_fp64(shape, math):
