@@ -258,6 +258,50 @@ def test_small_batch_path_matches_large_tile_path(name, monkeypatch):
     assert grow.float().mean() >= 0.9 and torch.allclose(glogp[grow], lglogp[grow], atol=2e-4)
 
 
+@pytest.mark.parametrize("arch,B,R,K,T", [("BUTD", 3, 1, 8, 20), ("BUTD", 1, 36, 8, 1), ("BUTD", 40, 6, 2, 5), ("NIC", 7, 0, 8, 20),
+                                         ("AOA", 2, 1, 8, 3), ("AOA", 33, 12, 4, 20), ("BUTD", 300, 4, 7, 9)])
+def test_extreme_shapes_against_the_oracle(arch, B, R, K, T):
+    """Limits of the interface -- the widest beam the library takes (8), one region, one step, one image, beams that are not
+    a template size (2, 4, 7), row counts on both sides of the small-batch limit -- against the numpy oracle (tiny chaotic
+    models that emit <end> at varied lengths, fp32-grade mode: exact or tie-justified)."""
+    from simpleimagecaptionzoo_b200 import capdec, synth
+    d = dict(synth.TINY_DIMS[arch])
+    # <end> boosts chosen so that, even with the widest beam, some hypotheses complete early and others run to the limit
+    sd = synth.make_state_dict(arch, seed=11, chaotic=0.3 if arch == "AOA" else True,
+                               end_boost={"BUTD": 0.3, "NIC": -0.25, "AOA": 0.0}[arch], **d)
+    if arch == "BUTD":
+        feats = synth.make_region_feats(B, R, d["enc_dim"], 11)
+    elif arch == "NIC":
+        feats = synth.make_image_embed(B, d["embed_dim"], 11)
+    else:
+        feats = synth.make_refined_feats(B, R, d["hidden_dim"], 11)
+    dec = capdec.CaptionDecoder(arch, sd, hidden_dim=d["hidden_dim"], embed_dim=d["embed_dim"], vocab_size=d["vocab_size"],
+                                atten_dim=d.get("atten_dim", 0), enc_dim=d.get("enc_dim", 2048), num_heads=d.get("num_heads", 8),
+                                max_batch=B, max_regions=max(R, 1), max_rows=8, max_seq=20, math="f16x3")
+    dec.prepare(torch.from_numpy(feats).cuda())
+    tok, score, length = dec.beam_search(K, T)
+    greedy, glp = dec.sample(capdec.SAMPLE_GREEDY, 1, 0, T)
+    torch.cuda.synchronize()
+    o = orc.make_decoder(arch, sd, num_heads=d.get("num_heads", 8))
+    o.prepare(feats)
+    res = orc.beam_search_batched(o, K, T)
+    verdict = orc.agreement(tok.cpu().numpy(), res.tokens, res.min_gap, tol=1e-4)
+    assert "diff" not in verdict, verdict
+    exact = np.array([v == "exact" for v in verdict])
+    assert exact.mean() >= 0.8
+    assert np.array_equal(length.cpu().numpy()[exact], res.lengths[exact])
+    assert np.allclose(score.cpu().numpy()[exact], res.scores[exact], atol=1e-3)
+    ids, gaps, _ = orc.greedy_sample(o, T)
+    g = greedy.cpu().numpy()
+    for b in range(B):
+        if not np.array_equal(g[b], ids[b]):
+            t = int(np.argmax(g[b] != ids[b]))
+            assert gaps[b, t] < 1e-4, (b, t, gaps[b, t])
+    with pytest.raises(RuntimeError):
+        dec.beam_search(9, T)  # wider than max_rows
+    dec.close()
+
+
 def test_small_batch_launches_of_any_count_and_kind_follow_each_other(monkeypatch):
     """The fused small-batch launches synchronise through global counters that must be back at zero whenever a launch ends:
     an ODD number of fused launches per decode (NIC: one per step, 15 steps), graph replays back to back, and eager launches
