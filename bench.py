@@ -514,8 +514,18 @@ def measure(ctx, args, wname, batch, math, steps, warmup, cpu_images, headline):
         gbs = a_bytes / (kern["attention"]["ms_per_step"] * 1e-3) / 1e9
         kern["attention"].update({"algorithmic_gbs": gbs, "hbm_frac": gbs / peaks["hbm_gbs"]})
 
+    small = None
+    if B * (K + 1 if scst else K) <= 128 and w["arch"] == "BUTD":
+        # small-batch regime: a decode step streams the packed fp16 weights once -- top-down gates [4H, 2H], dec_att [A, H],
+        # language gates [4H, D + 2H], vocabulary [V, H] -- and little else; bound = HBM (the weights do not stay in L2)
+        H_, A_, D_, V_ = dims["hidden_dim"], dims["atten_dim"], dims["enc_dim"], dims["vocab_size"]
+        wbytes = 2.0 * (4 * H_ * 2 * H_ + A_ * H_ + 4 * H_ * (D_ + 2 * H_) + V_ * H_)
+        gbs = wbytes * T / (ms_per_step * 1e-3) / 1e9
+        small = {"bound": "hbm", "weight_bytes_per_decode_step": wbytes, "decode_steps": T, "achieved": gbs, "peak": load_peaks()["hbm_gbs"],
+                 "unit": "GB/s", "frac": gbs / load_peaks()["hbm_gbs"], "us_per_decode_step": 1e3 * ms_per_step / T,
+                 "note": "swap-AB split-K kernel (csrc/smallm.cuh); a step is 4 dependent launches / 7 dependent phases"}
     out = {
-        "value": value, "ms_per_step": ms_per_step, "steps": steps, "launches": launches, "clocks": clocks,
+        "value": value, "ms_per_step": ms_per_step, "steps": steps, "launches": launches, "clocks": clocks, "small_batch_roofline": small,
         "dtype": "f16 operands, f32 accumulate" if math == "f16" else "f16x3 split (fp32-grade), f32 accumulate",
         "config": {"workload": w["desc"], "images_per_gpu": B, "global_batch": n_total, "beam": K, "max_seq": T, "regions": R,
                    "vocab": dims["vocab_size"], "math": math,
@@ -601,8 +611,8 @@ def run_gpu_arm(args, w):
         "e2e_fp32_host": head["e2e_fp32_host"], "gpu_launches": head["launches"], "roofline": head["roofline"],
         "kernels": head["kernels"], "graph_captures": head["graph_captures"],
     }
-    for k in ("h2d_ceiling", "identity", "cpu_baseline", "parity_sample"):
-        if k in head:
+    for k in ("h2d_ceiling", "identity", "cpu_baseline", "parity_sample", "small_batch_roofline"):
+        if head.get(k) is not None:
             line[k] = head[k]
     default_run = args.workload == "butd_det" and args.batch == WORKLOADS["butd_det"]["batch"] and args.math == "f16"
     try:  # whatever happens in the extra passes, the headline line is printed
@@ -626,6 +636,7 @@ def run_gpu_arm(args, w):
                     "kernels": {c: {"ms_per_step": round(v["ms_per_step"], 4), "tflops": v["tflops"] and round(v["tflops"], 1),
                                     **({"hbm_frac": round(v["hbm_frac"], 3)} if "hbm_frac" in v else {})} for c, v in r["kernels"].items()},
                     "parity_sample": r.get("parity_sample"), "cpu_baseline": r.get("cpu_baseline"),
+                    **({"small_batch_roofline": r["small_batch_roofline"]} if r.get("small_batch_roofline") else {}),
                 }
     except BaseException as exc:  # noqa: BLE001
         line["workloads_aborted"] = f"{type(exc).__name__}: {exc}"[:300]
