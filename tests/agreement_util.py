@@ -71,18 +71,19 @@ def evaluate(name, images, math, limit=None):
             steps = max(t, 1)
             if int(gold["tie_bits"][lo + i]) & ((1 << steps) - 1):
                 tie += 1
-            elif int(gold["tie_bits"][lo + i]) >> steps:
-                # a near-tie AFTER the first differing position: the returned hypothesis is chosen among beams that already
-                # differ there (the final arg-max over live / completed hypotheses, or a later re-ranking), so a gap below
-                # 1e-4 at a later step flips the output just the same -- e.g. image 1038 of the BUTD set, whose two best
-                # live beams tie EXACTLY (gap 0.0) at steps 19-20 and where the numpy oracle itself picks the other beam
-                late += 1
-            else:
-                g = float(gold["gaps"][lo + i, :steps].min()) if "gaps" in gold else float(gold["min_gap"][lo + i])
-                diffs.append({"image": lo + i, "step": t, "min_gap_up_to_step": g})
+                continue
+            # not justified by north_star's rule as this repo reads it (a sub-1e-4 gap at or before the first differing
+            # position).  Reported beside it: whether a sub-1e-4 gap occurs LATER -- the returned hypothesis is chosen among
+            # beams that already differ at that position, so a late exact tie flips the output too (image 1038 of the BUTD set:
+            # its two best live beams reach gap 0.0 at steps 19-20 and the numpy oracle itself returns the other one) -- but
+            # with random-init models late near-ties are common, so this class is NOT counted as justified.
+            late_tie = bool(int(gold["tie_bits"][lo + i]) >> steps)
+            late += late_tie
+            g = float(gold["gaps"][lo + i, :steps].min()) if "gaps" in gold else float(gold["min_gap"][lo + i])
+            diffs.append({"image": lo + i, "step": t, "min_gap_up_to_step": g, "later_sub_tol_gap": late_tie})
     dec.close()
     return {"set": name, "arch": meta["arch"], "images": n_img, "math": math, "beam": K, "max_seq": T, "exact": exact,
-            "tie_justified": tie, "tie_justified_late": late, "diff": len(diffs), "exact_or_tie_frac": (exact + tie + late) / n_img,
-            "exact_frac": exact / n_img,
+            "tie_justified": tie, "diff": len(diffs), "diff_with_later_sub_tol_gap": late,
+            "exact_or_tie_frac": (exact + tie) / n_img, "exact_frac": exact / n_img,
             "tie_tolerance": meta["tol"], "diffs": diffs,
             "against": "the reference's own beam_search_sample tokens (tests/golden/make_agreement_set.py)"}

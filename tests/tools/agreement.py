@@ -31,7 +31,7 @@ def main():
         gaps = sorted(d["min_gap_up_to_step"] for d in r["diffs"])
         r["diff_gap_quantiles"] = {"min": gaps[0], "median": gaps[len(gaps) // 2], "max": gaps[-1]} if gaps else None
         out[math] = r
-        print(f"{args.set} {math}: exact {r['exact']} tie {r['tie_justified']}+{r['tie_justified_late']} late diff {r['diff']} of {r['images']}"
+        print(f"{args.set} {math}: exact {r['exact']} tie {r['tie_justified']} diff {r['diff']} ({r['diff_with_later_sub_tol_gap']} with a later sub-tol gap) of {r['images']}"
               f" -> {r['exact_or_tie_frac']:.4f}  diff gaps {r['diff_gap_quantiles']}", flush=True)
     path = args.out or os.path.join(ROOT, "gpurun_out", f"agreement_{args.set}_{args.images}.json")
     os.makedirs(os.path.dirname(path), exist_ok=True)
