@@ -41,6 +41,13 @@ def test_sass_is_blackwell_native():
     assert len(gemm) >= 12
     for f in gemm:
         assert "UTCHMMA" in f and " HMMA" not in f, f.split("\n", 1)[0]
+    # the small-batch swap-AB kernel (16 / 64 / 128 activation rows) and the chained pair kernel: tcgen05 + TMA + TMEM too
+    small = [f for f in funcs if f.startswith("_ZN6capdec13smallm_kernel")]
+    assert len(small) == 3
+    for f in small:
+        assert "UTCHMMA" in f and "UTMALDG" in f and "LDTM" in f and " HMMA" not in f, f.split("\n", 1)[0]
+    chain = [f for f in funcs if f.startswith("_ZN6capdec18gemm2_chain_kernel")]
+    assert len(chain) == 1 and "UTCHMMA.2CTA" in chain[0] and " HMMA" not in chain[0]
 
 
 def test_create_fails_loudly_without_gpu():
