@@ -15,6 +15,12 @@
  * stated.  One handle per (process, device); a handle is not re-entrant.  The caller owns every input and
  * output buffer and keeps it alive until the stream work has completed; the library owns its packed weights
  * and workspace, allocated in capdec_create (no allocation inside the decode loop).
+ *
+ * Concurrency on one device: decodes of <= 128 rows (batch x beam) run persistent kernels whose CTAs wait for each other
+ * (split-K exchange, grid barriers) and assume one CTA per SM is resident -- issue the decodes of one device one after
+ * the other (what the binding does: every call is ordered against the caller's current stream), as the reference does.
+ * Two such decodes racing for the SMs from different streams can starve each other; every device-side wait is bounded
+ * (~2 s) and then fails the launch with an error instead of hanging.
  */
 #ifndef CAPDEC_H_
 #define CAPDEC_H_
