@@ -1,5 +1,7 @@
 """Pin the numpy oracle against the golden vectors produced by the reference's own code
 (tests/golden/make_golden.py).  CPU only."""
+import os
+
 import numpy as np
 import pytest
 
@@ -140,3 +142,34 @@ def test_refiner_then_decode_matches_golden(name):
         if not np.array_equal(ids[b], gold["greedy"][b]):
             t = int(np.argmax(ids[b] != gold["greedy"][b]))
             assert gaps[b, t] < 1e-4, (b, t, gaps[b, t])
+
+
+@pytest.mark.parametrize("name,images,lo", [("butd", 5000, 1025), ("aoa_bu", 1000, 450)])
+def test_oracle_reproduces_the_reference_captions_of_the_agreement_sets(name, images, lo):
+    """A slice of the agreement sets (captions decoded by the REFERENCE's own code, tests/golden/make_agreement_set.py),
+    chosen to contain the images where oracle and reference differ (1038; 460): the oracle returns the reference's caption,
+    or the first difference is preceded / followed by a sub-1e-4 gap (an arbitrary choice between tied beams)."""
+    from tests import agreement_util as au
+    if not os.path.exists(au.set_path(name, images)):
+        pytest.skip("agreement set not generated")
+    meta, gold = au.load_set(name, images)
+    n = 16
+    chunk_lo = (lo // meta["chunk"]) * meta["chunk"]
+    f = au.feats_for(name, chunk_lo, meta["chunk"], meta["regions"])[lo - chunk_lo:lo - chunk_lo + n]
+    from simpleimagecaptionzoo_b200 import synth
+    dims = synth.DIMS[au.SETS[name]]
+    sd = synth.make_state_dict(au.SETS[name], seed=0, **dims)
+    if name == "aoa_bu":
+        sd.update(synth.make_refiner_state_dict(hidden_dim=dims["hidden_dim"], enc_dim=2048, seed=0))
+        f = orc.aoa_project_refine(sd, f)
+    o = orc.make_decoder(au.SETS[name], sd)
+    o.prepare(f)
+    res = orc.beam_search_batched(o, meta["beam"], meta["max_seq"])
+    want = gold["tokens"][lo:lo + n].astype(np.int32)
+    same = (res.tokens == want).all(1)
+    assert np.array_equal(same, gold["oracle_equal"][lo:lo + n])
+    assert same.sum() >= n - 1
+    for b in np.nonzero(~same)[0]:
+        assert int(gold["tie_bits"][lo + b]) != 0  # a sub-1e-4 gap somewhere in the decode
+    # the stored per-step gaps are this oracle's
+    assert np.allclose(np.minimum(res.min_gap, 1e3).astype(np.float16).astype(np.float32), gold["gaps"][lo:lo + n].astype(np.float32), atol=2e-3)
