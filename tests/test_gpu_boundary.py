@@ -302,6 +302,28 @@ def test_extreme_shapes_against_the_oracle(arch, B, R, K, T):
     dec.close()
 
 
+@pytest.mark.parametrize("B,reps", [(1, 60), (16, 100), (42, 40)])
+def test_small_batch_path_is_bit_stable_over_many_replays(B, reps):
+    """The split-K exchange sums in split order and the CTAs synchronise through counters: a race there would show up as
+    run-to-run differences.  The same decode replayed many times (beam search + multinomial rollout, both math modes' default)
+    must return bit-identical tokens AND scores every time."""
+    from simpleimagecaptionzoo_b200 import capdec, synth
+    d = synth.DIMS["BUTD"]
+    sd = synth.make_state_dict("BUTD", seed=0, **d)
+    dec = capdec.CaptionDecoder("BUTD", sd, hidden_dim=d["hidden_dim"], embed_dim=d["embed_dim"], vocab_size=d["vocab_size"],
+                                atten_dim=d["atten_dim"], enc_dim=d["enc_dim"], max_batch=B, max_regions=36, max_rows=3, max_seq=20)
+    dec.prepare(torch.from_numpy(synth.make_region_feats(B, 36, d["enc_dim"], 5)).cuda())
+    tok0, score0, _ = (t.clone() for t in dec.beam_search(3, 20))
+    seq0, lp0 = (t.clone() for t in dec.sample(capdec.SAMPLE_MULTINOMIAL, 3, 9, 20))
+    for _ in range(reps):
+        tok, score, _ = dec.beam_search(3, 20)
+        assert torch.equal(tok, tok0) and torch.equal(score, score0)
+    for _ in range(reps // 4):
+        seq, lp = dec.sample(capdec.SAMPLE_MULTINOMIAL, 3, 9, 20)
+        assert torch.equal(seq, seq0) and torch.equal(lp, lp0)
+    dec.close()
+
+
 def test_small_batch_launches_of_any_count_and_kind_follow_each_other(monkeypatch):
     """The fused small-batch launches synchronise through global counters that must be back at zero whenever a launch ends:
     an ODD number of fused launches per decode (NIC: one per step, 15 steps), graph replays back to back, and eager launches
