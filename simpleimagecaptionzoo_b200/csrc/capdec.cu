@@ -101,6 +101,11 @@ struct capdec_handle {
     float* small_slabs = nullptr;
     int* small_counters = nullptr;
     unsigned* small_bar = nullptr;  // SM_MAX_PHASES x (arrivals, departures) grid-barrier counters, zero between uses
+    // attention kernel CONCURRENT with the [language gates -> logits] launch on the small-batch path (CAPDEC_NO_OVERLAP=1: in series)
+    bool small_overlap = true;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int* att_done = nullptr;  // images whose context rows are written, cumulative over a decode
     bool small_hint = true;      // CAPDEC_SMALL_HINT=0: no L2 eviction-priority hints on the small-batch kernel's weight loads
     bool chain = false;          // CAPDEC_CHAIN=1: top-down gates and dec_att in ONE launch of the chained pair kernel (measured slower)
     int* chain_sync = nullptr;   // [2][row blocks] ready / passed counters of the chained pair kernel (zero between launches)
@@ -367,6 +372,8 @@ struct SmallDesc {
     int w_lo;
     int M, N, Kdim;
     EpiParams e;
+    const int* wait_ctr = nullptr;  // see SmallPhase::wait_ctr
+    int wait_target = 0, wait_kb = 0;
 };
 
 bool small_ok(const capdec_handle* h, int M) { return h->small_slabs != nullptr && M <= h->small_rows; }
@@ -392,7 +399,7 @@ int small_ksplit(int tiles, int total_kb, int num_sms) {
 }
 
 template <int N_ACT>
-int launch_small_t(capdec_handle* h, SmallParams& p, const SmallDesc* d, int n, cudaStream_t st) {
+int launch_small_t(capdec_handle* h, SmallParams& p, const SmallDesc* d, int n, cudaStream_t st, int sms) {
     using C = SmallCfg<N_ACT>;
     auto kern = smallm_kernel<N_ACT>;
     CK(h, smem_attr(reinterpret_cast<const void*>(kern), C::SMEM_BYTES));
@@ -403,14 +410,15 @@ int launch_small_t(capdec_handle* h, SmallParams& p, const SmallDesc* d, int n, 
         CKS(h, make_map(h, &P.map_x, d[q].x->base, d[q].x->rows, d[q].x->ld, 0, N_ACT));
         if (P.tiles * P.ksplit > max_items) max_items = P.tiles * P.ksplit;
     }
-    const int grid = max_items < h->num_sms ? max_items : h->num_sms;
-    CK(h, launch_pdl(h, kern, dim3(n > 1 ? h->num_sms : grid), dim3(SM_THREADS), C::SMEM_BYTES, st, p));
+    const int grid = max_items < sms ? max_items : sms;
+    CK(h, launch_pdl(h, kern, dim3(n > 1 ? sms : grid), dim3(SM_THREADS), C::SMEM_BYTES, st, p));
     return CAPDEC_OK;
 }
 
 // One launch for up to SM_MAX_PHASES dependent GEMMs on the same <= small_rows activation rows.
-int launch_small(capdec_handle* h, const SmallDesc* d, int n, cudaStream_t st) {
+int launch_small(capdec_handle* h, const SmallDesc* d, int n, cudaStream_t st, int grid_limit = 0) {
     if (n < 1 || n > SM_MAX_PHASES) return fail(h, CAPDEC_ERR_INVALID, "small-batch launch: bad phase count");
+    const int sms = (grid_limit > 0 && grid_limit < h->num_sms) ? grid_limit : h->num_sms;  // SMs this launch may count on
     SmallParams p{};
     p.n_phases = n;
     p.slabs = h->small_slabs;
@@ -428,8 +436,9 @@ int launch_small(capdec_handle* h, const SmallDesc* d, int n, cudaStream_t st) {
         P.passes = h->split ? 3 : 1;
         P.w_lo_off = D.w_lo, P.x_lo_off = D.x_lo;
         P.tiles = (D.N + SM_TILE_N - 1) / SM_TILE_N;
-        P.ksplit = small_ksplit(P.tiles, P.k_blocks * P.passes, h->num_sms);
+        P.ksplit = small_ksplit(P.tiles, P.k_blocks * P.passes, sms);
         P.epi = D.epi, P.ktop = D.ktop;
+        P.wait_ctr = D.wait_ctr, P.wait_target = D.wait_target, P.wait_kb = D.wait_kb;
         // the step's weights (72 MB) cycle through an L2 that keeps ~60 MB of them: the vocabulary matrix is streamed
         // evict-first so that the gate matrices (evict-last) survive from one step to the next
         P.w_hint = h->small_hint ? ((D.epi == EPI_TOPK || D.epi == EPI_SAMPLE) ? 1 : 2) : 0;
@@ -443,9 +452,9 @@ int launch_small(capdec_handle* h, const SmallDesc* d, int n, cudaStream_t st) {
                   : epi0 == EPI_GLU ? CAPDEC_CAT_GEMM_GLU : CAPDEC_CAT_GEMM_LOGITS;
     prof_begin(h, cat, flops, st);
     int status;
-    if (max_m <= 16) status = launch_small_t<16>(h, p, d, n, st);
-    else if (max_m <= 64) status = launch_small_t<64>(h, p, d, n, st);
-    else status = launch_small_t<128>(h, p, d, n, st);
+    if (max_m <= 16) status = launch_small_t<16>(h, p, d, n, st, sms);
+    else if (max_m <= 64) status = launch_small_t<64>(h, p, d, n, st, sms);
+    else status = launch_small_t<128>(h, p, d, n, st, sms);
     prof_end(h, st);
     CKS(h, status);
     CK(h, cudaGetLastError());
@@ -912,6 +921,7 @@ struct StepCtx {
     int forced_ld = 0;
     float* states = nullptr;  // capdec_score_states: this step's slice of the [M, T, H] predict-input export (row stride states_ld) or null
     size_t states_ld = 0;
+    int* att_done = nullptr;  // small-batch overlap: counter the attention kernel adds its finished images to, or null
     float* alphas = nullptr;  // where this step's attention maps go ([row * alpha_stride + region]) or null
     size_t alpha_stride = 0;
 };
@@ -962,8 +972,8 @@ int launch_chain(capdec_handle* h, const SmallDesc& d1, const SmallDesc& d2, cud
 
 // Run dependent GEMMs on the same activation rows: ONE persistent launch with grid barriers between them on the
 // small-batch path (smallm.cuh), one launch each otherwise (or while per-launch timing is on).
-int run_gemms(capdec_handle* h, const SmallDesc* d, int n, int M, cudaStream_t st) {
-    if (n > 1 && small_ok(h, M) && h->small_fuse && !h->prof) return launch_small(h, d, n, st);
+int run_gemms(capdec_handle* h, const SmallDesc* d, int n, int M, cudaStream_t st, int grid_limit = 0) {
+    if (n > 1 && small_ok(h, M) && h->small_fuse && !h->prof) return launch_small(h, d, n, st, grid_limit);
     if (n == 2 && !small_ok(h, M) && h->chain && h->pair_gemm && !h->prof && d[0].epi == EPI_LSTM && d[1].epi == EPI_STORE &&
         d[0].M == d[1].M && (d[0].M + 2 * BLOCK_M - 1) / (2 * BLOCK_M) <= h->chain_blocks)
         return launch_chain(h, d[0], d[1], st);
@@ -1018,7 +1028,7 @@ int launch_butd_att_mma_t(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
     prof_begin(h, CAPDEC_CAT_ATTENTION, 0.0, st);
     CK(h, launch_pdl(h, kern, dim3(grid), dim3(C::THREADS), smem, st, h->enc16.p, h->enc16.ld, h->feats16.p, h->feats16.ld,
                      static_cast<size_t>(h->B) * h->R, h->dec_ctx, h->w_aff, h->b_aff, h->B, h->R, h->A, h->D, c.K, h->XB.p, h->XB.ld,
-                     c.alphas, c.alpha_stride));
+                     c.alphas, c.alpha_stride, c.att_done));
     prof_end(h, st);
     CK(h, cudaGetLastError());
     h->launches++;
@@ -1127,10 +1137,26 @@ int step_butd(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
         g[1] = SmallDesc{EPI_STORE, 1, &x_da, h->XB.lo, &w_da, h->W_aux2.lo, c.M, A, H, e};
     }
     CKS(h, run_gemms(h, g, 2, c.M, st));
-    if (c.K <= 1) CKS(h, launch_butd_att<1>(h, c, st));
-    else if (c.K <= 3) CKS(h, launch_butd_att<3>(h, c, st));
-    else if (c.K <= 5) CKS(h, launch_butd_att<5>(h, c, st));
-    else CKS(h, launch_butd_att<8>(h, c, st));
+    // Small-batch path: the attention kernel runs on a side stream CONCURRENTLY with the [language gates -> logits] launch.
+    // The language LSTM's K range is [ctx | h1 | h2]: its weight tiles and the h1 / h2 splits do not depend on the attention,
+    // so that launch (shrunk by the SMs the attention's one-CTA-per-image grid may occupy) starts right away and only the
+    // activation loads of its ctx k-blocks wait for the attention's counter.
+    const bool overlap = h->small_overlap && h->side && small_ok(h, c.M) && h->small_fuse && !h->prof && !h->split && !c.alphas &&
+                         !h->no_stream_attention && h->att_variant == 0 && h->A <= 1024 && h->D <= 2048 && h->A % 16 == 0 && h->D % 32 == 0 &&
+                         h->num_sms - h->B >= 4 * ((4 * h->H + SM_TILE_N - 1) / SM_TILE_N);  // the shrunk launch still holds the gate GEMM's 4-way split in one round (B <= 20)
+    StepCtx ca = c;
+    cudaStream_t att_st = st;
+    if (overlap) {
+        ca.att_done = h->att_done;
+        att_st = h->side;
+        CK(h, cudaEventRecord(h->ev_fork, st));
+        CK(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    }
+    if (c.K <= 1) CKS(h, launch_butd_att<1>(h, ca, att_st));
+    else if (c.K <= 3) CKS(h, launch_butd_att<3>(h, ca, att_st));
+    else if (c.K <= 5) CKS(h, launch_butd_att<5>(h, ca, att_st));
+    else CKS(h, launch_butd_att<8>(h, ca, att_st));
+    if (overlap) CK(h, cudaEventRecord(h->ev_join, h->side));
     {  // language LSTM (BUTD_Model.py:268)
         CKS(h, map_a(h, &x_lm, h->XB));
         CKS(h, map_b(h, &w_lm, h->W_l2));
@@ -1144,11 +1170,18 @@ int step_butd(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
         e.ld16 = h->Hb2.ld;
         e.lo16 = h->Hb2.lo;
         g[0] = SmallDesc{EPI_LSTM, 1, &x_lm, h->XB.lo, &w_lm, h->W_l2.lo, c.M, 4 * H, D + H + H, e};
+        if (overlap) {  // the ctx columns (k-blocks below D / 64) arrive from the concurrent attention kernel
+            g[0].wait_ctr = h->att_done;
+            g[0].wait_target = h->B * c.t;  // cumulative over the decode: reset_state zeroes the counter
+            g[0].wait_kb = D / BLOCK_K;
+        }
     }
     CKS(h, map_a(h, &x_pr, h->Hb2));
     CKS(h, map_b(h, &w_pr, h->W_pred));
     g[1] = SmallDesc{c.logits_epi, c.ktop, &x_pr, h->Hb2.lo, &w_pr, h->W_pred.lo, c.M, h->V, H, logits_epi(h, c)};
-    return run_gemms(h, g, 2, c.M, st);
+    CKS(h, run_gemms(h, g, 2, c.M, st, overlap ? h->num_sms - h->B : 0));
+    if (overlap) CK(h, cudaStreamWaitEvent(st, h->ev_join, 0));  // the side stream joins: later work is ordered after the attention too
+    return CAPDEC_OK;
 }
 
 AdvOp op_copy(const Act16& src, int src_col, const Act16& dst, int dst_col, int n) {
@@ -1323,6 +1356,7 @@ int reset_state(capdec_handle* h, int M, cudaStream_t st) {
     if (h->XB.p) CK(h, cudaMemsetAsync(h->XB.p, 0, static_cast<size_t>(M) * h->XB.ld * sizeof(__half), st));
     CK(h, cudaMemsetAsync(h->c1[0], 0, static_cast<size_t>(M) * h->H * sizeof(float), st));
     if (h->c2[0]) CK(h, cudaMemsetAsync(h->c2[0], 0, static_cast<size_t>(M) * h->H * sizeof(float), st));
+    if (h->att_done) CK(h, cudaMemsetAsync(h->att_done, 0, sizeof(int), st));
     return CAPDEC_OK;
 }
 
@@ -1481,6 +1515,9 @@ void capdec_destroy(capdec_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->side) cudaStreamDestroy(h->side);
     for (void* p : h->allocs) cudaFree(p);
     for (auto& kv : h->raw) cudaFree(kv.second.d);
     delete h;
@@ -1556,6 +1593,14 @@ static int create_impl(capdec_handle* h) {
     CKS(h, dalloc(h, &h->out_lengths, h->Bmax));
     CKS(h, dalloc(h, &h->seed_dev, 1));
     CKS(h, alloc_small(h));
+    if (h->small_slabs && c.arch == CAPDEC_ARCH_BUTD) {
+        const char* no = getenv("CAPDEC_NO_OVERLAP");
+        h->small_overlap = !(no && no[0] == '1');
+        CKS(h, dalloc(h, &h->att_done, 1));
+        CK(h, cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+        CK(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CK(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
     {
         const char* nc = getenv("CAPDEC_CHAIN");
         h->chain = nc && nc[0] == '1';

@@ -689,7 +689,7 @@ __global__ void __launch_bounds__(288, CTAS)
 butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __half* __restrict__ feats16, int ld_feats,
                           size_t total_rows, const float* __restrict__ dec_ctx, const float* __restrict__ w_aff, float b_aff, int B,
                           int R, int A, int D, int K, __half* __restrict__ ctx16, int ld16, float* __restrict__ alphas_out,
-                          size_t alpha_stride) {
+                          size_t alpha_stride, int* __restrict__ done_ctr) {
     constexpr int STAGES = AttMmaCfg<KR, CTAS>::STAGES;
     const AttMmaShape sh = att_mma_shape(R, ld_enc, ld_feats);
     extern __shared__ __align__(128) uint8_t att_smem[];
@@ -915,6 +915,13 @@ butd_attention_mma_kernel(const __half* __restrict__ enc16, int ld_enc, const __
             }
         }
         named_bar_sync(1, 256);  // s_dec16 / s_e / s_alpha are rewritten by the next image
+    }
+    // Small-batch path: a GEMM kernel that runs CONCURRENTLY with this one (smallm.cuh) waits for the context rows through
+    // this counter -- images finished, cumulative over the decode.  The 256 consumers' stores happen-before the barrier above.
+    if (done_ctr && tid == 0) {
+        int n = 0;
+        for (int img = blockIdx.x; img < B; img += gridDim.x) ++n;
+        if (n) asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(done_ctr), "r"(n) : "memory");
     }
 }
 

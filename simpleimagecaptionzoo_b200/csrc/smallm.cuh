@@ -42,6 +42,9 @@ struct SmallPhase {
     int tiles, ksplit;
     int epi, ktop;
     int w_hint;         // L2 priority of the weight lines: 0 = default, 1 = evict-first, 2 = evict-last
+    const int* wait_ctr;  // non-null: activation columns below wait_kb k-blocks are written by a kernel running CONCURRENTLY (the
+    int wait_target;      //   attention); their loads wait until *wait_ctr >= wait_target, the weight tiles are requested before
+    int wait_kb;
     EpiParams e;
 };
 
@@ -536,10 +539,54 @@ __global__ void __launch_bounds__(SM_THREADS, 1) smallm_kernel(const __grid_cons
             // that precedes the phase (weights do not depend on the previous phase); only the activation tiles follow here.
             if (lane == 0) {
                 const uint64_t pol_first = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
+                // K order of an item.  Normally the contiguous k-blocks [kk0, kk1) of its split.  When the activation columns below
+                // wait_kb k-blocks come from a kernel running concurrently (wait_ctr), every split takes its share of the
+                // INDEPENDENT k-blocks first and its share of the dependent ones last: all CTAs stream weights and multiply while the
+                // other kernel runs, request the dependent weight tiles ahead, and after the counter passes only those k-blocks'
+                // activation tiles are missing.  (The MMA warp just consumes n_kb stages per item: the order is the producer's.)
+                const bool mixed = P.wait_ctr != nullptr && P.passes == 1 && P.wait_kb % P.ksplit == 0 && (total_kb - P.wait_kb) % P.ksplit == 0;
                 for (int item = blockIdx.x; item < items; item += gridDim.x) {
                     const int tile = item / P.ksplit, split = item - tile * P.ksplit;
                     const int kk0 = (split * total_kb) / P.ksplit, kk1 = ((split + 1) * total_kb) / P.ksplit;
-                    for (int kk = kk0; kk < kk1; ++kk) {
+                    int n_ind = kk1 - kk0, ind0 = kk0, n_dep = 0, dep0 = 0;
+                    if (mixed) {
+                        n_dep = P.wait_kb / P.ksplit, dep0 = split * n_dep;
+                        n_ind = (total_kb - P.wait_kb) / P.ksplit, ind0 = P.wait_kb + split * n_ind;
+                    } else if (P.wait_ctr != nullptr && kk0 < P.wait_kb) {
+                        n_dep = n_ind, dep0 = ind0, n_ind = 0;  // contiguous split that touches the dependent columns: all of it waits
+                    }
+                    const int n_kb = n_ind + n_dep;
+                    for (int i = 0; i < n_kb; ++i) {
+                        const int kk = i < n_ind ? ind0 + i : dep0 + (i - n_ind);
+                        if (i == n_ind && n_dep > 0) {
+                            // entering the dependent k-blocks: request their weight tiles (as many as the ring holds), THEN wait
+                            // for the counter; the loop body below adds the activation tiles
+                            if (pre == 0) {
+                                pre_stage = stage;
+                                for (int u = i; u < n_kb && pre < STAGES; ++u, ++pre) {
+                                    const int ku = dep0 + (u - n_ind);
+                                    const int pass_u = ku / P.k_blocks;
+                                    const int kw = (ku - pass_u * P.k_blocks) * BLOCK_K + (pass_u == 1 ? P.w_lo_off : 0);
+                                    mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                                    mbar_arrive_expect_tx(full_bar + 8 * stage, Cfg::STAGE_BYTES);
+                                    if (P.w_hint == 0) tma_load_2d(smem_base + stage * Cfg::STAGE_BYTES, &P.map_w, full_bar + 8 * stage, kw, tile * SM_TILE_N);
+                                    else tma_load_2d_hint(smem_base + stage * Cfg::STAGE_BYTES, &P.map_w, full_bar + 8 * stage, kw, tile * SM_TILE_N,
+                                                          P.w_hint == 1 ? pol_first : pol_last);
+                                    if (++stage == STAGES) stage = 0, phase ^= 1;
+                                }
+                            }
+                            const long long t0 = clock64();
+                            while (true) {
+                                int v;
+                                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(P.wait_ctr) : "memory");
+                                if (v >= P.wait_target) break;
+                                if (clock64() - t0 > 4000000000LL) {
+                                    printf("capdec: wait for the concurrent attention kernel timed out (block %d: %d of %d)\n", blockIdx.x, v, P.wait_target);
+                                    __trap();
+                                }
+                            }
+                            fence_proxy_async_all();  // its generic-proxy stores are ordered before this thread's TMA reads
+                        }
                         const int pass = kk / P.k_blocks;
                         const int kb = kk - pass * P.k_blocks;
                         const int kx = kb * BLOCK_K + (pass == 2 ? P.x_lo_off : 0);  // hi*hi, hi(x)*lo(w), lo(x)*hi(w)
@@ -562,7 +609,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) smallm_kernel(const __grid_cons
                 if (q + 1 < p.n_phases) {  // request the next phase's first weight tiles now: they land during the grid barrier
                     const SmallPhase& Pn = p.ph[q + 1];
                     const int item = blockIdx.x;
-                    if (item < Pn.tiles * Pn.ksplit) {
+                    if (item < Pn.tiles * Pn.ksplit && Pn.wait_ctr == nullptr) {  // (a waiting phase orders its k-blocks itself)
                         const int n_kb = Pn.k_blocks * Pn.passes;
                         const int tile = item / Pn.ksplit, split = item - tile * Pn.ksplit;
                         const int kk0 = (split * n_kb) / Pn.ksplit, kk1 = ((split + 1) * n_kb) / Pn.ksplit;
