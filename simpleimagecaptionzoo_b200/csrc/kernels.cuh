@@ -1712,7 +1712,7 @@ __global__ void beam_init_kernel(BeamState s, AdvOps ops, int parent_is_img) {
 //   shrink the beam; survivors keep their sorted order; states follow their parent.
 template <int KTOP, int KR>
 __global__ void __launch_bounds__(128, KR <= 3 ? 12 : 8) beam_step_kernel(const float* __restrict__ part, int n_tiles, BeamState s, int t,
-                                                        AdvOps ops) {
+                                                        AdvOps ops, int* __restrict__ done_ctr) {
     griddep_launch();
     griddep_wait();  // the inputs come from earlier kernels of the stream
     constexpr int PS = topk_part_stride(KTOP);
@@ -1839,6 +1839,12 @@ __global__ void __launch_bounds__(128, KR <= 3 ? 12 : 8) beam_step_kernel(const 
         if (s.hist_parent) s.hist_parent[static_cast<size_t>(t - 1) * s.B * K + img * K + threadIdx.x] = s_parent[threadIdx.x] - img * K;
     }
     advance_image<KR>(ops, img, K, s_parent, s_tok, threadIdx.x, blockDim.x);
+    // Small-batch path: the next step's gate GEMM launch runs CONCURRENTLY with this kernel (it streams its weights meanwhile) and
+    // loads the operand rows assembled above only once every image has passed here -- images done, cumulative over the decode.
+    if (done_ctr) {
+        __syncthreads();
+        if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(done_ctr) : "memory");
+    }
 }
 
 // Result selection (BUTD_Model.py:306-315): the best COMPLETED hypothesis if any, else live slot 0 (slots stay

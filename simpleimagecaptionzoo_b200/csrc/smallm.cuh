@@ -185,8 +185,8 @@ __device__ __forceinline__ void small_epi_lstm(const SmallPhase& P, const float*
         for (int u = 0; u < SM_U; ++u) {
             const int m = row0 + lb + 4 * u;
             const bool ok = lb + 4 * u < nrows;
-            gidx[u] = (e.gather && ok) ? __ldg(e.gather_idx + m) : 0;
-            prow[u] = (e.parent && ok) ? __ldg(e.parent + m) : m;
+            gidx[u] = (e.gather && ok) ? __ldcg(e.gather_idx + m) : 0;  // (L2 loads: a phase that waited for the bookkeeping kernel
+            prow[u] = (e.parent && ok) ? __ldcg(e.parent + m) : m;      //  running beside it reads what that kernel just wrote)
         }
         float4 ad[SM_U], g[SM_U];
         float cp[SM_U];
@@ -667,7 +667,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) smallm_kernel(const __grid_cons
                 const int split = item - tile * P.ksplit;
                 const int row0 = split * rpc;
                 const int nrows = P.M - row0 < rpc ? (P.M - row0 > 0 ? P.M - row0 : 0) : rpc;
-                small_epi_prefetch(P, tile, row0, nrows, t);
+                if (P.wait_ctr == nullptr) small_epi_prefetch(P, tile, row0, nrows, t);  // (a waiting phase's indices are not final yet)
                 mbar_wait(tfull_bar + 8 * acc, acc_phase);
                 if (t == 0 && item == blockIdx.x && q < 2) small_stamp(p.trace, slot, 4 + 6 * q);
                 tc_fence_after();
