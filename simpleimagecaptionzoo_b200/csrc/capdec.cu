@@ -1151,7 +1151,7 @@ int step_butd(capdec_handle* h, const StepCtx& c, cudaStream_t st) {
     // so that launch (shrunk by the SMs the attention's one-CTA-per-image grid may occupy) starts right away and only the
     // activation loads of its ctx k-blocks wait for the attention's counter.
     const bool overlap = h->small_overlap && h->side && small_ok(h, c.M) && h->small_fuse && !h->prof && !h->split && !c.alphas &&
-                         !h->no_stream_attention && h->att_variant == 0 && h->A <= 1024 && h->D <= 2048 && h->A % 16 == 0 && h->D % 32 == 0 &&
+                         !h->no_stream_attention && h->att_variant != 1 && h->A <= 1024 && h->D <= 2048 && h->A % 16 == 0 && h->D % 32 == 0 &&
                          h->num_sms - h->B >= 4 * ((4 * h->H + SM_TILE_N - 1) / SM_TILE_N);  // the shrunk launch still holds the gate GEMM's 4-way split in one round (B <= 20)
     StepCtx ca = c;
     cudaStream_t att_st = st;
