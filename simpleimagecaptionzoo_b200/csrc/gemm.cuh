@@ -96,10 +96,24 @@ constexpr int SAMPLE_PART_STRIDE = 5;  // max, sumexp, best perturbed, best inde
 
 // ------------------------------------------------------------------------------------------------ math helpers
 // sigmoid / tanh from ex2.approx + fast division: absolute error ~1e-7 (fp32 noise level), ~6 instructions each.
-__device__ __forceinline__ float sigmoidf_acc(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float tanhf_acc(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
+// MUFU.EX2 / MUFU.LG2 alone.  exp2f / __expf / __log2f wrap the MUFU in a range test and two multiplies for subnormal
+// results / arguments (3 of the ~10 instructions per logit in the log-softmax epilogues); a flushed subnormal cannot change any
+// of the sums formed here (each holds a term >= 1, or is 1 + e), and the logarithms only see normal arguments.
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_ftz(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float exp_ftz(float x) { return ex2_ftz(x * LOG2E); }
+__device__ __forceinline__ float sigmoidf_acc(float x) { return __fdividef(1.0f, 1.0f + exp_ftz(-x)); }
+__device__ __forceinline__ float tanhf_acc(float x) { return 1.0f - __fdividef(2.0f, 1.0f + exp_ftz(2.0f * x)); }
 
 __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
     hi = __float2half_rn(x);
@@ -126,9 +140,19 @@ __device__ __forceinline__ float gumbel_from_bits(uint32_t x) {
     const float u = (static_cast<float>(x >> 8) + 0.5f) * 5.9604644775390625e-08f;  // 2^-24
     const float t = 1.0f - u;
     const float e_series = t * fmaf(t, fmaf(t, fmaf(t, 0.25f, 0.33333334f), 0.5f), 1.0f);  // -log(1-t), t < 2^-6: rel err < 1e-8
-    const float e_lg2 = -LN2 * __log2f(u);
+    const float e_lg2 = -LN2 * lg2_ftz(u);
     const float e = t < 0.015625f ? e_series : e_lg2;                                       // E = -log(u) ~ Exp(1)
-    return -LN2 * __log2f(e);
+    return -LN2 * lg2_ftz(e);
+}
+// gumbel_bits without fmix32's closing h ^= h >> 16 (which leaves the top 16 bits as they are): enough for a conservative
+// compare of the top bits, two instructions less per column in the sampling epilogue's filter.
+__device__ __forceinline__ uint32_t gumbel_bits_open(uint32_t row_step_hash, uint32_t v) {
+    uint32_t h = row_step_hash ^ (v * 0xC2B2AE3Du);
+    h ^= h >> 16;
+    h *= 0x85EBCA6Bu;
+    h ^= h >> 13;
+    h *= 0xC2B2AE35u;
+    return h;
 }
 __device__ __forceinline__ float gumbel_from_hash(uint32_t row_step_hash, uint32_t v) {
     return gumbel_from_bits(gumbel_bits(row_step_hash, v));
@@ -136,7 +160,7 @@ __device__ __forceinline__ float gumbel_from_hash(uint32_t row_step_hash, uint32
 // Smallest 24-bit uniform (x >> 8) whose noise can exceed tau:  g > tau  <=>  u > exp(-exp(-tau)).  Conservative by two
 // units (and by the caller's margin on tau), so that no possible winner is ever skipped; tau = -inf gives 0 (all pass).
 __device__ __forceinline__ uint32_t gumbel_pass_threshold(float tau) {
-    const float U = __expf(-__expf(-tau));
+    const float U = exp_ftz(-exp_ftz(-tau));
     const int thr = static_cast<int>(U * 16777216.0f) - 2;
     return thr > 0 ? static_cast<uint32_t>(thr) : 0u;
 }
@@ -489,8 +513,8 @@ __device__ __forceinline__ float logits_chunk_stats(float (&v)[32], int n0, int 
     const float mn2 = mn * LOG2E;
     float a4[4] = {0.f, 0.f, 0.f, 0.f};  // four independent partial sums instead of one 32-long dependent chain
 #pragma unroll
-    for (int i = 0; i < 32; ++i) a4[i & 3] += exp2f(fmaf(v[i], LOG2E, -mn2));  // exp2(-inf) = 0 for the padded columns
-    s = s * exp2f(fmaf(m, LOG2E, -mn2)) + ((a4[0] + a4[1]) + (a4[2] + a4[3]));
+    for (int i = 0; i < 32; ++i) a4[i & 3] += ex2_ftz(fmaf(v[i], LOG2E, -mn2));  // exp2(-inf) = 0 for the padded columns
+    s = s * ex2_ftz(fmaf(m, LOG2E, -mn2)) + ((a4[0] + a4[1]) + (a4[2] + a4[3]));
     m = mn;
     return cmax;
 }
@@ -602,14 +626,39 @@ struct DrawState {
                 // compare); the two logarithms are evaluated for the few columns that pass (~1e-3 of a uniform vocabulary
                 // once the running best has settled, none of a trained model's low-probability words).  Exact: the columns
                 // skipped could not have won, the others are evaluated as before and in the same order.
+                // Branch-free filter, then the few survivors.  Per column: the hash up to its last multiply and ONE compare --
+                // x = h ^ (h >> 16) keeps h's top 16 bits, so (x >> 8) >= thr needs h >= (thr << 8) & 0xFFFF0000 -- setting
+                // a bit of a 32-bit mask; no per-column branch, 32 independent chains.  (ncu on the per-column-branch form:
+                // 39 instructions per column at one issue per 5.6 cycles per warp -- with 32 rows per warp the rare "this
+                // column might win" block ran for a fifth of all columns -- and the tensor pipe 36 % busy.)  The survivors of
+                // all 32 lanes are then evaluated four at a time, in column order as before, so the draw is unchanged.
+                // Padded columns of the vocabulary's tail chunk hold -inf and cannot win.
                 const uint32_t thr = gumbel_pass_threshold(best - cmax - 1e-3f);
-#pragma unroll 8
-                for (int i = 0; i < 32; ++i) {
-                    const uint32_t x = gumbel_bits(rs, static_cast<uint32_t>(n0 + i));
-                    if ((x >> 8) >= thr && n0 + i < p.N) {
-                        const float pv = v[i] + gumbel_from_bits(x);
-                        if (pv > best) best = pv, best_i = n0 + i, best_raw = v[i];
+                uint32_t mask = 0xFFFFFFFFu;
+                if (thr != 0u) {
+                    const uint32_t thr_hi = (thr << 8) & 0xFFFF0000u;
+                    mask = 0u;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        mask |= gumbel_bits_open(rs, static_cast<uint32_t>(n0 + i)) >= thr_hi ? (1u << i) : 0u;
+                }
+                while (mask != 0u) {
+                    int ci[4];
+                    float cp[4], cv[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        ci[q] = mask != 0u ? __ffs(static_cast<int>(mask)) - 1 : -1;
+                        mask &= mask - 1u;  // 0 stays 0
                     }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int i = ci[q] < 0 ? 0 : ci[q];
+                        cv[q] = v[i];
+                        cp[q] = cv[q] + gumbel_from_bits(gumbel_bits(rs, static_cast<uint32_t>(n0 + i)));
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (ci[q] >= 0 && cp[q] > best) best = cp[q], best_i = n0 + ci[q], best_raw = cv[q];
                 }
             } else if (cmax > best) {
 #pragma unroll

@@ -294,7 +294,7 @@ __device__ __forceinline__ void small_epi_topk(const SmallPhase& P, const float*
         const float4 a = *reinterpret_cast<const float4*>(row + c);
         const float x[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) s4[i] += exp2f(fmaf(x[i], LOG2E, -mx2));  // exp2(-inf) = 0 for the padded columns
+        for (int i = 0; i < 4; ++i) s4[i] += ex2_ftz(fmaf(x[i], LOG2E, -mx2));  // exp2(-inf) = 0 for the padded columns
         if (fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])) > tv[KTOP - 1]) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -369,7 +369,7 @@ __device__ __forceinline__ void small_epi_sample(const SmallPhase& P, const floa
         const float4 a = *reinterpret_cast<const float4*>(row + c);
         const float x[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) s4[i] += exp2f(fmaf(x[i], LOG2E, -mx2));
+        for (int i = 0; i < 4; ++i) s4[i] += ex2_ftz(fmaf(x[i], LOG2E, -mx2));
         if (e.forced) {
             const int f = forced - (n_base + c);
             if (f >= 0 && f < 4) bv = 3.0e38f, bi = forced, braw = f == 0 ? x[0] : (f == 1 ? x[1] : (f == 2 ? x[2] : x[3]));
