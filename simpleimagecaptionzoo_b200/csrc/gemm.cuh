@@ -519,6 +519,21 @@ __device__ __forceinline__ float logits_chunk_stats(float (&v)[32], int n0, int 
     return cmax;
 }
 
+// v[i] for a run-time i out of registers: 31 selects.  (Indexing the array instead puts it into local memory -- 128 bytes per
+// thread and chunk through the L1 / shared-memory arrays that the tensor core is reading its operands from: measured, the K = 1024
+// logit GEMM fell from 1000 to 780 TFLOP/s.)
+__device__ __forceinline__ float pick32(const float (&v)[32], int i) {
+    float a[16], b[8], c[4];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = (i & 16) ? v[16 + j] : v[j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = (i & 8) ? a[8 + j] : a[j];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[j] = (i & 4) ? b[4 + j] : b[j];
+    const float d0 = (i & 2) ? c[2] : c[0], d1 = (i & 2) ? c[3] : c[1];
+    return (i & 1) ? d1 : d0;
+}
+
 // Running per-row state of the fused log-softmax / top-k epilogue.  It is carried in registers across all the
 // vocabulary tiles one CTA processes for a row block (a "run"), so the top-k warm-up is paid once per run and a
 // row produces only runs * EPI_SPLIT partial records: (max, sum of exp(x - max), KTOP largest logits with their
@@ -532,6 +547,17 @@ struct TopkState {
         m = -INFINITY, s = 0.f;
 #pragma unroll
         for (int q = 0; q < KTOP; ++q) tv[q] = -INFINITY, ti[q] = 0x7FFFFFFF;
+    }
+    __device__ __forceinline__ void insert(float x, int idx) {  // x > tv[KTOP - 1]; ties keep the lower index first
+        tv[KTOP - 1] = x;
+        ti[KTOP - 1] = idx;
+#pragma unroll
+        for (int q = KTOP - 1; q > 0; --q) {
+            if (tv[q] > tv[q - 1]) {
+                const float fv = tv[q]; tv[q] = tv[q - 1]; tv[q - 1] = fv;
+                const int iv = ti[q]; ti[q] = ti[q - 1]; ti[q - 1] = iv;
+            }
+        }
     }
     __device__ __forceinline__ void tile(uint32_t taddr, int n_base, int c0, int c1, const GemmParams& p) {
         float4 nb[8];
@@ -548,18 +574,23 @@ struct TopkState {
             tmem_ld_32x32(taddr + c * 32, v);
             const float cmax = logits_chunk_stats(v, n0, p.N, p.epi.bias, cb, m, s);
             if (cmax > tv[KTOP - 1]) {
+                const float t0 = tv[KTOP - 1];
+                if (t0 == -INFINITY) {  // the run's first chunk: every column enters
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    if (v[i] > tv[KTOP - 1]) {
-                        tv[KTOP - 1] = v[i];
-                        ti[KTOP - 1] = n0 + i;
+                    for (int i = 0; i < 32; ++i)
+                        if (v[i] > tv[KTOP - 1]) insert(v[i], n0 + i);
+                } else {
+                    // Columns above the chunk-start threshold as a bit mask (branch-free, 32 independent compares), then only
+                    // those, in column order: with 32 rows per warp "some lane has a new top-k entry" holds for most chunks
+                    // of a run, and the unrolled 32-column insertion above is ~15 issue slots per column for all of them.
+                    uint32_t mask = 0u;
 #pragma unroll
-                        for (int q = KTOP - 1; q > 0; --q) {
-                            if (tv[q] > tv[q - 1]) {
-                                const float fv = tv[q]; tv[q] = tv[q - 1]; tv[q - 1] = fv;
-                                const int iv = ti[q]; ti[q] = ti[q - 1]; ti[q - 1] = iv;
-                            }
-                        }
+                    for (int i = 0; i < 32; ++i) mask |= v[i] > t0 ? (1u << i) : 0u;
+                    while (mask != 0u) {
+                        const int i = __ffs(static_cast<int>(mask)) - 1;
+                        mask &= mask - 1u;
+                        const float x = pick32(v, i);
+                        if (x > tv[KTOP - 1]) insert(x, n0 + i);
                     }
                 }
             }
@@ -653,7 +684,7 @@ struct DrawState {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const int i = ci[q] < 0 ? 0 : ci[q];
-                        cv[q] = v[i];
+                        cv[q] = pick32(v, i);
                         cp[q] = cv[q] + gumbel_from_bits(gumbel_bits(rs, static_cast<uint32_t>(n0 + i)));
                     }
 #pragma unroll
