@@ -208,6 +208,8 @@ __device__ __forceinline__ void store_h16x16(__half* dst, int lo_off, const floa
     }
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // pre[8] holds the chunk's 32 bias values when the chunk is full (requested one chunk ahead by the caller, so that their
 // L1 / L2 latency overlaps the previous chunk's arithmetic); the vocabulary's tail chunk loads its own.
 __device__ __forceinline__ void request_bias32(float4 (&pre)[8], const float* __restrict__ bias, int n0, int N) {
@@ -417,7 +419,6 @@ __device__ __forceinline__ void epi_lstm(uint32_t taddr, int row, int n_base, in
 // Issued by an epilogue thread as soon as it knows its next tile, i.e. while the tile's MMAs are still running:
 // pulls the thread's additive rows (embedding-gate row of its word: a random 16 KB row of a 155 MB table, i.e. an
 // HBM miss; per-image hoisted row; previous cell state) into L2 so that the epilogue proper sees L2 latency.
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 template <int BLOCK_N>
 __device__ __forceinline__ void epi_lstm_prefetch(int row, int n_base, int c0, int c1, const GemmParams& p) {
     const EpiParams& e = p.epi;
@@ -560,16 +561,18 @@ struct TopkState {
         }
     }
     __device__ __forceinline__ void tile(uint32_t taddr, int n_base, int c0, int c1, const GemmParams& p) {
-        float4 nb[8];
-        request_bias32(nb, p.epi.bias, n_base + c0 * 32, p.N);
+        // The chunk's 32 bias values (one 128-byte line, the same for every row) are loaded right before the accumulator, so
+        // that the two latencies overlap; the line was pulled into L1 two chunks earlier.  (Holding the next chunk's values in
+        // registers instead cost 32 register moves per chunk in this non-unrolled loop.)
+        prefetch_l1(p.epi.bias + min(n_base + c0 * 32, p.N - 1));
+        prefetch_l1(p.epi.bias + min(n_base + c0 * 32 + 32, p.N - 1));
 #pragma unroll 1
         for (int c = c0; c < c1; ++c) {
             const int n0 = n_base + c * 32;
             if (n0 >= p.N) break;
+            if (c + 2 < c1) prefetch_l1(p.epi.bias + min(n0 + 64, p.N - 1));
             float4 cb[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) cb[i] = nb[i];
-            if (c + 1 < c1) request_bias32(nb, p.epi.bias, n0 + 32, p.N);
+            request_bias32(cb, p.epi.bias, n0, p.N);
             float v[32];
             tmem_ld_32x32(taddr + c * 32, v);
             const float cmax = logits_chunk_stats(v, n0, p.N, p.epi.bias, cb, m, s);
@@ -583,9 +586,14 @@ struct TopkState {
                     // Columns above the chunk-start threshold as a bit mask (branch-free, 32 independent compares), then only
                     // those, in column order: with 32 rows per warp "some lane has a new top-k entry" holds for most chunks
                     // of a run, and the unrolled 32-column insertion above is ~15 issue slots per column for all of them.
-                    uint32_t mask = 0u;
+                    // v > t0  <=>  the sign of t0 - v (x - x is +0), shifted into the mask from column 31 down, two chains
+                    uint32_t mhi = 0u, mlo = 0u;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) mask |= v[i] > t0 ? (1u << i) : 0u;
+                    for (int i = 15; i >= 0; --i) {
+                        mhi = __funnelshift_l(__float_as_uint(t0 - v[16 + i]), mhi, 1);
+                        mlo = __funnelshift_l(__float_as_uint(t0 - v[i]), mlo, 1);
+                    }
+                    uint32_t mask = (mhi << 16) | mlo;
                     while (mask != 0u) {
                         const int i = __ffs(static_cast<int>(mask)) - 1;
                         mask &= mask - 1u;
@@ -631,16 +639,18 @@ struct DrawState {
         forced = (p.epi.forced && row < p.M) ? __ldg(p.epi.forced + static_cast<size_t>(row) * p.epi.forced_ld + p.epi.step) : -1;
     }
     __device__ __forceinline__ void tile(uint32_t taddr, int n_base, int c0, int c1, const GemmParams& p) {
-        float4 nb[8];
-        request_bias32(nb, p.epi.bias, n_base + c0 * 32, p.N);
+        // The chunk's 32 bias values (one 128-byte line, the same for every row) are loaded right before the accumulator, so
+        // that the two latencies overlap; the line was pulled into L1 two chunks earlier.  (Holding the next chunk's values in
+        // registers instead cost 32 register moves per chunk in this non-unrolled loop.)
+        prefetch_l1(p.epi.bias + min(n_base + c0 * 32, p.N - 1));
+        prefetch_l1(p.epi.bias + min(n_base + c0 * 32 + 32, p.N - 1));
 #pragma unroll 1
         for (int c = c0; c < c1; ++c) {
             const int n0 = n_base + c * 32;
             if (n0 >= p.N) break;
+            if (c + 2 < c1) prefetch_l1(p.epi.bias + min(n0 + 64, p.N - 1));
             float4 cb[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) cb[i] = nb[i];
-            if (c + 1 < c1) request_bias32(nb, p.epi.bias, n0 + 32, p.N);
+            request_bias32(cb, p.epi.bias, n0, p.N);
             float v[32];
             tmem_ld_32x32(taddr + c * 32, v);
             const float cmax = logits_chunk_stats(v, n0, p.N, p.epi.bias, cb, m, s);

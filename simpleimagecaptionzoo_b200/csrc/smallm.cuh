@@ -443,7 +443,6 @@ __device__ __forceinline__ void small_stamp(unsigned long long* trace, int slot,
     }
 }
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // Issued by an epilogue thread BEFORE it waits for its tile's accumulator: pulls what its first batch of rows will read
 // besides the partial sums -- bias / hoisted per-image row, the gathered embedding-gate row (a random row of a 155 MB
