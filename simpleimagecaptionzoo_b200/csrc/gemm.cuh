@@ -672,34 +672,39 @@ struct DrawState {
                 // a bit of a 32-bit mask; no per-column branch, 32 independent chains.  (ncu on the per-column-branch form:
                 // 39 instructions per column at one issue per 5.6 cycles per warp -- with 32 rows per warp the rare "this
                 // column might win" block ran for a fifth of all columns -- and the tensor pipe 36 % busy.)  The survivors of
-                // all 32 lanes are then evaluated four at a time, in column order as before, so the draw is unchanged.
+                // all 32 lanes are then evaluated two at a time, in column order as before, so the draw is unchanged.
                 // Padded columns of the vocabulary's tail chunk hold -inf and cannot win.
                 const uint32_t thr = gumbel_pass_threshold(best - cmax - 1e-3f);
-                uint32_t mask = 0xFFFFFFFFu;
-                if (thr != 0u) {
+                if (thr == 0u) {  // nothing to compare against yet (the run's first chunk): every column, 32 independent chains
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float pv = v[i] + gumbel_from_bits(gumbel_bits(rs, static_cast<uint32_t>(n0 + i)));
+                        if (pv > best) best = pv, best_i = n0 + i, best_raw = v[i];
+                    }
+                } else {
                     const uint32_t thr_hi = (thr << 8) & 0xFFFF0000u;
-                    mask = 0u;
+                    uint32_t mask = 0u;
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
                         mask |= gumbel_bits_open(rs, static_cast<uint32_t>(n0 + i)) >= thr_hi ? (1u << i) : 0u;
-                }
-                while (mask != 0u) {
-                    int ci[4];
-                    float cp[4], cv[4];
+                    while (mask != 0u) {  // two survivors per pass (their logits come out of registers by 31 selects each)
+                        int ci[2];
+                        float cp[2], cv[2];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        ci[q] = mask != 0u ? __ffs(static_cast<int>(mask)) - 1 : -1;
-                        mask &= mask - 1u;  // 0 stays 0
+                        for (int q = 0; q < 2; ++q) {
+                            ci[q] = mask != 0u ? __ffs(static_cast<int>(mask)) - 1 : -1;
+                            mask &= mask - 1u;  // 0 stays 0
+                        }
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const int i = ci[q] < 0 ? 0 : ci[q];
+                            cv[q] = pick32(v, i);
+                            cp[q] = cv[q] + gumbel_from_bits(gumbel_bits(rs, static_cast<uint32_t>(n0 + i)));
+                        }
+#pragma unroll
+                        for (int q = 0; q < 2; ++q)
+                            if (ci[q] >= 0 && cp[q] > best) best = cp[q], best_i = n0 + ci[q], best_raw = cv[q];
                     }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int i = ci[q] < 0 ? 0 : ci[q];
-                        cv[q] = pick32(v, i);
-                        cp[q] = cv[q] + gumbel_from_bits(gumbel_bits(rs, static_cast<uint32_t>(n0 + i)));
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (ci[q] >= 0 && cp[q] > best) best = cp[q], best_i = n0 + ci[q], best_raw = cv[q];
                 }
             } else if (cmax > best) {
 #pragma unroll
