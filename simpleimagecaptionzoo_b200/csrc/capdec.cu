@@ -91,6 +91,7 @@ struct capdec_handle {
     const float* mask = nullptr;
     int64_t launches = 0;
     bool pair_gemm = true;             // CAPDEC_GEMM_1CTA=1 selects the single-CTA GEMM kernel instead of the CTA-pair one
+    int logit_ew = LOGIT_EPI_WARPS;    // CAPDEC_LOGIT_EW=8: the sampling epilogue on 8 warps like the other epilogues (A/B)
     bool mgroup_split = true;          // CAPDEC_MGROUP_SPLIT=0: one row block per pair in the large-M tile walk (round 1's walk)
     bool no_stream_attention = false;  // CAPDEC_NO_STREAM_ATTENTION=1: use the non-persistent attention kernel
     int att_variant = 0;               // CAPDEC_ATT_VARIANT=1: FFMA streaming kernel instead of the MMA-fragment kernel
@@ -327,9 +328,9 @@ int launch_gemm_t(capdec_handle* h, const CUtensorMap& ma, const CUtensorMap& mb
 }
 
 // D[M,N] = A[M,Kdim] * B[N,Kdim]^T with the chosen epilogue.
-template <int EPI, int KTOP>
+template <int EPI, int KTOP, int EW = EPI_WARPS>
 int launch_gemm2_t(capdec_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
-    auto kern = gemm2_kernel<EPI, KTOP>;
+    auto kern = gemm2_kernel<EPI, KTOP, EW>;
     CK(h, smem_attr(reinterpret_cast<const void*>(kern), GemmCfg2::SMEM_BYTES));
     const int items = p.runs > 0 ? p.num_m_blocks * p.runs : p.num_m_blocks * p.num_n_blocks;
     const int pairs = items < h->num_sms / 2 ? items : h->num_sms / 2;
@@ -347,7 +348,7 @@ int launch_gemm2_t(capdec_handle* h, const CUtensorMap& ma, const CUtensorMap& m
     const int cat = EPI == EPI_LSTM ? CAPDEC_CAT_GEMM_LSTM : EPI == EPI_STORE ? CAPDEC_CAT_GEMM_STORE
                   : EPI == EPI_GLU ? CAPDEC_CAT_GEMM_GLU : CAPDEC_CAT_GEMM_LOGITS;
     prof_begin(h, cat, 2.0 * p.M * p.N * (static_cast<double>(p.k_blocks) * BLOCK_K), st);
-    CK(h, launch_pdl(h, kern, dim3(2 * pairs), dim3(GEMM_THREADS), GemmCfg2::SMEM_BYTES, st, ma, mb, pg));
+    CK(h, launch_pdl(h, kern, dim3(2 * pairs), dim3(64 + 32 * EW), GemmCfg2::SMEM_BYTES, st, ma, mb, pg));
     prof_end(h, st);
     CK(h, cudaGetLastError());
     h->launches++;
@@ -465,11 +466,10 @@ int launch_small(capdec_handle* h, const SmallDesc* d, int n, cudaStream_t st, i
 }
 
 // number of partial records per row the logit GEMM writes for M rows (what the bookkeeping kernels merge)
-int logit_slots(const capdec_handle* h, int M, int N);
-
-int logit_slots(const capdec_handle* h, int M, int N) {
+// (the pair kernel's sampling epilogue runs on logit_ew warps, its top-k epilogue on EPI_WARPS: see dispatch)
+int logit_slots(const capdec_handle* h, int M, int N, int epi) {
     if (small_ok(h, M)) return (N + SM_TILE_N - 1) / SM_TILE_N;
-    return logit_runs(h, M, N) * EPI_SPLIT;
+    return logit_runs(h, M, N) * (h->pair_gemm && epi == EPI_SAMPLE ? h->logit_ew / 4 : EPI_SPLIT);
 }
 
 int alloc_small(capdec_handle* h) {
@@ -518,7 +518,9 @@ int launch_gemm(capdec_handle* h, int epi, int ktop, const Operand& oa, int a_lo
             case EPI_STORE: return launch_gemm2_t<EPI_STORE, 1>(h, ma, mb, p, st);
             case EPI_LSTM: return launch_gemm2_t<EPI_LSTM, 1>(h, ma, mb, p, st);
             case EPI_GLU: return launch_gemm2_t<EPI_GLU, 1>(h, ma, mb, p, st);
-            case EPI_SAMPLE: return launch_gemm2_t<EPI_SAMPLE, 1>(h, ma, mb, p, st);
+            case EPI_SAMPLE:
+                if (h->logit_ew == LOGIT_EPI_WARPS) return launch_gemm2_t<EPI_SAMPLE, 1, LOGIT_EPI_WARPS>(h, ma, mb, p, st);
+                return launch_gemm2_t<EPI_SAMPLE, 1>(h, ma, mb, p, st);
             case EPI_TOPK:
                 if (ktop <= 4) return launch_gemm2_t<EPI_TOPK, 4>(h, ma, mb, p, st);
                 return launch_gemm2_t<EPI_TOPK, 8>(h, ma, mb, p, st);
@@ -934,7 +936,7 @@ EpiParams logits_epi(capdec_handle* h, const StepCtx& c) {
     EpiParams e{};
     e.bias = h->b_pred;
     e.part = h->part;
-    e.n_tiles = logit_slots(h, c.M, h->V);
+    e.n_tiles = logit_slots(h, c.M, h->V, c.logits_epi);
     e.seed = c.seed;
     e.seed_ptr = c.seed_ptr;
     e.step = c.t - 1;
@@ -1566,6 +1568,8 @@ static int create_impl(capdec_handle* h) {
         h->pair_gemm = !(g1 && g1[0] == '1');
         const char* mg = getenv("CAPDEC_MGROUP_SPLIT");
         h->mgroup_split = !(mg && mg[0] == '0');
+        const char* ew = getenv("CAPDEC_LOGIT_EW");
+        if (ew && atoi(ew) == EPI_WARPS) h->logit_ew = EPI_WARPS;
         const char* ng = getenv("CAPDEC_NO_GRAPH");
         h->use_graphs = !(ng && ng[0] == '1');
         const char* np = getenv("CAPDEC_PDL");
@@ -1574,7 +1578,7 @@ static int create_impl(capdec_handle* h) {
         h->att_variant = v ? atoi(v) : 0;
     }
     h->Mmax = h->Bmax * h->Kmax;
-    h->n_tiles_v = ((V + BN - 1) / BN) * EPI_SPLIT;  // partial slots per row: (N tile, column share)
+    h->n_tiles_v = ((V + BN - 1) / BN) * LOGIT_EPI_SPLIT_MAX;  // partial slots per row: (N tile, column share)
     const int M = h->Mmax;
 
     CKS(h, dalloc(h, &h->scale_tmp, static_cast<size_t>(V > 4 * H ? V : 4 * H)));
@@ -1976,7 +1980,7 @@ static int enqueue_beam_search(capdec_handle* h, int32_t beam, int32_t max_seq, 
     else beam_init_kernel<8><<<B, 128, 0, st>>>(s, adv_ops(h, true), nic ? 1 : 0);
     CK(h, cudaGetLastError());
     h->launches++;
-    const int n_slots = logit_slots(h, M, h->V);  // partial records per row written by the logit GEMM
+    const int n_slots = logit_slots(h, M, h->V, EPI_TOPK);  // partial records per row written by the logit GEMM
     StepCtx c{};
     c.M = M, c.K = K, c.logits_epi = EPI_TOPK, c.ktop = ktop_for(K);
     const AdvOps ops = adv_ops(h, false);
@@ -2124,7 +2128,7 @@ static int sample_impl(capdec_handle* h, int32_t mode, int32_t n_per_image, uint
     else sample_init_kernel<8><<<B, 128, 0, st>>>(s, adv_ops(h, true), nic ? 1 : 0);
     CK(h, cudaGetLastError());
     h->launches++;
-    const int n_slots = logit_slots(h, M, h->V);
+    const int n_slots = logit_slots(h, M, h->V, EPI_SAMPLE);
     StepCtx c{};
     c.M = M, c.K = n, c.logits_epi = EPI_SAMPLE, c.ktop = 1;
     c.seed = static_cast<uint32_t>(seed & 0xFFFFFFFFu);
@@ -2272,7 +2276,7 @@ int capdec_test_gemm_time(int32_t m, int32_t n, int32_t k, int32_t epi, int32_t 
             e.c_in = c0, e.c_out = c1, e.ldc = n / 4;
             e.out16 = H16.p, e.ld16 = H16.ld, e.lo16 = H16.lo;
         } else if (epi == EPI_TOPK) {
-            const int nt = logit_slots(h, m, n);
+            const int nt = logit_slots(h, m, n, EPI_TOPK);
             if ((status = dalloc(h, &part, static_cast<size_t>(m) * nt * topk_part_stride(4))) != CAPDEC_OK) break;
             e.part = part;
             e.n_tiles = nt;

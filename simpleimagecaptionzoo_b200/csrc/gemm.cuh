@@ -27,6 +27,8 @@ constexpr int UMMA_K = 16;
 constexpr int EPI_WARPS = 8;                      // 2 warps per TMEM lane quarter, each owns half of the tile's columns
 constexpr int EPI_SPLIT = EPI_WARPS / 4;
 constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int LOGIT_EPI_WARPS = 12;               // pair kernel, sampling epilogue (see gemm2_kernel)
+constexpr int LOGIT_EPI_SPLIT_MAX = LOGIT_EPI_WARPS / 4;
 
 enum EpiKind { EPI_STORE = 0, EPI_LSTM = 1, EPI_GLU = 2, EPI_TOPK = 3, EPI_SAMPLE = 4 };
 
@@ -942,10 +944,14 @@ struct GemmCfg2 {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
 };
 
-template <int EPI, int KTOP>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+// EW epilogue warps (a multiple of 4: EW / 4 warps per TMEM lane quarter share a tile's columns).  The sampling epilogue, the
+// longest per column, runs with 12 (LOGIT_EPI_WARPS: 448 threads, 128 registers): 820 -> 864 TFLOP/s in the SCST step; the
+// top-k epilogue measured the same with 8 and 12 (NIC 794 / 794, BUTD 1050 / 1028 TFLOP/s) and stays on 8.
+template <int EPI, int KTOP, int EW = EPI_WARPS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
     using Cfg = GemmCfg2;
+    constexpr int ES = EW / 4;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int BLOCK_N = Cfg::BLOCK_N;
     extern __shared__ uint8_t smem_raw[];
@@ -974,7 +980,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar + 8 * s, 1);
-            mbar_init(tempty_bar + 8 * s, 2 * EPI_WARPS);
+            mbar_init(tempty_bar + 8 * s, 2 * EW);
         }
         fence_barrier_init();
     }
@@ -1049,7 +1055,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         const int quarter = warp & 3;
         const int split = (warp - 2) >> 2;
         constexpr int CHUNKS = BLOCK_N / 32;
-        const int c0 = split * (CHUNKS / EPI_SPLIT), c1 = c0 + CHUNKS / EPI_SPLIT;
+        const int c0 = split * CHUNKS / ES, c1 = (split + 1) * CHUNKS / ES;
         int acc = 0;
         uint32_t acc_phase = 0;
         TopkState<KTOP> tk;
@@ -1068,7 +1074,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             else if constexpr (EPI == EPI_LSTM) epi_lstm<BLOCK_N>(taddr, row, n_base, c0, c1, p);
             else if constexpr (EPI == EPI_GLU) epi_glu<BLOCK_N>(taddr, row, n_base, c0, c1, p);
             else {
-                const int slot = (p.runs > 0 ? it.run : n_blk) * EPI_SPLIT + split;
+                const int slot = (p.runs > 0 ? it.run : n_blk) * ES + split;
                 if constexpr (EPI == EPI_TOPK) {
                     if (first) tk.init();
                     tk.tile(taddr, n_base, c0, c1, p);
