@@ -258,6 +258,43 @@ def test_small_batch_path_matches_large_tile_path(name, monkeypatch):
     assert grow.float().mean() >= 0.9 and torch.allclose(glogp[grow], lglogp[grow], atol=2e-4)
 
 
+@pytest.mark.parametrize("name", ["butd_full_k3", "nic_full_k3"])
+def test_sampling_epilogue_draws_do_not_depend_on_its_warp_count(name, monkeypatch):
+    """The large-tile logit GEMM's sampling epilogue runs on 12 warps (three column shares per tile and accumulator row,
+    CAPDEC_LOGIT_EW=8: two).  The noise is a function of (seed, row, step, word) only and the shares' partial records meet in
+    the bookkeeping kernel, so the drawn words are the same and the log-probs agree to fp32 summation order; likewise SCST's
+    one-pass rollouts and teacher-forced re-scoring."""
+    from simpleimagecaptionzoo_b200 import capdec
+    meta, gold = load_case(name)
+    sd, feats, mask = rebuild(meta)
+    d = meta["dims"]
+    B, n = meta["B"], 5
+    monkeypatch.setenv("CAPDEC_NO_SMALLM", "1")  # the large-tile kernels at the goldens' 96 rows
+    kw = dict(hidden_dim=d["hidden_dim"], embed_dim=d["embed_dim"], vocab_size=d["vocab_size"], atten_dim=d.get("atten_dim", 0),
+              enc_dim=d.get("enc_dim", 2048), num_heads=d.get("num_heads", 8), max_batch=B, max_regions=max(meta["R"], 1),
+              max_rows=n + 1, max_seq=meta["T"], math="f16x3")
+    ft = torch.from_numpy(feats).cuda()
+
+    def run():
+        dec = capdec.CaptionDecoder(meta["arch"], sd, **kw)
+        dec.prepare(ft, None)
+        seq, logp = dec.sample(capdec.SAMPLE_MULTINOMIAL, n, 17, meta["T"])
+        out = [seq.clone(), logp.clone()] + [t.clone() for t in dec.scst_rollout(n, 23, meta["T"])]
+        out.append(dec.score(seq, n).clone())
+        torch.cuda.synchronize()
+        dec.close()
+        return out
+
+    twelve = run()
+    monkeypatch.setenv("CAPDEC_LOGIT_EW", "8")
+    eight = run()
+    for a, b in zip(twelve, eight):
+        if a.dtype in (torch.int32, torch.int64):
+            assert torch.equal(a, b)
+        else:
+            assert torch.allclose(a, b, atol=2e-4)
+
+
 @pytest.mark.parametrize("arch,B,R,K,T", [("BUTD", 3, 1, 8, 20), ("BUTD", 1, 36, 8, 1), ("BUTD", 40, 6, 2, 5), ("NIC", 7, 0, 8, 20),
                                          ("AOA", 2, 1, 8, 3), ("AOA", 33, 12, 4, 20), ("BUTD", 300, 4, 7, 9)])
 def test_extreme_shapes_against_the_oracle(arch, B, R, K, T):

@@ -18,7 +18,9 @@ for i, name in enumerate(h):
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
-a, b = starts[which], starts[which + 1]
+per = max(1, (len(starts) - 1) // max(1, len(rr) - 2))  # the source page may list every launch more than once
+a, b = starts[which * per], starts[which * per + 1]
+print(rows[a][1][:100])
 hdr, body = rows[a + 1], rows[a + 2:b]
 S, E = hdr.index("Warp Stall Sampling (All Samples)"), hdr.index("Instructions Executed")
 tot = sum(int(r[S]) for r in body); tote = sum(int(r[E]) for r in body)
