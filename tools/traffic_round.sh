@@ -1,5 +1,7 @@
+# Per-launch DRAM traffic of the current build for the bench line, then the bench itself -- usage under gpurun:
+#   bash tools/traffic_round.sh <tag>
 set -u
-tag=r02l
+tag=${1:-r02}
 mkdir -p gpurun_out
 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/plain_${tag}.log 2>&1 || { tail -5 gpurun_out/plain_${tag}.log; exit 1; }
 ncu --set full --clock-control none --import-source on -k regex:'gemm2_kernel|attention|beam_step' -s 380 -c 6 -o gpurun_out/prof_${tag} -f \
